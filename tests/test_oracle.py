@@ -1,0 +1,118 @@
+"""CPU: the oracle (oracle/dmnerf_oracle.py) against the fixtures written by oracle/make_golden.py from
+the unmodified reference.  On the machine that generated them the match is bit-exact; elsewhere the
+host BLAS may round differently, hence the small tolerances (stage-wise, teacher-forced inputs)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import dmnerf_oracle as O
+from dmnerf_b200 import synth
+
+RTOL, ATOL = 2e-5, 2e-6
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(a.detach().numpy() if torch.is_tensor(a) else a, b, rtol=rtol, atol=atol)
+
+
+def test_embed(golden_dir):
+    g = load(golden_dir, "embed.npz")
+    x = torch.from_numpy(g["x"])
+    close(O.embed(x, 10), g["pos"])
+    close(O.embed(x / x.norm(dim=-1, keepdim=True), 4), g["dir"])
+    assert g["pos"].shape[1] == 63 and g["dir"].shape[1] == 27
+
+
+def test_mlp(golden_dir):
+    for ins_num in (13, 59):
+        g = load(golden_dir, "mlp_ins%d.npz" % ins_num)
+        w = O.to_torch(synth.make_weights(int(g["seed"]), ins_num))
+        y = O.mlp_forward(w, torch.from_numpy(g["x"]))
+        assert y.shape[1] == 4 + ins_num + 1
+        close(y, g["y"], rtol=1e-4, atol=1e-5)
+
+
+def test_composite(golden_dir):
+    g = load(golden_dir, "composite.npz")
+    rgb, w, d, ins, acc = O.composite(torch.from_numpy(g["raw"]), torch.from_numpy(g["z"]), torch.from_numpy(g["rays_d"]))
+    close(rgb, g["rgb"]); close(w, g["weights"]); close(d, g["depth"]); close(ins, g["ins"])
+    close(acc, g["weights"].sum(-1), rtol=1e-5)
+    assert float(w[0].abs().max()) == 0.0            # empty ray
+    assert float(w[1, :4].sum()) > 0.99              # (nearly) opaque at the first samples
+
+
+def test_sample_pdf(golden_dir):
+    g = load(golden_dir, "sample_pdf.npz")
+    b, w = torch.from_numpy(g["bins"]), torch.from_numpy(g["weights"])
+    close(O.sample_pdf(b, w, 128, det=True), g["det"], rtol=1e-5, atol=1e-5)
+    close(O.sample_pdf(b, w, 128, det=False, u=torch.from_numpy(g["u"])), g["rnd"], rtol=1e-5, atol=1e-5)
+
+
+def test_rays_and_z(golden_dir):
+    g = load(golden_dir, "rays.npz")
+    o, d = O.get_rays_k(480, 640, torch.from_numpy(g["K"]), torch.from_numpy(g["c2w"]))
+    close(d.reshape(-1, 3)[g["idx"]], g["rays_d"]); close(o.reshape(-1, 3)[g["idx"]], g["rays_o"])
+    close(O.z_val_sample(3, 4.0, 15.0, 64)[1], g["z"], rtol=0, atol=0)
+    close(O.z_val_sample(3, 0.0, 6.5, 64)[2], g["z_replica"], rtol=0, atol=0)
+    wl = synth.workload("dmsr_study")                # numpy twin used by bench/tests
+    close(wl["rays_d"][g["idx"]], g["rays_d"], rtol=1e-6, atol=1e-6)
+
+
+def _render_case(golden_dir, tag):
+    g = load(golden_dir, "render_%s.npz" % tag)
+    ins_num = int(g["ins_num"])
+    pc = O.to_torch(synth.make_weights(int(g["seed_coarse"]), ins_num))
+    pf = O.to_torch(synth.make_weights(int(g["seed_fine"]), ins_num))
+    ro, rd = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+    zc = O.z_val_sample(ro.shape[0], float(g["near"]), float(g["far"]), 64)
+    return g, pc, pf, ro, rd, zc
+
+
+def test_render_inference(golden_dir):
+    for tag in ("study", "room0"):
+        g, pc, pf, ro, rd, zc = _render_case(golden_dir, tag)
+        with torch.no_grad():
+            out = O.render(ro, rd, pc, pf, zc, perturb=0.0)
+        for k in ("rgb_fine", "ins_fine", "z_vals_fine", "raw_fine", "raw_coarse", "rgb_coarse", "ins_coarse",
+                  "z_vals_coarse", "depth_fine", "depth_coarse"):
+            close(out[k], g["det_" + k], rtol=2e-3, atol=2e-3)     # end-to-end: ill-conditioned
+        z = out["z_vals_fine"]
+        assert bool((z[:, 1:] >= z[:, :-1]).all())
+        assert float(out["acc_fine"].max()) <= 1.0 + 1e-5
+
+
+def test_render_train_and_grads(golden_dir):
+    g, pc, pf, ro, rd, zc = _render_case(golden_dir, "study")
+    for d in (pc, pf):
+        for v in d.values():
+            v.requires_grad_(True)
+    out = O.render(ro, rd, pc, pf, zc, perturb=1.0, t_rand=torch.from_numpy(g["t_rand"]), u=torch.from_numpy(g["u"]),
+                   is_train=True)
+    loss = O.train_loss(out, torch.from_numpy(g["target"]))
+    close(loss, g["loss"], rtol=1e-4)
+    loss.backward()
+    for nm, d in (("coarse", pc), ("fine", pf)):
+        for k, v in d.items():
+            ref = g["grad_%s_%s" % (nm, k)]
+            got = v.grad if v.grad is not None else torch.zeros_like(v)
+            if k.endswith("weight"):
+                got = got[::8, ::8]
+            scale = max(float(np.abs(ref).max()), 1e-8)
+            assert float((got - torch.from_numpy(ref)).abs().max()) <= 2e-3 * scale + 1e-9, (nm, k)
+    # detach topology: the instance terms never reach the trunk through ins_feature_linear's input
+    assert pc["mlps.0.weight"].grad is not None
+
+
+def test_fp64_twin_noise_floor(golden_dir):
+    """The fp32 oracle vs its own fp64 twin: the yard-stick for what 'parity' can mean stage-wise."""
+    g = load(golden_dir, "mlp_ins13.npz")
+    w = synth.make_weights(int(g["seed"]), 13)
+    y32 = O.mlp_forward(O.to_torch(w), torch.from_numpy(g["x"]))
+    y64 = O.mlp_forward(O.to_torch(w, torch.float64), torch.from_numpy(g["x"]).double())
+    rel = float((y32.double() - y64).norm() / y64.norm())
+    assert rel < 5e-6
