@@ -1,0 +1,260 @@
+// extern "C" boundary of libdmnerf_b200.so: context, weight binding, stage entry points and the
+// whole-pipeline render call.  See include/dmnerf_b200.h for the contract of every symbol.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "umma_api.cuh"
+
+namespace dmnerf {
+
+static thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+// Grow-only device scratch buffer.
+struct Scratch {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (ptr) DMN_CUDA(cudaFree(ptr));
+    ptr = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4;
+    DMN_CUDA(cudaMalloc(&ptr, want));
+    cap = want;
+    return 0;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+}  // namespace dmnerf
+
+using namespace dmnerf;
+
+struct dmnerf_ctx {
+  int device = 0;
+  NetParams net[2];
+  UmmaWeights packed[2];          // tensor-core operand images (umma_api.cuh)
+  Scratch ws_raw_c, ws_raw_f, ws_z_c, ws_z_f, ws_w_c, ws_w_f;
+  Scratch host_in, host_out;      // device staging for the *_host entry point
+  dmnerf_ctx() { memset(net, 0, sizeof(net)); }
+};
+
+extern "C" {
+
+DMNERF_API int dmnerf_abi_version(void) { return DMNERF_ABI_VERSION; }
+DMNERF_API const char* dmnerf_last_error(void) { return g_error.c_str(); }
+DMNERF_API int64_t dmnerf_launch_count(void) { return g_launches.load(); }
+
+DMNERF_API int dmnerf_ctx_create(int device, dmnerf_ctx** out) {
+  DMN_CHECK(out != nullptr, "ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  DMN_CUDA(cudaGetDeviceCount(&count));
+  DMN_CHECK(device >= 0 && device < count, "ctx_create: device %d not in [0,%d)", device, count);
+  DMN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DMN_CUDA(cudaGetDeviceProperties(&prop, device));
+  DMN_CHECK(prop.major == 10, "ctx_create: this library is built for sm_100a only (device is sm_%d%d)", prop.major,
+            prop.minor);
+  dmnerf_ctx* c = new dmnerf_ctx();
+  c->device = device;
+  *out = c;
+  return 0;
+}
+
+DMNERF_API int dmnerf_ctx_destroy(dmnerf_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 2; ++i) umma_weights_free(ctx->packed[i]);
+  Scratch* all[] = {&ctx->ws_raw_c, &ctx->ws_raw_f, &ctx->ws_z_c, &ctx->ws_z_f, &ctx->ws_w_c, &ctx->ws_w_f,
+                    &ctx->host_in, &ctx->host_out};
+  for (Scratch* s : all) s->release();
+  delete ctx;
+  return 0;
+}
+
+DMNERF_API int dmnerf_set_weights(dmnerf_ctx* ctx, int net, const float* const* params, int n_params, int ins_num, void* stream) {
+  DMN_CHECK(ctx != nullptr, "set_weights: ctx is NULL");
+  DMN_CHECK(net == 0 || net == 1, "set_weights: net must be 0 (coarse) or 1 (fine), got %d", net);
+  DMN_CHECK(n_params == DMNERF_N_PARAMS, "set_weights: expected %d tensors (state_dict order), got %d",
+            DMNERF_N_PARAMS, n_params);
+  DMN_CHECK(ins_num >= 1 && ins_num <= DMNERF_MAX_INS, "set_weights: ins_num=%d out of range [1,%d]", ins_num,
+            DMNERF_MAX_INS);
+  NetParams& p = ctx->net[net];
+  for (int l = 0; l < N_LAYERS; ++l) {
+    DMN_CHECK(params[2 * l] && params[2 * l + 1], "set_weights: parameter %d is NULL", 2 * l);
+    p.w[l] = params[2 * l];
+    p.b[l] = params[2 * l + 1];
+  }
+  p.ins_num = ins_num;
+  p.bound = true;
+  return umma_weights_pack(ctx->packed[net], p, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_posenc(const float* x, int64_t m, int n_freqs, float* out, void* stream) {
+  DMN_CHECK(m >= 0, "posenc: negative row count");
+  DMN_CHECK(m == 0 || (x && out), "posenc: NULL buffer");
+  return launch_posenc(x, m, n_freqs, out, (cudaStream_t)stream);
+}
+
+static int mlp_dispatch(dmnerf_ctx* ctx, int net, const float* x, const float* ro, const float* rd, const float* z,
+                        int64_t m, int s, float* out, int impl, cudaStream_t st) {
+  DMN_CHECK(ctx != nullptr, "mlp: ctx is NULL");
+  DMN_CHECK(net == 0 || net == 1, "mlp: net must be 0 or 1");
+  DMN_CHECK(m >= 0, "mlp: negative row count");
+  DMN_CHECK(impl >= DMNERF_IMPL_AUTO && impl <= DMNERF_IMPL_UMMA, "mlp: unknown impl %d", impl);
+  if (m == 0) return 0;
+  DMN_CHECK(out != nullptr, "mlp: out is NULL");
+  if (impl == DMNERF_IMPL_AUTO) impl = umma_available(ctx->packed[net]) ? DMNERF_IMPL_UMMA : DMNERF_IMPL_SIMT;
+  if (impl == DMNERF_IMPL_UMMA)
+    return launch_mlp_umma(ctx->packed[net], ctx->net[net], x, ro, rd, z, m, s, out, st);
+  return launch_mlp_simt(ctx->net[net], x, ro, rd, z, m, s, out, st);
+}
+
+DMNERF_API int dmnerf_mlp_forward(dmnerf_ctx* ctx, int net, const float* x, int64_t m, float* out, int impl, void* stream) {
+  DMN_CHECK(m <= 0 || x != nullptr, "mlp_forward: x is NULL");
+  return mlp_dispatch(ctx, net, x, nullptr, nullptr, nullptr, m, 1, out, impl, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_mlp_forward_rays(dmnerf_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* z,
+                            int64_t n, int s, float* out, int impl, void* stream) {
+  DMN_CHECK(n >= 0 && s >= 1, "mlp_forward_rays: bad sizes n=%lld s=%d", (long long)n, s);
+  DMN_CHECK(n == 0 || (rays_o && rays_d && z), "mlp_forward_rays: NULL input");
+  return mlp_dispatch(ctx, net, nullptr, rays_o, rays_d, z, n * s, s, out, impl, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_composite(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all_ins,
+                     float* rgb, float* weights, float* depth, float* ins, float* acc, void* stream) {
+  DMN_CHECK(n >= 0, "composite: negative ray count");
+  DMN_CHECK(n == 0 || (raw && z && rays_d), "composite: NULL input");
+  return launch_composite(raw, z, rays_d, n, s, c, keep_all_ins, rgb, weights, depth, ins, acc, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int n_bins, int n_samples, const float* u,
+                      float* out, void* stream) {
+  DMN_CHECK(n >= 0, "sample_pdf: negative ray count");
+  DMN_CHECK(n == 0 || (bins && weights && out), "sample_pdf: NULL buffer");
+  return launch_sample_pdf(bins, weights, n, n_bins, n_samples, u, out, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int na, int nb, float* out, void* stream) {
+  DMN_CHECK(n >= 0, "sort_concat: negative ray count");
+  DMN_CHECK(n == 0 || ((a || na == 0) && (b || nb == 0) && out), "sort_concat: NULL buffer");
+  return launch_sort_concat(a, b, n, na, nb, out, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n, int S, int NI, int flags, int impl,
+                          void* stream) {
+  DMN_CHECK(ctx && io, "render_forward: NULL ctx/io");
+  DMN_CHECK(n >= 0 && S >= 3 && NI >= 2, "render_forward: bad sizes n=%lld S=%d I=%d", (long long)n, S, NI);
+  DMN_CHECK(ctx->net[0].bound && ctx->net[1].bound, "render_forward: bind both networks with dmnerf_set_weights first");
+  DMN_CHECK(ctx->net[0].ins_num == ctx->net[1].ins_num, "render_forward: coarse/fine ins_num differ");
+  if (n == 0) return 0;
+  DMN_CHECK(io->rays_o && io->rays_d && io->z_coarse, "render_forward: rays_o / rays_d / z_coarse is NULL");
+  const bool perturb = (flags & DMNERF_FLAG_PERTURB) != 0;
+  DMN_CHECK(!perturb || (io->t_rand && io->u), "render_forward: PERTURB needs t_rand and u");
+  DMN_CHECK(io->z_row_stride == 0 || io->z_row_stride >= S, "render_forward: bad z_row_stride");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = 4 + ctx->net[0].ins_num + 1, F = S + NI;
+  const int keep = (flags & DMNERF_FLAG_KEEP_INS) ? 1 : 0;
+  DMN_CUDA(cudaSetDevice(ctx->device));
+
+  // scratch for whatever the caller does not want back
+  float* z_c = io->z_vals_coarse;
+  if (!z_c) { if (ctx->ws_z_c.reserve((size_t)n * S * 4)) return 2; z_c = (float*)ctx->ws_z_c.ptr; }
+  float* z_f = io->z_vals_fine;
+  if (!z_f) { if (ctx->ws_z_f.reserve((size_t)n * F * 4)) return 2; z_f = (float*)ctx->ws_z_f.ptr; }
+  float* w_c = io->weights_coarse;
+  if (!w_c) { if (ctx->ws_w_c.reserve((size_t)n * S * 4)) return 2; w_c = (float*)ctx->ws_w_c.ptr; }
+  float* raw_c = io->raw_coarse;
+  if (!raw_c) { if (ctx->ws_raw_c.reserve((size_t)n * S * C * 4)) return 2; raw_c = (float*)ctx->ws_raw_c.ptr; }
+  float* raw_f = io->raw_fine;
+  if (!raw_f) { if (ctx->ws_raw_f.reserve((size_t)n * F * C * 4)) return 2; raw_f = (float*)ctx->ws_raw_f.ptr; }
+
+  int rc;
+  // render.py:40-47  coarse depths (+ stratified jitter)
+  if ((rc = launch_prep_z(io->z_coarse, io->z_row_stride, perturb ? io->t_rand : nullptr, n, S, z_c, st))) return rc;
+  // render.py:49-61  points, embeddings, coarse network
+  if ((rc = mlp_dispatch(ctx, 0, nullptr, io->rays_o, io->rays_d, z_c, n * S, S, raw_c, impl, st))) return rc;
+  // render.py:63     coarse composite
+  if ((rc = launch_composite(raw_c, z_c, io->rays_d, n, S, C, keep, io->rgb_coarse, w_c, io->depth_coarse,
+                             io->ins_coarse, io->acc_coarse, st))) return rc;
+  // render.py:66-70  importance sampling + merge
+  if ((rc = launch_hier_sample(z_c, w_c, perturb ? io->u : nullptr, n, S, NI, z_f, st))) return rc;
+  // render.py:71-82  fine network on all S+I depths
+  if ((rc = mlp_dispatch(ctx, 1, nullptr, io->rays_o, io->rays_d, z_f, n * F, F, raw_f, impl, st))) return rc;
+  // render.py:86     fine composite
+  if ((rc = launch_composite(raw_f, z_f, io->rays_d, n, F, C, keep, io->rgb_fine, io->weights_fine, io->depth_fine,
+                             io->ins_fine, io->acc_fine, st))) return rc;
+  return 0;
+}
+
+DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* h, int64_t n, int S, int NI, int flags,
+                               int impl, void* stream) {
+  DMN_CHECK(ctx && h, "render_forward_host: NULL ctx/io");
+  DMN_CHECK(n >= 0, "render_forward_host: negative ray count");
+  if (n == 0) return 0;
+  DMN_CHECK(h->rays_o && h->rays_d && h->z_coarse, "render_forward_host: rays_o / rays_d / z_coarse is NULL");
+  DMN_CHECK(ctx->net[0].bound && ctx->net[1].bound, "render_forward_host: bind both networks first");
+  cudaStream_t st = (cudaStream_t)stream;
+  DMN_CUDA(cudaSetDevice(ctx->device));
+  const int ins = ctx->net[0].ins_num, C = 4 + ins + 1, F = S + NI;
+  const int n_ins_out = (flags & DMNERF_FLAG_KEEP_INS) ? ins + 1 : ins;
+  const bool perturb = (flags & DMNERF_FLAG_PERTURB) != 0;
+  const size_t zin = (h->z_row_stride == 0) ? (size_t)S : (size_t)n * h->z_row_stride;
+
+  // ---- inputs: one device arena
+  size_t in_floats = (size_t)n * 6 + zin + (perturb ? (size_t)n * (S + NI) : 0);
+  if (ctx->host_in.reserve(in_floats * 4)) return 2;
+  float* d = (float*)ctx->host_in.ptr;
+  dmnerf_render_io io;
+  memset(&io, 0, sizeof(io));
+  float* p = d;
+  DMN_CUDA(cudaMemcpyAsync(p, h->rays_o, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_o = p; p += n * 3;
+  DMN_CUDA(cudaMemcpyAsync(p, h->rays_d, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_d = p; p += n * 3;
+  DMN_CUDA(cudaMemcpyAsync(p, h->z_coarse, zin * 4, cudaMemcpyHostToDevice, st)); io.z_coarse = p; p += zin;
+  io.z_row_stride = h->z_row_stride;
+  if (perturb) {
+    DMN_CHECK(h->t_rand && h->u, "render_forward_host: PERTURB needs t_rand and u");
+    DMN_CUDA(cudaMemcpyAsync(p, h->t_rand, (size_t)n * S * 4, cudaMemcpyHostToDevice, st)); io.t_rand = p; p += n * S;
+    DMN_CUDA(cudaMemcpyAsync(p, h->u, (size_t)n * NI * 4, cudaMemcpyHostToDevice, st)); io.u = p; p += n * NI;
+  }
+  // ---- outputs: one device arena, carved for every non-NULL host output
+  struct Out { float* dmnerf_render_io::* hp; float* dmnerf_render_io::* dp; size_t per_ray; };
+  const Out outs[] = {
+      {&dmnerf_render_io::rgb_coarse, &dmnerf_render_io::rgb_coarse, 3}, {&dmnerf_render_io::rgb_fine, &dmnerf_render_io::rgb_fine, 3},
+      {&dmnerf_render_io::depth_coarse, &dmnerf_render_io::depth_coarse, 1}, {&dmnerf_render_io::depth_fine, &dmnerf_render_io::depth_fine, 1},
+      {&dmnerf_render_io::acc_coarse, &dmnerf_render_io::acc_coarse, 1}, {&dmnerf_render_io::acc_fine, &dmnerf_render_io::acc_fine, 1},
+      {&dmnerf_render_io::ins_coarse, &dmnerf_render_io::ins_coarse, (size_t)n_ins_out}, {&dmnerf_render_io::ins_fine, &dmnerf_render_io::ins_fine, (size_t)n_ins_out},
+      {&dmnerf_render_io::z_vals_coarse, &dmnerf_render_io::z_vals_coarse, (size_t)S}, {&dmnerf_render_io::z_vals_fine, &dmnerf_render_io::z_vals_fine, (size_t)F},
+      {&dmnerf_render_io::weights_coarse, &dmnerf_render_io::weights_coarse, (size_t)S}, {&dmnerf_render_io::weights_fine, &dmnerf_render_io::weights_fine, (size_t)F},
+      {&dmnerf_render_io::raw_coarse, &dmnerf_render_io::raw_coarse, (size_t)S * C}, {&dmnerf_render_io::raw_fine, &dmnerf_render_io::raw_fine, (size_t)F * C},
+  };
+  size_t out_floats = 0;
+  for (const Out& o : outs) if (h->*(o.hp)) out_floats += (size_t)n * o.per_ray;
+  if (ctx->host_out.reserve(out_floats * 4 + 16)) return 2;
+  float* q = (float*)ctx->host_out.ptr;
+  for (const Out& o : outs) if (h->*(o.hp)) { io.*(o.dp) = q; q += (size_t)n * o.per_ray; }
+
+  int rc = dmnerf_render_forward(ctx, &io, n, S, NI, flags, impl, stream);
+  if (rc) return rc;
+  for (const Out& o : outs)
+    if (h->*(o.hp))
+      DMN_CUDA(cudaMemcpyAsync(h->*(o.hp), io.*(o.dp), (size_t)n * o.per_ray * 4, cudaMemcpyDeviceToHost, st));
+  DMN_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

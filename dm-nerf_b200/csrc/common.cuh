@@ -1,0 +1,89 @@
+// Shared declarations for libdmnerf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/dmnerf_b200.h"
+
+namespace dmnerf {
+
+// Layer indices in reference state_dict order (networks/dm_nerf.py:65-78).
+enum Layer {
+  L_TRUNK0 = 0,  // mlps.0 .. mlps.7 -> 0..7
+  L_RGB_FEAT = 8,
+  L_INS_FEAT = 9,
+  L_RGB_HID = 10,   // rgb_feature_linears.0  (128 x 283)
+  L_INS_HID = 11,   // ins_feature_linears.0  (128 x 256)
+  L_DENSITY = 12,
+  L_INS_OUT = 13,
+  L_RGB_OUT = 14,
+  N_LAYERS = 15
+};
+
+constexpr int W_HID = 256;
+constexpr int CH_POS = DMNERF_CH_POS;   // 63
+constexpr int CH_DIR = DMNERF_CH_DIR;   // 27
+constexpr int CH_IN = CH_POS + CH_DIR;  // 90
+constexpr int L_POS = 10;
+constexpr int L_DIR = 4;
+
+// Live (caller-owned) fp32 parameter storage of one DM_NeRF.
+struct NetParams {
+  const float* w[N_LAYERS];
+  const float* b[N_LAYERS];
+  int ins_num;
+  bool bound;
+};
+
+__host__ __device__ inline int layer_out(int l, int ins_num) {
+  return l < 10 ? W_HID : (l < 12 ? W_HID / 2 : (l == L_DENSITY ? 1 : (l == L_INS_OUT ? ins_num + 1 : 3)));
+}
+__host__ __device__ inline int layer_in(int l) {
+  return l == 0 ? CH_POS : (l == 5 ? W_HID + CH_POS : (l == L_RGB_HID ? W_HID + CH_DIR : (l >= L_INS_OUT ? W_HID / 2 : W_HID)));
+}
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define DMN_CHECK(cond, ...)                   \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::dmnerf::set_error(__VA_ARGS__);        \
+      return 1;                                \
+    }                                          \
+  } while (0)
+
+#define DMN_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      ::dmnerf::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return 2;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+#define DMN_LAUNCH_OK()                                     \
+  do {                                                      \
+    ::dmnerf::g_launches.fetch_add(1);                      \
+    DMN_CUDA(cudaGetLastError());                           \
+  } while (0)
+
+// ---- launchers implemented in the individual .cu files (all return 0 / non-zero status) ----
+int launch_posenc(const float* x, int64_t m, int n_freqs, float* out, cudaStream_t st);
+int launch_composite(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all,
+                     float* rgb, float* weights, float* depth, float* ins, float* acc, cudaStream_t st);
+int launch_sample_pdf(const float* bins, const float* weights, int64_t n, int nb, int ns, const float* u, float* out,
+                      cudaStream_t st);
+int launch_sort_concat(const float* a, const float* b, int64_t n, int na, int nb, float* out, cudaStream_t st);
+int launch_prep_z(const float* z_in, int64_t z_stride, const float* t_rand, int64_t n, int s, float* z_out,
+                  cudaStream_t st);
+int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int ni, float* z_fine,
+                       cudaStream_t st);
+// MLP, SIMT fp32 path.  Exactly one of x / (rays_o, rays_d, z) is used.
+int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
+                    int64_t m, int s, float* out, cudaStream_t st);
+
+}  // namespace dmnerf

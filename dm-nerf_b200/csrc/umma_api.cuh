@@ -1,0 +1,24 @@
+// Interface between the C-ABI layer and the tcgen05 (UMMA) MLP kernel.
+#pragma once
+#include "common.cuh"
+
+namespace dmnerf {
+
+// Tensor-core operand image of one DM_NeRF: every layer's weight matrix split into bf16 hi/lo parts and
+// laid out in the exact shared-memory image (K-major, 128B swizzle, 64-wide K slabs) the kernel streams
+// with bulk async copies.  Owned by the context; rebuilt by dmnerf_set_weights.
+struct UmmaWeights {
+  void* image = nullptr;        // packed bf16 operand image (device)
+  float* bias = nullptr;        // packed fp32 biases (device)
+  size_t image_bytes = 0;
+  int ins_num = 0;
+  bool ready = false;
+};
+
+int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st);
+void umma_weights_free(UmmaWeights& w);
+bool umma_available(const UmmaWeights& w);
+int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, const float* rays_o, const float* rays_d,
+                    const float* z, int64_t m, int s, float* out, cudaStream_t st);
+
+}  // namespace dmnerf

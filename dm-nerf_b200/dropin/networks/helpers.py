@@ -1,0 +1,14 @@
+"""networks.helpers (reference networks/helpers.py): the hot-path functions come from the B200 package;
+everything else (ray selection for training, rotation helpers) is re-exported from the reference when
+DMNERF_REFERENCE_ROOT points at a checkout."""
+import importlib.util as _ilu
+import os as _os
+
+_ref = _os.environ.get("DMNERF_REFERENCE_ROOT")
+if _ref and _os.path.exists(_os.path.join(_ref, "networks", "helpers.py")):
+    _spec = _ilu.spec_from_file_location("_dmnerf_reference_helpers", _os.path.join(_ref, "networks", "helpers.py"))
+    _mod = _ilu.module_from_spec(_spec)
+    _spec.loader.exec_module(_mod)
+    globals().update({k: v for k, v in vars(_mod).items() if not k.startswith("__")})
+
+from dmnerf_b200.helpers import sample_pdf, z_val_sample, get_rays_k   # noqa: F401,E402

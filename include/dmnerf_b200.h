@@ -1,0 +1,127 @@
+/*
+ * dmnerf_b200.h -- C ABI of the B200-native DM-NeRF volumetric renderer (libdmnerf_b200.so).
+ *
+ * The reference (vLAR-group/DM-NeRF) has no FFI: its boundary is the Python call surface
+ *   networks/render.py:31   dm_nerf(rays, pos_embedder, view_embedder, model_coarse, model_fine, z_vals_coarse, args)
+ *   networks/render.py:6    render_train(raw, z_vals, rays_d)
+ *   networks/dm_nerf.py:80  DM_NeRF.forward(x)
+ *   networks/dm_nerf.py:37  Embedder.embed(x)
+ *   networks/helpers.py:123 sample_pdf(bins, weights, N_samples, det)
+ * Each entry point below names the reference function it replaces.  All pointers are plain device
+ * pointers (float32, row-major, contiguous) unless the name ends in _host; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Every function returns 0 on success and a non-zero
+ * status otherwise (never throws); dmnerf_last_error() returns a thread-local message.  No torch types
+ * cross this boundary -- see INTEGRATION.md for the ctypes binding the Python host layer uses.
+ */
+#ifndef DMNERF_B200_H_
+#define DMNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DMNERF_API __attribute__((visibility("default")))
+#else
+#define DMNERF_API
+#endif
+
+#define DMNERF_ABI_VERSION 1
+#define DMNERF_N_PARAMS 30          /* tensors in DM_NeRF.state_dict() order, networks/dm_nerf.py:65-78 */
+#define DMNERF_CH_POS 63            /* get_embedder(10): 3 + 3*2*10, networks/dm_nerf.py:41-55 */
+#define DMNERF_CH_DIR 27            /* get_embedder(4) */
+#define DMNERF_MAX_INS 127          /* ins_num + 1 <= 128 */
+
+/* MLP implementation selector */
+#define DMNERF_IMPL_AUTO 0          /* tcgen05 path when available for the shape, else SIMT */
+#define DMNERF_IMPL_SIMT 1          /* fp32 CUDA-core reference kernel */
+#define DMNERF_IMPL_UMMA 2          /* tcgen05 tensor-core kernel, bf16x3 split operands, fp32 accumulate */
+
+/* dmnerf_render_* flags */
+#define DMNERF_FLAG_PERTURB   1     /* args.perturb > 0: t_rand and u must be given (render.py:40-47, helpers.py:135) */
+#define DMNERF_FLAG_WANT_RAW  2     /* materialise raw_coarse / raw_fine (training, penalizer.py) */
+#define DMNERF_FLAG_KEEP_INS  4     /* keep all ins_num+1 instance channels, no detach: manipulator.py:86-105 */
+
+typedef struct dmnerf_ctx dmnerf_ctx;
+
+/* All per-ray inputs/outputs of one dm_nerf() call (networks/render.py:31-96).  Any output pointer
+ * may be NULL (not written).  Shapes: N rays, S coarse samples, I importance samples, F = S + I,
+ * C = 4 + ins_num + 1. */
+typedef struct dmnerf_render_io {
+  const float* rays_o;       /* [N,3] */
+  const float* rays_d;       /* [N,3] un-normalised */
+  const float* z_coarse;     /* [S] shared row (z_row_stride = 0) or [N,S] (z_row_stride = S) */
+  int64_t      z_row_stride;
+  const float* t_rand;       /* [N,S] stratified jitter uniforms or NULL (render.py:46) */
+  const float* u;            /* [N,I] inverse-CDF uniforms or NULL => linspace(0,1,I) (helpers.py:131-135) */
+  float* rgb_coarse;         /* [N,3] */
+  float* rgb_fine;           /* [N,3] */
+  float* depth_coarse;       /* [N] */
+  float* depth_fine;         /* [N] */
+  float* acc_coarse;         /* [N]  sum of weights (north_star acc_map) */
+  float* acc_fine;           /* [N] */
+  float* ins_coarse;         /* [N,ins_num] post-sigmoid, last class dropped (render.py:24-26) */
+  float* ins_fine;           /* [N,ins_num] */
+  float* z_vals_coarse;      /* [N,S] (after jitter) */
+  float* z_vals_fine;        /* [N,F] sorted */
+  float* weights_coarse;     /* [N,S] */
+  float* weights_fine;       /* [N,F] */
+  float* raw_coarse;         /* [N,S,C] only with DMNERF_FLAG_WANT_RAW */
+  float* raw_fine;           /* [N,F,C] */
+} dmnerf_render_io;
+
+DMNERF_API int         dmnerf_abi_version(void);
+DMNERF_API const char* dmnerf_last_error(void);
+
+DMNERF_API int dmnerf_ctx_create(int device, dmnerf_ctx** out);
+DMNERF_API int dmnerf_ctx_destroy(dmnerf_ctx* ctx);
+
+/* Bind one network's LIVE parameter storage (30 device pointers, state_dict order) and re-pack the
+ * tensor-core operand image.  net: 0 = coarse, 1 = fine.  Replaces model.load_state_dict()/the
+ * nn.Module parameter reads of DM_NeRF.forward (networks/dm_nerf.py:80-106).  Call again after every
+ * in-place optimizer update. */
+DMNERF_API int dmnerf_set_weights(dmnerf_ctx* ctx, int net, const float* const* params, int n_params, int ins_num,
+                       void* stream);
+
+/* Embedder.embed, networks/dm_nerf.py:37-38: x [M,3] -> out [M, 3 + 6*n_freqs]. */
+DMNERF_API int dmnerf_posenc(const float* x, int64_t m, int n_freqs, float* out, void* stream);
+
+/* DM_NeRF.forward, networks/dm_nerf.py:80-106: x [M,90] -> out [M,C]. */
+DMNERF_API int dmnerf_mlp_forward(dmnerf_ctx* ctx, int net, const float* x, int64_t m, float* out, int impl, void* stream);
+
+/* Same network evaluated at points given as rays + depths (render.py:49-61 fused: pts = o + d z,
+ * both embeddings, MLP).  z [N,S] -> out [N,S,C]. */
+DMNERF_API int dmnerf_mlp_forward_rays(dmnerf_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* z,
+                            int64_t n, int s, float* out, int impl, void* stream);
+
+/* render_train, networks/render.py:6-28 (keep_all_ins != 0: manipulator_render, manipulator.py:86-105).
+ * raw [N,S,C], z [N,S], rays_d [N,3] -> rgb [N,3], weights [N,S], depth [N], ins [N, C-5 or C-4], acc [N]. */
+DMNERF_API int dmnerf_composite(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c,
+                     int keep_all_ins, float* rgb, float* weights, float* depth, float* ins, float* acc,
+                     void* stream);
+
+/* sample_pdf, networks/helpers.py:123-155.  bins [N,nb], weights [N,nb-1]; u [N,ns] or NULL (det). */
+DMNERF_API int dmnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int n_bins, int n_samples,
+                      const float* u, float* out, void* stream);
+
+/* torch.sort(torch.cat([a, b], -1), -1).values, networks/render.py:70.  a [N,na], b [N,nb] -> [N,na+nb]. */
+DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int na, int nb, float* out, void* stream);
+
+/* dm_nerf(), networks/render.py:31-96, whole per-ray pipeline on device buffers. */
+DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n_rays, int n_coarse,
+                          int n_importance, int flags, int impl, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies rays in, renders, copies every non-NULL
+ * output back, and synchronises the stream.  This is the end-to-end entry point bench.py times. */
+DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* io_host, int64_t n_rays, int n_coarse,
+                               int n_importance, int flags, int impl, void* stream);
+
+/* Number of kernels this library has launched on the calling thread's contexts since load. */
+DMNERF_API int64_t dmnerf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMNERF_B200_H_ */
