@@ -48,6 +48,9 @@ struct dmnerf_ctx {
   UmmaWeights packed[2];          // tensor-core operand images (umma_api.cuh)
   Scratch ws_raw_c, ws_raw_f, ws_z_c, ws_z_f, ws_w_c, ws_w_f;
   Scratch host_in, host_out;      // device staging for the *_host entry point
+  bool profiling = false;
+  bool profile_valid = false;
+  cudaEvent_t ev[DMNERF_N_STAGES + 1] = {};
   dmnerf_ctx() { memset(net, 0, sizeof(net)); }
 };
 
@@ -81,6 +84,7 @@ DMNERF_API int dmnerf_ctx_destroy(dmnerf_ctx* ctx) {
   Scratch* all[] = {&ctx->ws_raw_c, &ctx->ws_raw_f, &ctx->ws_z_c, &ctx->ws_z_f, &ctx->ws_w_c, &ctx->ws_w_f,
                     &ctx->host_in, &ctx->host_out};
   for (Scratch* s : all) s->release();
+  for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -184,20 +188,52 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
   if (!raw_f) { if (ctx->ws_raw_f.reserve((size_t)n * F * C * 4)) return 2; raw_f = (float*)ctx->ws_raw_f.ptr; }
 
   int rc;
+  const bool prof = ctx->profiling;
+  int stage = 0;
+#define DMN_STAGE_MARK() do { if (prof) DMN_CUDA(cudaEventRecord(ctx->ev[stage++], st)); } while (0)
+  DMN_STAGE_MARK();
   // render.py:40-47  coarse depths (+ stratified jitter)
   if ((rc = launch_prep_z(io->z_coarse, io->z_row_stride, perturb ? io->t_rand : nullptr, n, S, z_c, st))) return rc;
+  DMN_STAGE_MARK();
   // render.py:49-61  points, embeddings, coarse network
   if ((rc = mlp_dispatch(ctx, 0, nullptr, io->rays_o, io->rays_d, z_c, n * S, S, raw_c, impl, st))) return rc;
+  DMN_STAGE_MARK();
   // render.py:63     coarse composite
   if ((rc = launch_composite(raw_c, z_c, io->rays_d, n, S, C, keep, io->rgb_coarse, w_c, io->depth_coarse,
                              io->ins_coarse, io->acc_coarse, st))) return rc;
+  DMN_STAGE_MARK();
   // render.py:66-70  importance sampling + merge
   if ((rc = launch_hier_sample(z_c, w_c, perturb ? io->u : nullptr, n, S, NI, z_f, st))) return rc;
+  DMN_STAGE_MARK();
   // render.py:71-82  fine network on all S+I depths
   if ((rc = mlp_dispatch(ctx, 1, nullptr, io->rays_o, io->rays_d, z_f, n * F, F, raw_f, impl, st))) return rc;
+  DMN_STAGE_MARK();
   // render.py:86     fine composite
   if ((rc = launch_composite(raw_f, z_f, io->rays_d, n, F, C, keep, io->rgb_fine, io->weights_fine, io->depth_fine,
                              io->ins_fine, io->acc_fine, st))) return rc;
+  DMN_STAGE_MARK();
+#undef DMN_STAGE_MARK
+  ctx->profile_valid = prof;
+  return 0;
+}
+
+DMNERF_API int dmnerf_profile_enable(dmnerf_ctx* ctx, int enable) {
+  DMN_CHECK(ctx != nullptr, "profile_enable: ctx is NULL");
+  DMN_CUDA(cudaSetDevice(ctx->device));
+  if (enable)
+    for (cudaEvent_t& e : ctx->ev)
+      if (!e) DMN_CUDA(cudaEventCreate(&e));
+  ctx->profiling = enable != 0;
+  ctx->profile_valid = false;
+  return 0;
+}
+
+DMNERF_API int dmnerf_profile_read(dmnerf_ctx* ctx, float* ms_out, int n_out) {
+  DMN_CHECK(ctx && ms_out, "profile_read: NULL argument");
+  DMN_CHECK(n_out >= DMNERF_N_STAGES, "profile_read: need room for %d stages", DMNERF_N_STAGES);
+  DMN_CHECK(ctx->profile_valid, "profile_read: no profiled render call recorded");
+  DMN_CUDA(cudaEventSynchronize(ctx->ev[DMNERF_N_STAGES]));
+  for (int i = 0; i < DMNERF_N_STAGES; ++i) DMN_CUDA(cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
   return 0;
 }
 

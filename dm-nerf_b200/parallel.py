@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing for the render path: rays are independent units, so a frame (or a
+trajectory) is split into contiguous ray ranges per rank with the weights replicated, each rank renders its
+slab with the fused kernels, and ONE all-gather of the packed image slabs assembles the result on every rank.
+No collective sits on the data path of the kernels themselves."""
+import torch
+
+
+def shard_range(n_items, world, rank, multiple=1):
+    """Contiguous [lo, hi) of `n_items` for `rank`; every shard but the last is a multiple of `multiple` and all
+    shards have equal padded length (returned as third value) so a fixed-size all-gather can be used."""
+    per = -(-n_items // world)
+    per = -(-per // multiple) * multiple
+    lo = min(rank * per, n_items)
+    hi = min(lo + per, n_items)
+    return lo, hi, per
+
+
+IMAGE_KEYS = ("rgb_fine", "depth_fine", "acc_fine", "ins_fine")
+
+
+def pack_image(out, keys=IMAGE_KEYS):
+    """[n, 3 + 1 + 1 + ins] packed slab of the per-ray outputs that make up the rendered image."""
+    cols = [out[k] if out[k].dim() == 2 else out[k][:, None] for k in keys]
+    return torch.cat(cols, -1).contiguous()
+
+
+def unpack_image(packed, ins_num, keys=IMAGE_KEYS):
+    widths = {"rgb_fine": 3, "depth_fine": 1, "acc_fine": 1, "ins_fine": ins_num}
+    res, c = {}, 0
+    for k in keys:
+        w = widths[k]
+        res[k] = packed[..., c:c + w] if w > 1 or k == "ins_fine" else packed[..., c]
+        c += w
+    return res
+
+
+def gather_image(out, world, group=None, pad_to=None):
+    """All-gather the packed image slab of every rank: returns [world, n_pad, 5 + ins] on every rank."""
+    import torch.distributed as dist
+    slab = pack_image(out)
+    if pad_to is not None and slab.shape[0] < pad_to:
+        slab = torch.cat([slab, slab.new_zeros(pad_to - slab.shape[0], slab.shape[1])], 0)
+    full = slab.new_empty((world * slab.shape[0],) + tuple(slab.shape[1:]))
+    dist.all_gather_into_tensor(full, slab, group=group)
+    return full.view((world,) + tuple(slab.shape))
+
+
+def render_frame_sharded(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, N_importance=128, render_fn=None,
+                         group=None):
+    """Render one frame split across the ranks of the default process group (strong scaling over rays) and return
+    the full-frame image dict on every rank.  `render_fn` defaults to the CUDA renderer."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if render_fn is None:
+        from .render import render_rays as render_fn
+    n = rays_o.shape[0]
+    lo, hi, per = shard_range(n, world, rank, multiple=128)
+    out = render_fn(rays_o[lo:hi], rays_d[lo:hi], model_coarse, model_fine, z_vals_coarse, N_importance=N_importance,
+                    want_raw=False, want_coarse=False)
+    ins_num = out["ins_fine"].shape[-1]
+    full = gather_image(out, world, group=group, pad_to=per)                 # [world, per, 5+ins]
+    flat = full.reshape(world * per, -1)[:n]
+    return unpack_image(flat, ins_num)

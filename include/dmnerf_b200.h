@@ -118,6 +118,14 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
 DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* io_host, int64_t n_rays, int n_coarse,
                                int n_importance, int flags, int impl, void* stream);
 
+/* Per-stage device timing of dmnerf_render_forward (CUDA events recorded on the launch stream around each stage):
+ * enable != 0 switches recording on.  dmnerf_profile_read synchronises the last recorded events and writes the
+ * elapsed milliseconds of the last render call: [0] coarse depths, [1] coarse network, [2] coarse composite,
+ * [3] importance sampling + merge, [4] fine network, [5] fine composite.  n_out must be >= 6. */
+#define DMNERF_N_STAGES 6
+DMNERF_API int dmnerf_profile_enable(dmnerf_ctx* ctx, int enable);
+DMNERF_API int dmnerf_profile_read(dmnerf_ctx* ctx, float* ms_out, int n_out);
+
 /* Number of kernels this library has launched on the calling thread's contexts since load. */
 DMNERF_API int64_t dmnerf_launch_count(void);
 
