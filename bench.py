@@ -35,6 +35,7 @@ import numpy as np   # noqa: E402
 import torch         # noqa: E402
 
 N_COARSE, N_IMPORTANCE = 64, 128
+_CPU_THREADS = None
 
 
 def parse():
@@ -58,13 +59,27 @@ def cpu_reference_rate(workload, seconds, chunk=1024):
     from dmnerf_b200 import synth
     wl = synth.workload(workload)
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     pc = O.to_torch(synth.make_weights(101, wl["ins_num"]))
     pf = O.to_torch(synth.make_weights(202, wl["ins_num"]))
     ro, rd = torch.from_numpy(wl["rays_o"]), torch.from_numpy(wl["rays_d"])
     z = O.z_val_sample(chunk, wl["near"], wl["far"], N_COARSE)
     n_total = ro.shape[0]
     with torch.no_grad():
+        # the reference would run with torch's default (= all cores); on many-core hosts that oversubscribes these
+        # small GEMMs badly, so give the CPU arm its best thread count (quick calibration on 256 rays)
+        global _CPU_THREADS
+        if _CPU_THREADS is None:
+            best = None
+            for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+                torch.set_num_threads(th)
+                O.render(ro[:256], rd[:256], pc, pf, z[:256], perturb=0.0, n_importance=N_IMPORTANCE)
+                t0 = time.perf_counter()
+                O.render(ro[256:512], rd[256:512], pc, pf, z[:256], perturb=0.0, n_importance=N_IMPORTANCE)
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, th)
+            _CPU_THREADS = best[1]
+        torch.set_num_threads(_CPU_THREADS)
         O.render(ro[:chunk], rd[:chunk], pc, pf, z, perturb=0.0, n_importance=N_IMPORTANCE)     # warm-up
         done, t0 = 0, time.perf_counter()
         pos = chunk

@@ -217,6 +217,17 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
   return 0;
 }
 
+DMNERF_API int dmnerf_sync_check(dmnerf_ctx* ctx, void* stream) {
+  DMN_CHECK(ctx != nullptr, "sync_check: ctx is NULL");
+  DMN_CUDA(cudaSetDevice(ctx->device));
+  DMN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int i = 0; i < 2; ++i) {
+    int rc = umma_check_status(ctx->packed[i], (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 DMNERF_API int dmnerf_profile_enable(dmnerf_ctx* ctx, int enable) {
   DMN_CHECK(ctx != nullptr, "profile_enable: ctx is NULL");
   DMN_CUDA(cudaSetDevice(ctx->device));
@@ -289,8 +300,7 @@ DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_i
   for (const Out& o : outs)
     if (h->*(o.hp))
       DMN_CUDA(cudaMemcpyAsync(h->*(o.hp), io.*(o.dp), (size_t)n * o.per_ray * 4, cudaMemcpyDeviceToHost, st));
-  DMN_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return dmnerf_sync_check(ctx, stream);
 }
 
 }  // extern "C"

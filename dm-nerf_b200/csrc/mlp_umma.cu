@@ -1,13 +1,655 @@
-// tcgen05 MLP kernel -- placeholder until the probe results are in (see tools/umma_probe.cu).
+// tcgen05 (UMMA) implementation of the DM_NeRF network for one 128-sample tile per CTA (persistent, 1 CTA / SM).
+//
+// Arithmetic: every fp32 operand is split into bf16 hi + bf16 lo (16 significand bits); each algorithmic GEMM is issued
+// as three tensor passes  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  accumulating in fp32 in tensor memory (relative error
+// ~2^-16 per product, measured ~1e-5 on outputs, inside the 1e-4 parity budget; single-pass bf16/tf32 is not).
+//
+// Data flow per tile (nothing 256-wide ever leaves the SM):
+//   * activations: three rotating 128-column "slots"; the bf16-hi half of a slot lives in tensor memory (A operand of the
+//     two TS passes: no shared-memory read), the bf16-lo half in shared memory as two K-major SWIZZLE_128B slabs (SS pass).
+//   * every 256-wide layer is executed as two N=128 half-steps with separate TMEM accumulators, so the epilogue of one
+//     half-step (TMEM -> registers -> bias/ReLU/split -> slot) overlaps the tensor work of the next.
+//   * weights: packed once per weight update (dmnerf_set_weights) into the exact shared-memory image, streamed in
+//     16 KB stages through a ring with 1-D bulk async copies (TMA engine, mbarrier completion) from L2.
+//   * heads: rgb_feature_linear / ins_feature_linear have no activation, so they are folded into the following layer at
+//     pack time (W' = W2 W1, fp64 accumulate); density (N=1) is a CUDA-core dot product inside layer 7's epilogue.
+//
+// Warp roles: warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 prologue (points +
+// positional encoding) and epilogue.  All waits are bounded: a protocol bug raises an error code, never a hang.
+#include <cstring>
+#include <vector>
+
+#include "ray_ops.cuh"
+#include "umma.cuh"
 #include "umma_api.cuh"
 
 namespace dmnerf {
-int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t) { w.ins_num = p.ins_num; w.ready = false; return 0; }
-void umma_weights_free(UmmaWeights& w) { if (w.image) cudaFree(w.image); if (w.bias) cudaFree(w.bias); w = UmmaWeights(); }
-bool umma_available(const UmmaWeights& w) { return w.ready; }
-int launch_mlp_umma(const UmmaWeights&, const NetParams&, const float*, const float*, const float*, const float*, int64_t,
-                    int, float*, cudaStream_t) {
-  set_error("tcgen05 MLP kernel not available in this build");
-  return 3;
+namespace uk {
+
+using namespace umma;
+
+constexpr int TILE_M = 128;
+constexpr int NS = 5;                      // weight ring stages
+constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
+constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
+constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;
+constexpr int N_STEPS = 20;
+constexpr int MAX_CHUNKS = 5;
+constexpr int MAX_STAGES = 160;
+constexpr int EPI_THREADS = 256;
+constexpr int N_THREADS = 128 + EPI_THREADS;
+
+// tensor-memory column map (512 columns x 128 lanes x 32 bit)
+constexpr uint32_t TC_ACC = 0;             // two accumulators: [0,128) and [128,256)
+constexpr uint32_t TC_SLOT = 256;          // bf16-hi halves of the three slots: 64 columns each
+constexpr uint32_t TC_E = 448;             // bf16-hi of the position embedding (64 K -> 32 columns)
+constexpr uint32_t TC_D = 480;             // bf16-hi of the direction embedding (32 K -> 16 columns)
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t SM_SLOT = 0;
+constexpr uint32_t SM_E = 3 * SLOT_BYTES;
+constexpr uint32_t SM_D = SM_E + CHUNK_BYTES;
+constexpr uint32_t SM_RING = SM_D + CHUNK_BYTES;
+constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = SM_MISC + 2048 + 1024;      // misc block + alignment slack
+
+enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..5 = slot*2 + half
+
+struct Step {
+  int8_t n_chunks;
+  int8_t chunk[MAX_CHUNKS];   // ChunkKind or slot*2+j
+  int8_t dep[MAX_CHUNKS];     // tile-relative step whose epilogue produces the chunk; -1 = tile inputs
+  int8_t ksteps[MAX_CHUNKS];  // K/16 MMAs for this chunk (4, or 2 for the direction embedding)
+  int8_t out_slot;            // destination slot, or -1 = write network outputs
+  int8_t relu;
+  int16_t n;                  // MMA N (multiple of 16, <= 128)
+};
+
+struct Program {
+  Step step[N_STEPS];
+  uint32_t stage_off[MAX_STAGES];     // byte offset of every weight stage in the packed image
+  int32_t n_stages;
+  int32_t ins_num;
+};
+
+struct Misc {                  // lives at SM_MISC
+  uint64_t full[NS], empty[NS];
+  uint64_t acc_full[2], epi_done[2], inputs_ready;
+  uint32_t tmem_base;
+  int32_t abort_flag;
+  float dens[2][TILE_M];
+};
+
+struct KArgs {
+  const uint8_t* image;        // packed bf16 operand image
+  const float* bias;           // [N_STEPS][128] + wd[256] + bd
+  const float* x;              // [M, 90] or nullptr
+  const float* rays_o; const float* rays_d; const float* z;   // rays mode
+  int64_t m;
+  int32_t s;                   // samples per ray (rays mode)
+  float* out;                  // [M, C]
+  int32_t* status;             // device error word
+};
+
+// ------------------------------------------------------------------------------------------------ bounded waits
+__device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*(volatile int32_t*)&misc->abort_flag) return false;
+    if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
+      atomicExch(&misc->abort_flag, code);
+      atomicCAS(status, 0, code);
+      return false;
+    }
+  }
+  return true;
 }
+
+// ------------------------------------------------------------------------------------------------ prologue helpers
+// Element e of the embedding [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)] given precomputed sin/cos.
+template <int E0, int COUNT, int L>
+__device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* COUNT */) {
+  constexpr int F_LO = (E0 <= 3) ? 0 : (E0 - 3) / 6;
+  constexpr int F_HI_RAW = (E0 + COUNT - 1 - 3) / 6;
+  constexpr int F_HI = (E0 + COUNT - 1 < 3) ? -1 : (F_HI_RAW < L - 1 ? F_HI_RAW : L - 1);
+#pragma unroll
+  for (int i = 0; i < COUNT; ++i) vals[i] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (c >= E0 && c < E0 + COUNT) vals[c - E0] = v[c];
+#pragma unroll
+  for (int f = F_LO; f <= F_HI; ++f) {
+    const float sc = (float)(1 << f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sn, cs;
+      sincosf(v[c] * sc, &sn, &cs);
+      const int es = 3 + 6 * f + c, ec = es + 3;
+      if (es >= E0 && es < E0 + COUNT) vals[es - E0] = sn;
+      if (ec >= E0 && ec < E0 + COUNT) vals[ec - E0] = cs;
+    }
+  }
+}
+
+// 32 fp32 values -> bf16 hi into TMEM (16 columns; the hi half feeds two of the three passes, and a TMEM A operand
+// costs no shared-memory bandwidth), bf16 lo into a K-major SW128 slab row (columns [k0, k0+32)).
+__device__ __forceinline__ void store_split32(const float* vals, uint8_t* slab, int row, int k0, uint32_t tmem_addr) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<uint4*>(slab + sw128_offset(row, k0 + 8 * u)) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+  tmem_st_x16(tmem_addr, hi);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_constant__ Program prog, const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (a.m + TILE_M - 1) / TILE_M;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int C = 4 + prog.ins_num + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 1); mbar_init(&misc->epi_done[i], EPI_THREADS); }
+    mbar_init(&misc->inputs_ready, EPI_THREADS);
+    misc->abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&misc->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = misc->tmem_base;
+
+  if (warp == 0) {
+    // =========================================================== weight producer (one lane)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        int si = 0;
+        for (int t = 0; t < N_STEPS; ++t) {
+          const Step& st = prog.step[t];
+          const uint32_t bytes = (uint32_t)st.n * 128u;
+          for (int c = 0; c < 2 * st.n_chunks; ++c, ++si, ++it) {
+            const uint32_t slot = it % NS, ph = (it / NS) & 1;
+            if (!wait_or_abort(&misc->empty[slot], ph ^ 1, misc, 101, a.status)) goto done;
+            mbar_arrive_expect_tx(&misc->full[slot], bytes);
+            bulk_g2s(smem + SM_RING + slot * STAGE_BYTES, a.image + prog.stage_off[si], bytes, &misc->full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      uint32_t it = 0;
+      uint32_t seen_epi[2] = {0, 0}, seen_in = 0;
+      const uint32_t slot_base = smem_u32(smem + SM_SLOT), e_base = smem_u32(smem + SM_E), d_base = smem_u32(smem + SM_D);
+      const uint32_t ring_base = smem_u32(smem + SM_RING);
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        for (int t = 0; t < N_STEPS; ++t) {
+          const Step& st = prog.step[t];
+          const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
+          const uint32_t idesc = make_idesc_bf16(128, st.n);
+          const uint32_t d_tmem = tbase + TC_ACC + acc * 128;
+          // accumulator free: epilogue of global step g-2 finished
+          if (g >= 2) {
+            const uint32_t need = g / 2;        // completions of epi_done[acc] required
+            while (seen_epi[acc] < need) {
+              if (!wait_or_abort(&misc->epi_done[acc], seen_epi[acc] & 1, misc, 201, a.status)) goto done;
+              ++seen_epi[acc];
+            }
+          }
+          uint32_t first = 1;
+          for (int c = 0; c < st.n_chunks; ++c) {
+            const int kind = st.chunk[c];
+            // operand ready
+            if (st.dep[c] < 0) {
+              while (seen_in < (uint32_t)ti + 1) {
+                if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
+                ++seen_in;
+              }
+            } else {
+              const uint32_t gd = (uint32_t)ti * N_STEPS + st.dep[c], ad = gd & 1, need = gd / 2 + 1;
+              while (seen_epi[ad] < need) {
+                if (!wait_or_abort(&misc->epi_done[ad], seen_epi[ad] & 1, misc, 203, a.status)) goto done;
+                ++seen_epi[ad];
+              }
+            }
+            tc_fence_after();
+            uint32_t a_smem, a_tmem;
+            if (kind == CK_E) { a_smem = e_base; a_tmem = tbase + TC_E; }
+            else if (kind == CK_D) { a_smem = d_base; a_tmem = tbase + TC_D; }
+            else { a_smem = slot_base + kind * CHUNK_BYTES; a_tmem = tbase + TC_SLOT + kind * 32; }
+            const int ks = st.ksteps[c];
+            // ---- stage with W_hi: A_hi*W_hi (TS) + A_lo*W_hi (SS)
+            {
+              const uint32_t slot = it % NS, ph = (it / NS) & 1;
+              if (!wait_or_abort(&misc->full[slot], ph, misc, 204, a.status)) goto done;
+              tc_fence_after();
+              const uint32_t w = ring_base + slot * STAGE_BYTES;
+              for (int k = 0; k < ks; ++k) {
+                mma_ts(d_tmem, a_tmem + k * 8, make_sdesc_sw128(w + k * 32), idesc, first ? 0u : 1u);
+                first = 0;
+                mma_ss(d_tmem, make_sdesc_sw128(a_smem + k * 32), make_sdesc_sw128(w + k * 32), idesc, 1u);
+              }
+              mma_commit(&misc->empty[slot]);
+              ++it;
+            }
+            // ---- stage with W_lo: A_hi*W_lo (TS)
+            {
+              const uint32_t slot = it % NS, ph = (it / NS) & 1;
+              if (!wait_or_abort(&misc->full[slot], ph, misc, 205, a.status)) goto done;
+              tc_fence_after();
+              const uint32_t w = ring_base + slot * STAGE_BYTES;
+              for (int k = 0; k < ks; ++k)
+                mma_ts(d_tmem, a_tmem + k * 8, make_sdesc_sw128(w + k * 32), idesc, 1u);
+              mma_commit(&misc->empty[slot]);
+              ++it;
+            }
+          }
+          mma_commit(&misc->acc_full[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================================================== prologue + epilogue warps
+    const int et = tid - 128;                 // 0..255
+    const int q = et >> 7;                    // column half handled by this warpgroup
+    const int r = et & 127;                   // tile row == TMEM lane
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* e_slab = smem + SM_E;
+    uint8_t* d_slab = smem + SM_D;
+    float dens_acc = 0.0f;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int64_t tile = blockIdx.x + ti * gridDim.x;
+      const int64_t row = tile * TILE_M + r;
+      const bool valid = row < a.m;
+      // ---------------- prologue: points, embeddings -> E / D operands (hi: TMEM, lo: smem)
+      {
+        float vals[32];
+        if (a.x) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int e = 32 * q + i;
+            vals[i] = (valid && e < CH_POS) ? a.x[row * CH_IN + e] : 0.0f;
+          }
+          store_split32(vals, e_slab, r, 32 * q, tbase + lane_sel + TC_E + 16 * q);
+          if (q == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vals[i] = (valid && i < CH_DIR) ? a.x[row * CH_IN + CH_POS + i] : 0.0f;
+            store_split32(vals, d_slab, r, 0, tbase + lane_sel + TC_D);
+          }
+        } else {
+          float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+            const int64_t ray = row / a.s;
+            const float zz = a.z[row];
+            const float d0 = a.rays_d[ray * 3], d1 = a.rays_d[ray * 3 + 1], d2 = a.rays_d[ray * 3 + 2];
+            pt[0] = __fadd_rn(a.rays_o[ray * 3 + 0], __fmul_rn(d0, zz));      // render.py:49
+            pt[1] = __fadd_rn(a.rays_o[ray * 3 + 1], __fmul_rn(d1, zz));
+            pt[2] = __fadd_rn(a.rays_o[ray * 3 + 2], __fmul_rn(d2, zz));
+            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+            vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
+          }
+          if (q == 0) {
+            fill_embedding<0, 32, L_POS>(pt, vals);
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+            }
+            store_split32(vals, e_slab, r, 0, tbase + lane_sel + TC_E);
+            fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+            }
+            store_split32(vals, d_slab, r, 0, tbase + lane_sel + TC_D);
+          } else {
+            fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+            }
+            store_split32(vals, e_slab, r, 32, tbase + lane_sel + TC_E + 16);
+          }
+        }
+        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&misc->inputs_ready);
+      }
+      // ---------------- epilogues of the 20 half-steps
+      for (int t = 0; t < N_STEPS; ++t) {
+        const Step& st = prog.step[t];
+        const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
+        if (!wait_or_abort(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status)) goto done;
+        tc_fence_after();
+        const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
+        const float* bias = a.bias + t * 128;
+        if (st.out_slot >= 0) {
+          // hidden half-step: 64 columns per thread -> bias, (ReLU), split, store into the destination slot
+          const int slot = st.out_slot;
+          uint8_t* slab = smem + SM_SLOT + slot * SLOT_BYTES + q * CHUNK_BYTES;     // this thread's 64 columns = chunk q
+          const uint32_t lo_addr = tbase + lane_sel + TC_SLOT + slot * 64 + q * 32;
+          const bool is_l7 = (t == 14 || t == 15);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_x32(acc_addr + q * 64 + h * 32, v);
+            tmem_ld_wait();
+            float f[32];
+            const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + h * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            }
+            if (st.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            if (is_l7) {        // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
+              const float4* w4 = reinterpret_cast<const float4*>(a.bias + N_STEPS * 128 + (t - 14) * 128 + q * 64 + h * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 ww = __ldg(w4 + j);
+                dens_acc = fmaf(f[4 * j + 0], ww.x, dens_acc);
+                dens_acc = fmaf(f[4 * j + 1], ww.y, dens_acc);
+                dens_acc = fmaf(f[4 * j + 2], ww.z, dens_acc);
+                dens_acc = fmaf(f[4 * j + 3], ww.w, dens_acc);
+              }
+            }
+            store_split32(f, slab, r, h * 32, lo_addr + h * 16);
+          }
+          if (t == 15) {         // publish this column-half's partial sum of the density dot product; the rgb-head
+            misc->dens[q][r] = dens_acc;   // epilogue (3 barrier hops later) adds the two halves
+            dens_acc = 0.0f;
+          }
+          fence_proxy_async_smem();
+          tmem_st_wait();
+        } else if (t == N_STEPS - 2) {
+          // rgb head (N=16: 3 live columns) + density -> out[:, 0:4]          (dm_nerf.py:101-102,105)
+          if (q == 0) {
+            uint32_t v[16];
+            tmem_ld_x16(acc_addr, v);
+            tmem_ld_wait();
+            if (valid) {
+              float* o = a.out + row * C;
+              o[0] = __uint_as_float(v[0]) + __ldg(bias + 0);
+              o[1] = __uint_as_float(v[1]) + __ldg(bias + 1);
+              o[2] = __uint_as_float(v[2]) + __ldg(bias + 2);
+              o[3] = misc->dens[0][r] + misc->dens[1][r] + __ldg(a.bias + N_STEPS * 128 + 256);
+            }
+          }
+        } else {
+          // instance head (N = pad16(ins_num+1)) -> out[:, 4:]                  (dm_nerf.py:103,105)
+          const int n_ins = prog.ins_num + 1;
+          for (int c0 = q * 64; c0 < st.n && c0 < q * 64 + 64; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_x16(acc_addr + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+              float* o = a.out + row * C + 4;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < n_ins) o[c0 + j] = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&misc->epi_done[acc]);
+      }
+    }
+  }
+done:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host: program
+static void build_program(Program& P, int ins_num) {
+  memset(&P, 0, sizeof(P));
+  P.ins_num = ins_num;
+  int a_slot = -1, b_slot = -1, f_slot = -1;          // slots holding K-halves 0/1 of the current activation, free slot
+  int a_step = -1, b_step = -1;                        // steps that produced them
+  int t = 0;
+  auto add_chunk = [&](Step& s, int kind, int dep, int ks) {
+    s.chunk[s.n_chunks] = (int8_t)kind; s.dep[s.n_chunks] = (int8_t)dep; s.ksteps[s.n_chunks] = (int8_t)ks; ++s.n_chunks;
+  };
+  auto add_act = [&](Step& s) {
+    add_chunk(s, a_slot * 2 + 0, a_step, 4); add_chunk(s, a_slot * 2 + 1, a_step, 4);
+    add_chunk(s, b_slot * 2 + 0, b_step, 4); add_chunk(s, b_slot * 2 + 1, b_step, 4);
+  };
+  for (int l = 0; l < 8; ++l) {
+    int out0, out1;
+    if (l == 0) { out0 = 0; out1 = 1; }
+    else { out0 = f_slot; out1 = a_slot; }
+    for (int h = 0; h < 2; ++h) {
+      Step& s = P.step[t];
+      s.n = 128; s.relu = 1; s.out_slot = (int8_t)(h == 0 ? out0 : out1);
+      if (l == 0) add_chunk(s, CK_E, -1, 4);
+      else { add_act(s); if (l == 5) add_chunk(s, CK_E, -1, 4); }
+      ++t;
+    }
+    const int nf = (l == 0) ? 2 : b_slot;
+    a_slot = out0; b_slot = out1; f_slot = nf;
+    a_step = t - 2; b_step = t - 1;
+  }
+  // folded colour branch -> free slot; folded instance branch -> slot of K-half 0 (free once both MMAs completed)
+  const int rgb_slot = f_slot, ins_slot = a_slot;
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = (int8_t)rgb_slot; add_act(s); add_chunk(s, CK_D, -1, 2); ++t; }
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = (int8_t)ins_slot; add_act(s); ++t; }
+  { Step& s = P.step[t]; s.n = 16; s.relu = 0; s.out_slot = -1;
+    add_chunk(s, rgb_slot * 2 + 0, t - 2, 4); add_chunk(s, rgb_slot * 2 + 1, t - 2, 4); ++t; }
+  { Step& s = P.step[t]; s.n = (int16_t)(((ins_num + 1) + 15) / 16 * 16); s.relu = 0; s.out_slot = -1;
+    add_chunk(s, ins_slot * 2 + 0, t - 2, 4); add_chunk(s, ins_slot * 2 + 1, t - 2, 4); ++t; }
+  // stage offsets
+  uint32_t off = 0;
+  int si = 0;
+  for (int i = 0; i < N_STEPS; ++i)
+    for (int c = 0; c < 2 * P.step[i].n_chunks; ++c) { P.stage_off[si++] = off; off += (uint32_t)P.step[i].n * 128u; }
+  P.n_stages = si;
+}
+
+// ------------------------------------------------------------------------------------------------ host: packing
+struct PackStage {            // one entry per (step, chunk): produces the W_hi and the W_lo stage
+  const float* src; int ld; int n_base; int n_valid; int col_base; int k_valid; int n_rows; uint32_t off_hi; uint32_t off_lo;
+};
+
+__global__ void fold_kernel(const float* __restrict__ w2, int ld2, const float* __restrict__ w1, const float* __restrict__ b1,
+                            const float* __restrict__ b2, int extra_cols, float* __restrict__ wout, float* __restrict__ bout) {
+  // wout[n][k] = sum_j w2[n][j] w1[j][k] (k < 256);  wout[n][256 + e] = w2[n][256 + e];  bout[n] = sum_j w2[n][j] b1[j] + b2[n]
+  const int n = blockIdx.x, ldo = 256 + extra_cols;
+  for (int k = threadIdx.x; k < ldo + 1; k += blockDim.x) {
+    if (k < 256) {
+      double s = 0.0;
+      for (int j = 0; j < 256; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)w1[(size_t)j * 256 + k];
+      wout[(size_t)n * ldo + k] = (float)s;
+    } else if (k < ldo) {
+      wout[(size_t)n * ldo + k] = w2[(size_t)n * ld2 + k];
+    } else {
+      double s = (double)b2[n];
+      for (int j = 0; j < 256; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)b1[j];
+      bout[n] = (float)s;
+    }
+  }
+}
+
+__global__ void pack_kernel(const PackStage* __restrict__ stages, int n_entries, uint8_t* __restrict__ image) {
+  const int e = blockIdx.x;
+  if (e >= n_entries) return;
+  const PackStage ps = stages[e];
+  for (int idx = threadIdx.x; idx < ps.n_rows * 8; idx += blockDim.x) {
+    const int n = idx >> 3, u = idx & 7;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 8 * u + 2 * j + h;
+        v[h] = (n < ps.n_valid && k < ps.k_valid) ? ps.src[(size_t)(ps.n_base + n) * ps.ld + ps.col_base + k] : 0.0f;
+      }
+      umma::split_bf16x2(v[0], v[1], hi[j], lo[j]);
+    }
+    const uint32_t o = umma::sw128_offset(n, 8 * u);
+    *reinterpret_cast<uint4*>(image + ps.off_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(image + ps.off_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void bias_kernel(NetParams p, const float* __restrict__ fold_b_rgb, const float* __restrict__ fold_b_ins,
+                            float* __restrict__ bias) {
+  // [20][128] step biases, then density weights [256], then density bias
+  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < N_STEPS * 128 + 257; i += blockDim.x * gridDim.x) {
+    float v = 0.0f;
+    if (i < 16 * 128) {
+      const int t = i / 128, c = i % 128, l = t / 2, h = t % 2;
+      v = p.b[l][h * 128 + c];
+    } else if (i < 17 * 128) v = fold_b_rgb[i - 16 * 128];
+    else if (i < 18 * 128) v = fold_b_ins[i - 17 * 128];
+    else if (i < 19 * 128) { const int c = i - 18 * 128; v = c < 3 ? p.b[L_RGB_OUT][c] : 0.0f; }
+    else if (i < 20 * 128) { const int c = i - 19 * 128; v = c < p.ins_num + 1 ? p.b[L_INS_OUT][c] : 0.0f; }
+    else if (i < 20 * 128 + 256) v = p.w[L_DENSITY][i - 20 * 128];
+    else v = p.b[L_DENSITY][0];
+    bias[i] = v;
+  }
+}
+
+}  // namespace uk
+
+// ================================================================================================ API
+struct UmmaExtra {            // hangs off UmmaWeights::image allocation bookkeeping
+  uk::Program prog;
+  float* fold_w_rgb; float* fold_w_ins; float* fold_b; uk::PackStage* d_entries; int32_t* d_status;
+};
+
+static UmmaExtra* extra_of(const UmmaWeights& w) { return reinterpret_cast<UmmaExtra*>(w.extra); }
+
+void umma_weights_free(UmmaWeights& w) {
+  if (w.image) cudaFree(w.image);
+  if (w.bias) cudaFree(w.bias);
+  if (w.extra) {
+    UmmaExtra* x = extra_of(w);
+    if (x->fold_w_rgb) cudaFree(x->fold_w_rgb);
+    if (x->fold_w_ins) cudaFree(x->fold_w_ins);
+    if (x->fold_b) cudaFree(x->fold_b);
+    if (x->d_entries) cudaFree(x->d_entries);
+    if (x->d_status) cudaFree(x->d_status);
+    delete x;
+  }
+  w = UmmaWeights();
+}
+
+bool umma_available(const UmmaWeights& w) { return w.ready; }
+
+int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
+  using namespace uk;
+  if (w.extra && w.ins_num != p.ins_num) umma_weights_free(w);
+  if (!w.extra) {
+    UmmaExtra* x = new UmmaExtra();
+    memset(x, 0, sizeof(*x));
+    build_program(x->prog, p.ins_num);
+    w.extra = x;
+    w.ins_num = p.ins_num;
+    const uint32_t last = x->prog.n_stages - 1;
+    w.image_bytes = x->prog.stage_off[last] + (size_t)x->prog.step[N_STEPS - 1].n * 128;
+    DMN_CUDA(cudaMalloc(&w.image, w.image_bytes));
+    DMN_CUDA(cudaMalloc((void**)&w.bias, (N_STEPS * 128 + 260) * sizeof(float)));
+    DMN_CUDA(cudaMalloc((void**)&x->fold_w_rgb, 128 * 283 * sizeof(float)));
+    DMN_CUDA(cudaMalloc((void**)&x->fold_w_ins, 128 * 256 * sizeof(float)));
+    DMN_CUDA(cudaMalloc((void**)&x->fold_b, 256 * sizeof(float)));
+    DMN_CUDA(cudaMalloc((void**)&x->d_entries, MAX_STAGES * sizeof(PackStage)));
+    DMN_CUDA(cudaMalloc((void**)&x->d_status, sizeof(int32_t)));
+    DMN_CUDA(cudaMemsetAsync(x->d_status, 0, sizeof(int32_t), st));
+  }
+  UmmaExtra* x = extra_of(w);
+  // fold the activation-free feature layers into the following hidden layers (fp64 accumulate)
+  fold_kernel<<<128, 128, 0, st>>>(p.w[L_RGB_HID], 283, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], p.b[L_RGB_HID], 27, x->fold_w_rgb, x->fold_b);
+  DMN_LAUNCH_OK();
+  fold_kernel<<<128, 128, 0, st>>>(p.w[L_INS_HID], 256, p.w[L_INS_FEAT], p.b[L_INS_FEAT], p.b[L_INS_HID], 0, x->fold_w_ins, x->fold_b + 128);
+  DMN_LAUNCH_OK();
+  // one PackStage per (step, chunk)
+  std::vector<PackStage> ent;
+  int si = 0;
+  for (int t = 0; t < N_STEPS; ++t) {
+    const Step& s = x->prog.step[t];
+    for (int c = 0; c < s.n_chunks; ++c, si += 2) {
+      PackStage e;
+      memset(&e, 0, sizeof(e));
+      e.n_rows = s.n; e.off_hi = x->prog.stage_off[si]; e.off_lo = x->prog.stage_off[si + 1];
+      const int kind = s.chunk[c];
+      if (t < 16) {                                   // trunk layer l, output half h
+        const int l = t / 2, h = t % 2;
+        e.src = p.w[l]; e.ld = layer_in(l); e.n_base = h * 128; e.n_valid = 128;
+        if (kind == CK_E) { e.col_base = (l == 0) ? 0 : 256; e.k_valid = 63; }
+        else { e.col_base = 64 * c; e.k_valid = 64; }
+      } else if (t == 16) {                           // folded rgb hidden layer: [128][283]
+        e.src = x->fold_w_rgb; e.ld = 283; e.n_base = 0; e.n_valid = 128;
+        if (kind == CK_D) { e.col_base = 256; e.k_valid = 27; } else { e.col_base = 64 * c; e.k_valid = 64; }
+      } else if (t == 17) {                           // folded instance hidden layer: [128][256]
+        e.src = x->fold_w_ins; e.ld = 256; e.n_base = 0; e.n_valid = 128; e.col_base = 64 * c; e.k_valid = 64;
+      } else if (t == 18) {                           // rgb_linear [3][128]
+        e.src = p.w[L_RGB_OUT]; e.ld = 128; e.n_base = 0; e.n_valid = 3; e.col_base = 64 * c; e.k_valid = 64;
+      } else {                                        // ins_linear [ins_num+1][128]
+        e.src = p.w[L_INS_OUT]; e.ld = 128; e.n_base = 0; e.n_valid = p.ins_num + 1; e.col_base = 64 * c; e.k_valid = 64;
+      }
+      ent.push_back(e);
+    }
+  }
+  DMN_CHECK((int)ent.size() * 2 == x->prog.n_stages && (int)ent.size() <= MAX_STAGES, "umma pack: stage table mismatch");
+  DMN_CUDA(cudaMemcpyAsync(x->d_entries, ent.data(), ent.size() * sizeof(PackStage), cudaMemcpyHostToDevice, st));
+  DMN_CUDA(cudaStreamSynchronize(st));               // `ent` is a host temporary
+  pack_kernel<<<(unsigned)ent.size(), 256, 0, st>>>(x->d_entries, (int)ent.size(), (uint8_t*)w.image);
+  DMN_LAUNCH_OK();
+  bias_kernel<<<8, 256, 0, st>>>(p, x->fold_b, x->fold_b + 128, w.bias);
+  DMN_LAUNCH_OK();
+  w.ready = true;
+  return 0;
+}
+
+int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, const float* rays_o, const float* rays_d,
+                    const float* z, int64_t m, int s, float* out, cudaStream_t st) {
+  using namespace uk;
+  DMN_CHECK(w.ready && w.extra, "mlp(umma): weights not packed (call dmnerf_set_weights first)");
+  DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr && z != nullptr), "mlp(umma): pass either x or rays");
+  if (m == 0) return 0;
+  UmmaExtra* ex = extra_of(w);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  DMN_CUDA(cudaGetDevice(&dev));
+  DMN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = (m + TILE_M - 1) / TILE_M;
+  KArgs a;
+  a.image = (const uint8_t*)w.image; a.bias = w.bias; a.x = x; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
+  a.m = m; a.s = s; a.out = out; a.status = ex->d_status;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  mlp_umma_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+int umma_check_status(const UmmaWeights& w, cudaStream_t st) {
+  if (!w.extra) return 0;
+  int32_t code = 0;
+  DMN_CUDA(cudaMemcpyAsync(&code, extra_of(w)->d_status, sizeof(code), cudaMemcpyDeviceToHost, st));
+  DMN_CUDA(cudaStreamSynchronize(st));
+  DMN_CHECK(code == 0, "tcgen05 MLP kernel reported protocol error %d (bounded wait expired)", code);
+  return 0;
+}
+
 }  // namespace dmnerf

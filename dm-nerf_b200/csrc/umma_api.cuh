@@ -10,6 +10,7 @@ namespace dmnerf {
 struct UmmaWeights {
   void* image = nullptr;        // packed bf16 operand image (device)
   float* bias = nullptr;        // packed fp32 biases (device)
+  void* extra = nullptr;        // kernel program + folded-weight scratch (mlp_umma.cu)
   size_t image_bytes = 0;
   int ins_num = 0;
   bool ready = false;
@@ -18,6 +19,8 @@ struct UmmaWeights {
 int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st);
 void umma_weights_free(UmmaWeights& w);
 bool umma_available(const UmmaWeights& w);
+// Synchronises `st` and fails if the kernel raised a protocol error (bounded wait expired).
+int umma_check_status(const UmmaWeights& w, cudaStream_t st);
 int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, const float* rays_o, const float* rays_d,
                     const float* z, int64_t m, int s, float* out, cudaStream_t st);
 

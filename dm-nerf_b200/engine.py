@@ -68,6 +68,10 @@ class Context:
         self._keepalive[slot] = params
         return ins_num
 
+    def sync_check(self):
+        """Synchronise the current stream and raise if any native kernel reported an asynchronous failure."""
+        _lib.check(self.lib.dmnerf_sync_check(self.handle, self.stream()), "dmnerf_sync_check")
+
     def slot_for(self, model):
         """Slot to evaluate `model` alone (DM_NeRF.forward): reuse a slot it already occupies."""
         for s in (1, 0):

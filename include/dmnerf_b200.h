@@ -118,6 +118,10 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
 DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* io_host, int64_t n_rays, int n_coarse,
                                int n_importance, int flags, int impl, void* stream);
 
+/* Synchronise `stream` and report any asynchronous failure of the kernels launched through `ctx` (CUDA errors and
+ * the tensor-core kernel's bounded-wait protocol check). */
+DMNERF_API int dmnerf_sync_check(dmnerf_ctx* ctx, void* stream);
+
 /* Per-stage device timing of dmnerf_render_forward (CUDA events recorded on the launch stream around each stage):
  * enable != 0 switches recording on.  dmnerf_profile_read synchronises the last recorded events and writes the
  * elapsed milliseconds of the last render call: [0] coarse depths, [1] coarse network, [2] coarse composite,
