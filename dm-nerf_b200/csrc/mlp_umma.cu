@@ -167,94 +167,102 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
   const uint32_t tbase = misc->tmem_base;
 
   if (warp == 0) {
-    // =========================================================== weight producer (one lane)
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t ti = 0; ti < my_tiles; ++ti) {
-        int si = 0;
-        for (int t = 0; t < N_STEPS; ++t) {
-          const Step& st = prog.step[t];
-          const uint32_t bytes = (uint32_t)st.n * 128u;
-          for (int c = 0; c < 2 * st.n_chunks; ++c, ++si, ++it) {
-            const uint32_t slot = it % NS, ph = (it / NS) & 1;
-            if (!wait_or_abort(&misc->empty[slot], ph ^ 1, misc, 101, a.status)) goto done;
+    // =========================================================== weight producer (converged warp, one elected lane issues)
+    uint32_t it = 0;
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      int si = 0;
+      for (int t = 0; t < N_STEPS; ++t) {
+        const uint32_t bytes = (uint32_t)prog.step[t].n * 128u;
+        const int n_st = 2 * prog.step[t].n_chunks;
+        for (int c = 0; c < n_st; ++c, ++si, ++it) {
+          const uint32_t slot = it % NS, ph = (it / NS) & 1;
+          if (!wait_or_abort(&misc->empty[slot], ph ^ 1, misc, 101, a.status)) goto done;
+          if (elect_one()) {
             mbar_arrive_expect_tx(&misc->full[slot], bytes);
             bulk_g2s(smem + SM_RING + slot * STAGE_BYTES, a.image + prog.stage_off[si], bytes, &misc->full[slot]);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      uint32_t it = 0;
-      uint32_t seen_epi[2] = {0, 0}, seen_in = 0;
-      const uint32_t slot_base = smem_u32(smem + SM_SLOT), e_base = smem_u32(smem + SM_E), d_base = smem_u32(smem + SM_D);
-      const uint32_t ring_base = smem_u32(smem + SM_RING);
-      for (int64_t ti = 0; ti < my_tiles; ++ti) {
-        for (int t = 0; t < N_STEPS; ++t) {
-          const Step& st = prog.step[t];
-          const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
-          const uint32_t idesc = make_idesc_bf16(128, st.n);
-          const uint32_t d_tmem = tbase + TC_ACC + acc * 128;
-          // accumulator free: epilogue of global step g-2 finished
-          if (g >= 2) {
-            const uint32_t need = g / 2;        // completions of epi_done[acc] required
-            while (seen_epi[acc] < need) {
-              if (!wait_or_abort(&misc->epi_done[acc], seen_epi[acc] & 1, misc, 201, a.status)) goto done;
-              ++seen_epi[acc];
-            }
+    // =========================================================== MMA issuer (converged warp, one elected lane issues)
+    uint32_t it = 0;
+    uint32_t seen_epi0 = 0, seen_epi1 = 0, seen_in = 0;
+    const uint32_t slot_base = smem_u32(smem + SM_SLOT), e_base = smem_u32(smem + SM_E), d_base = smem_u32(smem + SM_D);
+    const uint32_t ring_base = smem_u32(smem + SM_RING);
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      for (int t = 0; t < N_STEPS; ++t) {
+        const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
+        const uint32_t idesc = make_idesc_bf16(128, prog.step[t].n);
+        const uint32_t d_tmem = tbase + TC_ACC + acc * 128;
+        const int n_chunks = prog.step[t].n_chunks;
+        // accumulator free: epilogue of global step g-2 finished  (g/2 completions of epi_done[acc])
+        if (g >= 2) {
+          uint32_t& seen = acc ? seen_epi1 : seen_epi0;
+          while (seen < g / 2) {
+            if (!wait_or_abort(&misc->epi_done[acc], seen & 1, misc, 201, a.status)) goto done;
+            ++seen;
           }
-          uint32_t first = 1;
-          for (int c = 0; c < st.n_chunks; ++c) {
-            const int kind = st.chunk[c];
-            // operand ready
-            if (st.dep[c] < 0) {
-              while (seen_in < (uint32_t)ti + 1) {
-                if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
-                ++seen_in;
-              }
-            } else {
-              const uint32_t gd = (uint32_t)ti * N_STEPS + st.dep[c], ad = gd & 1, need = gd / 2 + 1;
-              while (seen_epi[ad] < need) {
-                if (!wait_or_abort(&misc->epi_done[ad], seen_epi[ad] & 1, misc, 203, a.status)) goto done;
-                ++seen_epi[ad];
-              }
-            }
-            tc_fence_after();
-            uint32_t a_smem, a_tmem;
-            if (kind == CK_E) { a_smem = e_base; a_tmem = tbase + TC_E; }
-            else if (kind == CK_D) { a_smem = d_base; a_tmem = tbase + TC_D; }
-            else { a_smem = slot_base + kind * CHUNK_BYTES; a_tmem = tbase + TC_SLOT + kind * 32; }
-            const int ks = st.ksteps[c];
-            // ---- stage with W_hi: A_hi*W_hi (TS) + A_lo*W_hi (SS)
-            {
-              const uint32_t slot = it % NS, ph = (it / NS) & 1;
-              if (!wait_or_abort(&misc->full[slot], ph, misc, 204, a.status)) goto done;
-              tc_fence_after();
-              const uint32_t w = ring_base + slot * STAGE_BYTES;
-              for (int k = 0; k < ks; ++k) {
-                mma_ts(d_tmem, a_tmem + k * 8, make_sdesc_sw128(w + k * 32), idesc, first ? 0u : 1u);
-                first = 0;
-                mma_ss(d_tmem, make_sdesc_sw128(a_smem + k * 32), make_sdesc_sw128(w + k * 32), idesc, 1u);
-              }
-              mma_commit(&misc->empty[slot]);
-              ++it;
-            }
-            // ---- stage with W_lo: A_hi*W_lo (TS)
-            {
-              const uint32_t slot = it % NS, ph = (it / NS) & 1;
-              if (!wait_or_abort(&misc->full[slot], ph, misc, 205, a.status)) goto done;
-              tc_fence_after();
-              const uint32_t w = ring_base + slot * STAGE_BYTES;
-              for (int k = 0; k < ks; ++k)
-                mma_ts(d_tmem, a_tmem + k * 8, make_sdesc_sw128(w + k * 32), idesc, 1u);
-              mma_commit(&misc->empty[slot]);
-              ++it;
-            }
-          }
-          mma_commit(&misc->acc_full[acc]);
         }
+        uint32_t accum = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int kind = prog.step[t].chunk[c];
+          const int dep = prog.step[t].dep[c];
+          const int ks = prog.step[t].ksteps[c];
+          // operand ready
+          if (dep < 0) {
+            while (seen_in < (uint32_t)ti + 1) {
+              if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
+              ++seen_in;
+            }
+          } else {
+            const uint32_t gd = (uint32_t)ti * N_STEPS + dep, ad = gd & 1, need = gd / 2 + 1;
+            uint32_t& seen = ad ? seen_epi1 : seen_epi0;
+            while (seen < need) {
+              if (!wait_or_abort(&misc->epi_done[ad], seen & 1, misc, 203, a.status)) goto done;
+              ++seen;
+            }
+          }
+          uint32_t a_smem, a_tmem;
+          if (kind == CK_E) { a_smem = e_base; a_tmem = tbase + TC_E; }
+          else if (kind == CK_D) { a_smem = d_base; a_tmem = tbase + TC_D; }
+          else { a_smem = slot_base + kind * CHUNK_BYTES; a_tmem = tbase + TC_SLOT + kind * 32; }
+          const uint64_t a_desc = make_sdesc_sw128(a_smem);
+          // ---- stage with W_hi: A_hi*W_hi (TS) + A_lo*W_hi (SS)
+          {
+            const uint32_t slot = it % NS, ph = (it / NS) & 1;
+            if (!wait_or_abort(&misc->full[slot], ph, misc, 204, a.status)) goto done;
+            tc_fence_after();
+            const uint64_t w_desc = make_sdesc_sw128(ring_base + slot * STAGE_BYTES);
+            if (elect_one()) {
+              for (int k = 0; k < ks; ++k) {            // +2 on the descriptor = +32 bytes = 16 bf16 along K
+                mma_ts(d_tmem, a_tmem + k * 8, w_desc + 2 * k, idesc, accum);
+                accum = 1;
+                mma_ss(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, 1u);
+              }
+              mma_commit(&misc->empty[slot]);
+            }
+            accum = 1;
+            __syncwarp();
+            ++it;
+          }
+          // ---- stage with W_lo: A_hi*W_lo (TS)
+          {
+            const uint32_t slot = it % NS, ph = (it / NS) & 1;
+            if (!wait_or_abort(&misc->full[slot], ph, misc, 205, a.status)) goto done;
+            tc_fence_after();
+            const uint64_t w_desc = make_sdesc_sw128(ring_base + slot * STAGE_BYTES);
+            if (elect_one()) {
+              for (int k = 0; k < ks; ++k) mma_ts(d_tmem, a_tmem + k * 8, w_desc + 2 * k, idesc, 1u);
+              mma_commit(&misc->empty[slot]);
+            }
+            __syncwarp();
+            ++it;
+          }
+        }
+        if (elect_one()) mma_commit(&misc->acc_full[acc]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

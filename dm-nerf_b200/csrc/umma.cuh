@@ -17,6 +17,14 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (all 32 lanes must execute this).  Keeping the issuing warp converged lets the compiler hold
+// MMA operands in uniform registers instead of emitting a per-instruction R2UR waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- descriptors
 // Instruction descriptor, kind::f16, A/B = bf16 (K-major), D = fp32.  (cute/arch/mma_sm100_desc.hpp bit layout)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {

@@ -29,3 +29,23 @@ def frac_bad(got, ref, rtol, atol):
     got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     bad = np.abs(got - ref) > (atol + rtol * np.abs(ref))
     return float(bad.mean())
+
+
+def scale_err(got, ref):
+    """max |got-ref| / max |ref|: error relative to the tensor's own scale (outputs of a GEMM chain are sums with
+    cancellation, so an element-wise relative error is undefined near zero)."""
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+def rel_l2(got, ref):
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def raw_errs(got, ref):
+    """Parity metrics of a network output [..., C] per channel group (rgb logits | density | instance logits): the groups
+    have different scales (trained-like density weights are x30)."""
+    got = np.asarray(got); ref = np.asarray(ref)
+    groups = (slice(0, 3), slice(3, 4), slice(4, None))
+    return max(scale_err(got[..., g], ref[..., g]) for g in groups), max(rel_l2(got[..., g], ref[..., g]) for g in groups)
