@@ -92,7 +92,8 @@ struct KArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ bounded waits
-__device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+// Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
+__device__ __noinline__ bool slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*(volatile int32_t*)&misc->abort_flag) return false;
@@ -102,6 +103,54 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Mi
       return false;
     }
   }
+  return true;
+}
+__device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return slow_wait(bar, parity, misc, code, status);
+}
+
+// Position in the weight ring (warp-uniform).
+struct Ring {
+  uint32_t slot, phase;
+  __device__ __forceinline__ void advance() {
+    if (++slot == NS) { slot = 0; phase ^= 1; }
+  }
+};
+
+// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi on the TS path, A_lo*W_hi on the SS path) and
+// the W_lo stage (A_hi*W_lo, TS).  Executed by the whole (converged) MMA warp; one elected lane issues.
+template <int KS>
+__device__ __forceinline__ bool issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
+                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status) {
+  {
+    if (!wait_or_abort(&misc->full[ring.slot], ring.phase, misc, 204, status)) return false;
+    tc_fence_after();
+    const uint64_t w = make_sdesc_sw128(ring_base + ring.slot * STAGE_BYTES);
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
+        mma_ts(d_tmem, a_tmem + k * 8, w + 2 * k, idesc, k == 0 ? accum : 1u);
+        mma_ss(d_tmem, a_desc + 2 * k, w + 2 * k, idesc, 1u);
+      }
+      mma_commit(&misc->empty[ring.slot]);
+    }
+    __syncwarp();
+    ring.advance();
+  }
+  {
+    if (!wait_or_abort(&misc->full[ring.slot], ring.phase, misc, 205, status)) return false;
+    tc_fence_after();
+    const uint64_t w = make_sdesc_sw128(ring_base + ring.slot * STAGE_BYTES);
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, w + 2 * k, idesc, 1u);
+      mma_commit(&misc->empty[ring.slot]);
+    }
+    __syncwarp();
+    ring.advance();
+  }
+  accum = 1;
   return true;
 }
 
@@ -168,101 +217,103 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 
   if (warp == 0) {
     // =========================================================== weight producer (converged warp, one elected lane issues)
-    uint32_t it = 0;
+    Ring ring{0, 0};
+    const int n_stages = prog.n_stages;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      int si = 0;
-      for (int t = 0; t < N_STEPS; ++t) {
-        const uint32_t bytes = (uint32_t)prog.step[t].n * 128u;
-        const int n_st = 2 * prog.step[t].n_chunks;
-        for (int c = 0; c < n_st; ++c, ++si, ++it) {
-          const uint32_t slot = it % NS, ph = (it / NS) & 1;
-          if (!wait_or_abort(&misc->empty[slot], ph ^ 1, misc, 101, a.status)) goto done;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&misc->full[slot], bytes);
-            bulk_g2s(smem + SM_RING + slot * STAGE_BYTES, a.image + prog.stage_off[si], bytes, &misc->full[slot]);
-          }
-          __syncwarp();
+      for (int si = 0; si < n_stages; ++si) {
+        const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
+        if (!wait_or_abort(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status)) goto done;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
+          bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, a.image + off, bytes, &misc->full[ring.slot]);
         }
+        __syncwarp();
+        ring.advance();
       }
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer (converged warp, one elected lane issues)
-    uint32_t it = 0;
-    uint32_t seen_epi0 = 0, seen_epi1 = 0, seen_in = 0;
-    const uint32_t slot_base = smem_u32(smem + SM_SLOT), e_base = smem_u32(smem + SM_E), d_base = smem_u32(smem + SM_D);
-    const uint32_t ring_base = smem_u32(smem + SM_RING);
+    // The per-tile schedule is written out structurally (it mirrors build_program(), which drives the producer, the
+    // epilogue and the weight packing): 8 trunk layers x 2 half-steps, two folded hidden heads, two output heads.
+    Ring ring{0, 0};
+    uint32_t seen0 = 0, seen1 = 0, seen_in = 0;
+    const uint32_t slot_base = smem_u32(smem + SM_SLOT), ring_base = smem_u32(smem + SM_RING);
+    const uint64_t e_desc = make_sdesc_sw128(smem_u32(smem + SM_E)), d_desc = make_sdesc_sw128(smem_u32(smem + SM_D));
+    const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc16 = make_idesc_bf16(128, 16);
+    const uint32_t idesc_ins = make_idesc_bf16(128, prog.step[N_STEPS - 1].n);
+    // epilogue of global step gd finished (its output slot is readable, its accumulator is drained)
+    auto need_epi = [&](uint32_t gd) -> bool {
+      uint32_t& seen = (gd & 1) ? seen1 : seen0;
+      const uint32_t need = gd / 2 + 1;
+      while (seen < need) {
+        if (!wait_or_abort(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status)) return false;
+        ++seen;
+      }
+      tc_fence_after();
+      return true;
+    };
+    auto slot_chunk = [&](int slot, int j, uint32_t d_tmem, uint32_t idesc, uint32_t& accum) -> bool {
+      return issue_chunk<4>(misc, ring, ring_base, make_sdesc_sw128(slot_base + (slot * 2 + j) * CHUNK_BYTES),
+                            tbase + TC_SLOT + (slot * 2 + j) * 32, d_tmem, idesc, accum, a.status);
+    };
+    auto finish = [&](uint32_t acc) {
+      if (elect_one()) mma_commit(&misc->acc_full[acc]);
+      __syncwarp();
+    };
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      for (int t = 0; t < N_STEPS; ++t) {
-        const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
-        const uint32_t idesc = make_idesc_bf16(128, prog.step[t].n);
-        const uint32_t d_tmem = tbase + TC_ACC + acc * 128;
-        const int n_chunks = prog.step[t].n_chunks;
-        // accumulator free: epilogue of global step g-2 finished  (g/2 completions of epi_done[acc])
-        if (g >= 2) {
-          uint32_t& seen = acc ? seen_epi1 : seen_epi0;
-          while (seen < g / 2) {
-            if (!wait_or_abort(&misc->epi_done[acc], seen & 1, misc, 201, a.status)) goto done;
-            ++seen;
-          }
+      const uint32_t g0 = (uint32_t)ti * N_STEPS;
+      // ---- layer 0: E -> slots 0, 1
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t g = g0 + h;
+        if (g >= 2 && !need_epi(g - 2)) goto done;
+        while (seen_in < (uint32_t)ti + 1) {
+          if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
+          ++seen_in;
         }
+        tc_fence_after();
         uint32_t accum = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-          const int kind = prog.step[t].chunk[c];
-          const int dep = prog.step[t].dep[c];
-          const int ks = prog.step[t].ksteps[c];
-          // operand ready
-          if (dep < 0) {
-            while (seen_in < (uint32_t)ti + 1) {
-              if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
-              ++seen_in;
-            }
-          } else {
-            const uint32_t gd = (uint32_t)ti * N_STEPS + dep, ad = gd & 1, need = gd / 2 + 1;
-            uint32_t& seen = ad ? seen_epi1 : seen_epi0;
-            while (seen < need) {
-              if (!wait_or_abort(&misc->epi_done[ad], seen & 1, misc, 203, a.status)) goto done;
-              ++seen;
-            }
-          }
-          uint32_t a_smem, a_tmem;
-          if (kind == CK_E) { a_smem = e_base; a_tmem = tbase + TC_E; }
-          else if (kind == CK_D) { a_smem = d_base; a_tmem = tbase + TC_D; }
-          else { a_smem = slot_base + kind * CHUNK_BYTES; a_tmem = tbase + TC_SLOT + kind * 32; }
-          const uint64_t a_desc = make_sdesc_sw128(a_smem);
-          // ---- stage with W_hi: A_hi*W_hi (TS) + A_lo*W_hi (SS)
-          {
-            const uint32_t slot = it % NS, ph = (it / NS) & 1;
-            if (!wait_or_abort(&misc->full[slot], ph, misc, 204, a.status)) goto done;
-            tc_fence_after();
-            const uint64_t w_desc = make_sdesc_sw128(ring_base + slot * STAGE_BYTES);
-            if (elect_one()) {
-              for (int k = 0; k < ks; ++k) {            // +2 on the descriptor = +32 bytes = 16 bf16 along K
-                mma_ts(d_tmem, a_tmem + k * 8, w_desc + 2 * k, idesc, accum);
-                accum = 1;
-                mma_ss(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, 1u);
-              }
-              mma_commit(&misc->empty[slot]);
-            }
-            accum = 1;
-            __syncwarp();
-            ++it;
-          }
-          // ---- stage with W_lo: A_hi*W_lo (TS)
-          {
-            const uint32_t slot = it % NS, ph = (it / NS) & 1;
-            if (!wait_or_abort(&misc->full[slot], ph, misc, 205, a.status)) goto done;
-            tc_fence_after();
-            const uint64_t w_desc = make_sdesc_sw128(ring_base + slot * STAGE_BYTES);
-            if (elect_one()) {
-              for (int k = 0; k < ks; ++k) mma_ts(d_tmem, a_tmem + k * 8, w_desc + 2 * k, idesc, 1u);
-              mma_commit(&misc->empty[slot]);
-            }
-            __syncwarp();
-            ++it;
-          }
+        if (!issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, tbase + TC_ACC + h * 128, idesc128, accum, a.status)) goto done;
+        finish(h);
+      }
+      int sa = 0, sb = 1, sf = 2;                    // slots holding K-halves 0 / 1 of the activation, free slot
+      // ---- layers 1..7
+      for (int l = 1; l < 8; ++l) {
+        for (uint32_t h = 0; h < 2; ++h) {
+          const uint32_t g = g0 + 2 * l + h, d_tmem = tbase + TC_ACC + h * 128;
+          if (!need_epi(g - 2)) goto done;
+          uint32_t accum = 0;
+          if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
+          if (h == 0 && !need_epi(g - 1)) goto done;
+          if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
+          if (l == 5 && !issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, d_tmem, idesc128, accum, a.status)) goto done;
+          finish(h);
         }
-        if (elect_one()) mma_commit(&misc->acc_full[acc]);
-        __syncwarp();
+        const int t = sb; sb = sa; sa = sf; sf = t;   // (a, b, f) <- (f, a, b)
+      }
+      {
+        // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> free slot
+        uint32_t accum = 0, d_tmem = tbase + TC_ACC;
+        if (!need_epi(g0 + 14)) goto done;
+        if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
+        if (!need_epi(g0 + 15)) goto done;
+        if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
+        if (!issue_chunk<2>(misc, ring, ring_base, d_desc, tbase + TC_D, d_tmem, idesc128, accum, a.status)) goto done;
+        finish(0);
+        // ---- folded instance hidden layer (step 17, acc 1): h -> slot of K-half 0
+        accum = 0; d_tmem = tbase + TC_ACC + 128;
+        if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
+        if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
+        finish(1);
+        // ---- rgb head (step 18, acc 0, N=16) on the colour hidden slot
+        accum = 0; d_tmem = tbase + TC_ACC;
+        if (!need_epi(g0 + 16)) goto done;
+        if (!slot_chunk(sf, 0, d_tmem, idesc16, accum) || !slot_chunk(sf, 1, d_tmem, idesc16, accum)) goto done;
+        finish(0);
+        // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden slot
+        accum = 0; d_tmem = tbase + TC_ACC + 128;
+        if (!need_epi(g0 + 17)) goto done;
+        if (!slot_chunk(sa, 0, d_tmem, idesc_ins, accum) || !slot_chunk(sa, 1, d_tmem, idesc_ins, accum)) goto done;
+        finish(1);
       }
     }
   } else if (warp >= 4) {
@@ -466,6 +517,7 @@ static void build_program(Program& P, int ins_num) {
   int si = 0;
   for (int i = 0; i < N_STEPS; ++i)
     for (int c = 0; c < 2 * P.step[i].n_chunks; ++c) { P.stage_off[si++] = off; off += (uint32_t)P.step[i].n * 128u; }
+  P.stage_off[si] = off;               // sentinel: total image size
   P.n_stages = si;
 }
 
@@ -570,8 +622,7 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
     build_program(x->prog, p.ins_num);
     w.extra = x;
     w.ins_num = p.ins_num;
-    const uint32_t last = x->prog.n_stages - 1;
-    w.image_bytes = x->prog.stage_off[last] + (size_t)x->prog.step[N_STEPS - 1].n * 128;
+    w.image_bytes = x->prog.stage_off[x->prog.n_stages];
     DMN_CUDA(cudaMalloc(&w.image, w.image_bytes));
     DMN_CUDA(cudaMalloc((void**)&w.bias, (N_STEPS * 128 + 260) * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_w_rgb, 128 * 283 * sizeof(float)));
