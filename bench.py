@@ -297,8 +297,9 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "fine-network fused MLP (192 samples/ray)", "achieved": achieved_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": peak_src,
-                "note": "algorithmic FLOPs (2*192*MACs/sample per ray); the kernel runs 3 bf16 tensor passes per "
-                        "algorithmic MAC (hi/lo operand split for fp32 parity), so frac tops out near 1/3 on the tensor path",
+                "note": "algorithmic FLOPs (2*192*693504 MACs per ray, the reference's layer shapes); the kernel issues 3 bf16 "
+                        "tensor passes (hi/lo operand split for fp32 parity) over 565248 padded+folded MACs per sample, so "
+                        "frac cannot exceed 693504/(3*565248) = 0.409 of the bf16 peak",
                 "stage_ms_per_step": {k: float(v / args.steps) for k, v in
                                       zip(("coarse_z", "coarse_mlp", "coarse_composite", "hier_sample", "fine_mlp",
                                            "fine_composite"), stage_ms)}}

@@ -1,0 +1,65 @@
+"""Condense gpurun_out/ ncu artefacts into small tracked text files under profiles/ (run here, no GPU needed).
+    python tools/summarize_profiles.py r01"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = os.path.join(ROOT, "profiles")
+os.makedirs(out, exist_ok=True)
+go = os.path.join(ROOT, "gpurun_out")
+
+# 1. launch list (gpu__time_duration per launch) -> per-kernel share
+lp = os.path.join(go, "launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
+    hdr = rows[0]
+    ik, iv, ig, ib = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        a = agg.setdefault(r[ik].split("(")[0], [0, 0.0, r[ig], r[ib]])
+        a[0] += 1
+        a[1] += float(r[iv].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(out, "%s_launches.md" % tag), "w") as f:
+        f.write("# ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (gpu__time_duration.sum, "
+                "--clock-control none; cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | grid | block |\n|---|---|---|---|---|---|\n")
+        for k, (n, t, g, b) in agg.items():
+            f.write("| `%s` | %d | %.3f | %.1f%% | %s | %s |\n" % (k, n, t / 1e6, 100 * t / tot, g, b))
+    print("wrote launches summary")
+
+# 2. full-set capture of the fine-network kernel -> key metrics
+rp = os.path.join(go, "prof_umma.ncu-rep")
+if os.path.exists(rp):
+    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.sum",
+            "lts__t_sectors_srcunit_tex.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "sm__inst_executed.sum"]
+    got = {}
+    for h, u, v in zip(hdr, units, vals):
+        for w in want:
+            if h == w or h.endswith("." + w):
+                got[w] = (v, u)
+    with open(os.path.join(out, "%s_ncu_fine_mlp.md" % tag), "w") as f:
+        f.write("# ncu --set full, one launch of `mlp_umma_kernel` (fine network, 37 888 rays x 192 samples = 56 832 tiles)\n\n"
+                "Captured with `tools/gpu_prof.sh` (`--clock-control none --import-source on`); the .ncu-rep stays in gpurun_out/.\n\n"
+                "| metric | value | unit |\n|---|---|---|\n")
+        for w in want:
+            if w in got:
+                f.write("| %s | %s | %s |\n" % (w, got[w][0], got[w][1]))
+        try:
+            dr = float(got["dram__bytes_read.sum"][0].replace(",", "")); dw = float(got["dram__bytes_write.sum"][0].replace(",", ""))
+            f.write("\nDRAM traffic per launch: read %s %s + write %s %s.\n" % (got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"]))
+        except Exception:
+            pass
+    print("wrote ncu summary")
