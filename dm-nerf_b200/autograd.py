@@ -23,8 +23,8 @@ def mlp_forward(model, x, impl=_lib.IMPL_AUTO):
     if not x.is_cuda:
         raise RuntimeError("DM_NeRF.forward: expected a CUDA tensor (no CPU fallback)")
     if _needs_grad(model, x):
-        from .backward import MLPFunction
-        return MLPFunction.apply(model, x, impl)
+        from .backward import mlp_forward_grad
+        return mlp_forward_grad(model, x, impl)
     ctx = get_context(x.device)
     slot = ctx.slot_for(model)
     ins_num = ctx.bind(slot, model)

@@ -124,7 +124,7 @@ static int mlp_dispatch(dmnerf_ctx* ctx, int net, const float* x, const float* r
   if (impl == DMNERF_IMPL_AUTO) impl = umma_available(ctx->packed[net]) ? DMNERF_IMPL_UMMA : DMNERF_IMPL_SIMT;
   if (impl == DMNERF_IMPL_UMMA)
     return launch_mlp_umma(ctx->packed[net], ctx->net[net], x, ro, rd, z, m, s, out, st);
-  return launch_mlp_simt(ctx->net[net], x, ro, rd, z, m, s, out, st);
+  return launch_mlp_simt(ctx->net[net], x, ro, rd, z, m, s, out, nullptr, st);
 }
 
 DMNERF_API int dmnerf_mlp_forward(dmnerf_ctx* ctx, int net, const float* x, int64_t m, float* out, int impl, void* stream) {
@@ -157,6 +157,52 @@ DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int
   DMN_CHECK(n >= 0, "sort_concat: negative ray count");
   DMN_CHECK(n == 0 || ((a || na == 0) && (b || nb == 0) && out), "sort_concat: NULL buffer");
   return launch_sort_concat(a, b, n, na, nb, out, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,
+                               void* stream) {
+  DMN_CHECK(n >= 0 && s >= 1, "stratify: bad sizes");
+  DMN_CHECK(n == 0 || (z_in && z_out), "stratify: NULL buffer");
+  DMN_CHECK(z_row_stride == 0 || z_row_stride >= s, "stratify: bad z_row_stride");
+  return launch_prep_z(z_in, z_row_stride, t_rand, n, s, z_out, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int n_importance,
+                                  float* z_fine, void* stream) {
+  DMN_CHECK(n >= 0, "hier_sample: negative ray count");
+  DMN_CHECK(n == 0 || (z_c && w_c && z_fine), "hier_sample: NULL buffer");
+  return launch_hier_sample(z_c, w_c, u, n, s, n_importance, z_fine, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_act_floats_per_sample(void) { return ACT_FLOATS_PER_SAMPLE; }
+DMNERF_API int64_t dmnerf_mlp_backward_scratch_floats(int64_t m) { return (int64_t)mlp_backward_scratch_floats(m); }
+
+DMNERF_API int dmnerf_mlp_forward_train(dmnerf_ctx* ctx, int net, const float* x, const float* rays_o, const float* rays_d,
+                                        const float* z, int64_t m, int s, float* out, float* acts, void* stream) {
+  DMN_CHECK(ctx != nullptr, "mlp_forward_train: ctx is NULL");
+  DMN_CHECK(net == 0 || net == 1, "mlp_forward_train: net must be 0 or 1");
+  DMN_CHECK(m >= 0 && s >= 1, "mlp_forward_train: bad sizes");
+  if (m == 0) return 0;
+  DMN_CHECK(out && acts, "mlp_forward_train: out / acts is NULL");
+  return launch_mlp_simt(ctx->net[net], x, rays_o, rays_d, z, m, s, out, acts, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const float* d_out, int64_t m, float* const* grads,
+                                   float* scratch, void* stream) {
+  DMN_CHECK(ctx != nullptr, "mlp_backward: ctx is NULL");
+  DMN_CHECK(net == 0 || net == 1, "mlp_backward: net must be 0 or 1");
+  DMN_CHECK(m >= 0 && grads, "mlp_backward: bad arguments");
+  DMN_CHECK(m == 0 || (acts && d_out && scratch), "mlp_backward: NULL buffer");
+  return launch_mlp_backward(ctx->net[net], acts, d_out, m, grads, scratch, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c,
+                                         int keep_all_ins, const float* g_rgb, const float* g_depth, const float* g_acc,
+                                         const float* g_ins, const float* g_weights, float* d_raw, int accumulate, void* stream) {
+  DMN_CHECK(n >= 0, "composite_backward: negative ray count");
+  DMN_CHECK(n == 0 || (raw && z && rays_d && d_raw), "composite_backward: NULL buffer");
+  return launch_composite_backward(raw, z, rays_d, n, s, c, keep_all_ins, g_rgb, g_depth, g_acc, g_ins, g_weights, d_raw,
+                                   accumulate, (cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n, int S, int NI, int flags, int impl,

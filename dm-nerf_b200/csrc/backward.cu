@@ -1,0 +1,342 @@
+// Backward of the render path (BASELINE config 4: training step, reference train_dmsr.py:62-64), fp32 CUDA cores.
+//
+//   * composite_backward_kernel: d(rgb_map, depth_map, acc_map, ins_map) -> d raw, one warp per ray.  The transmittance
+//     product is differentiated in closed form with a reverse warp scan:  dL/dalpha_i = gw_i T_i - (sum_{j>i} gw_j w_j) / f_i.
+//     Honours the reference's detach topology (render.py:22-23: the instance map sees detached weights).
+//   * MLP backward over the activations saved by the training forward (mlp_simt.cu, ActPlanes): per layer
+//       dX = (dY W) (.) relu-mask   -> gemm_nn_kernel        dW += dY^T X -> gemm_tn_kernel (split over samples, fp32 atomics)
+//       db += column sums of dY     -> colsum_kernel
+//     with the reference's gradient routing (dm_nerf.py:95: the instance branch reads h.detach(), so it contributes to
+//     ins_feature_linear and below only).
+#include "ray_ops.cuh"
+
+namespace dmnerf {
+
+// ================================================================================================ composite backward
+constexpr int CB_WARPS = 4;
+
+__global__ void composite_backward_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                          const float* __restrict__ rays_d, int64_t n, int S, int C, int keep_all,
+                                          const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+                                          const float* __restrict__ g_acc, const float* __restrict__ g_ins,
+                                          const float* __restrict__ g_w, float* __restrict__ d_raw, int accumulate) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * CB_WARPS + warp;
+  if (ray >= n) return;
+  float* w = smem + (size_t)warp * 5 * S;      // weights
+  float* T = w + S;                            // exclusive transmittance
+  float* fi = T + S;                           // 1 - alpha + 1e-10
+  float* ex = fi + S;                          // delta_i * exp(-sigma_i delta_i)  (= d alpha / d sigma)
+  float* gw = ex + S;                          // dL/dw_i
+  const float* zr = z + ray * S;
+  const float* rr = raw + ray * S * C;
+  float* dr = d_raw + ray * S * C;
+  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const int n_ins_out = keep_all ? C - 4 : C - 5;
+
+  // ---- forward recompute (render.py:7-18) keeping alpha-chain intermediates
+  float carry = 1.0f;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    float alpha = 0.0f, f = 1.0f, dads = 0.0f;
+    if (i < S) {
+      const float dist = ((i == S - 1) ? 1e10f : zr[i + 1] - zr[i]) * dnorm;
+      const float sg = fmaxf(rr[(size_t)i * C + 3], 0.0f);
+      const float e = expf(-sg * dist);
+      alpha = 1.0f - e;
+      f = (1.0f - alpha) + 1e-10f;
+      dads = dist * e;
+    }
+    const float incl = warp_scan_mul(f, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    if (i < S) { T[i] = carry * excl; w[i] = alpha * T[i]; fi[i] = f; ex[i] = dads; }
+    carry *= __shfl_sync(FULL, incl, 31);
+  }
+  __syncwarp();
+
+  // ---- dL/dw_i and the colour-logit gradients
+  const float gr0 = g_rgb ? g_rgb[ray * 3] : 0.0f, gr1 = g_rgb ? g_rgb[ray * 3 + 1] : 0.0f, gr2 = g_rgb ? g_rgb[ray * 3 + 2] : 0.0f;
+  const float gd = g_depth ? g_depth[ray] : 0.0f, ga = g_acc ? g_acc[ray] : 0.0f;
+  for (int i = lane; i < S; i += 32) {
+    const float s0 = sigmoidf_acc(rr[(size_t)i * C]), s1 = sigmoidf_acc(rr[(size_t)i * C + 1]), s2 = sigmoidf_acc(rr[(size_t)i * C + 2]);
+    gw[i] = gr0 * s0 + gr1 * s1 + gr2 * s2 + gd * zr[i] + ga + (g_w ? g_w[ray * S + i] : 0.0f);
+    const float wi = w[i];
+    float v0 = gr0 * wi * s0 * (1.0f - s0), v1 = gr1 * wi * s1 * (1.0f - s1), v2 = gr2 * wi * s2 * (1.0f - s2);
+    if (accumulate) { v0 += dr[(size_t)i * C]; v1 += dr[(size_t)i * C + 1]; v2 += dr[(size_t)i * C + 2]; }
+    dr[(size_t)i * C] = v0; dr[(size_t)i * C + 1] = v1; dr[(size_t)i * C + 2] = v2;
+  }
+  __syncwarp();
+
+  // ---- instance logits: ins_map_k = sigmoid(sum_i w_i raw_ik); weights are detached unless keep_all (manipulator_render)
+  for (int k = lane; k < C - 4; k += 32) {
+    float a = 0.0f;
+    for (int i = 0; i < S; ++i) a += w[i] * rr[(size_t)i * C + 4 + k];
+    const float sk = sigmoidf_acc(a);
+    const float gk = (g_ins && k < n_ins_out) ? g_ins[ray * n_ins_out + k] * sk * (1.0f - sk) : 0.0f;
+    for (int i = 0; i < S; ++i) {
+      float v = gk * w[i];
+      if (accumulate) v += dr[(size_t)i * C + 4 + k];
+      dr[(size_t)i * C + 4 + k] = v;
+    }
+    if (keep_all && gk != 0.0f)
+      for (int i = 0; i < S; ++i) atomicAdd(&gw[i], gk * rr[(size_t)i * C + 4 + k]);   // shared-memory atomics
+  }
+  __syncwarp();
+
+  // ---- density: reverse exclusive scan of gw_j w_j, then the closed-form d alpha
+  float suffix = 0.0f;                                   // sum over samples after the current chunk
+  const int n_chunks = (S + 31) / 32;
+  for (int cb = n_chunks - 1; cb >= 0; --cb) {
+    const int i = cb * 32 + lane;
+    const float p = (i < S) ? gw[i] * w[i] : 0.0f;
+    float incl = p;                                      // inclusive suffix sum inside the chunk
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_down_sync(FULL, incl, d);
+      if (lane + d < 32) incl += o;
+    }
+    const float R = suffix + (incl - p);                 // sum_{j > i} gw_j w_j
+    if (i < S) {
+      const float dalpha = gw[i] * T[i] - R / fi[i];
+      float v = (rr[(size_t)i * C + 3] > 0.0f) ? dalpha * ex[i] : 0.0f;
+      if (accumulate) v += dr[(size_t)i * C + 3];
+      dr[(size_t)i * C + 3] = v;
+    }
+    suffix += __shfl_sync(FULL, incl, 0);
+  }
+}
+
+int launch_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all,
+                              const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_ins,
+                              const float* g_weights, float* d_raw, int accumulate, cudaStream_t st) {
+  DMN_CHECK(s >= 1 && s <= 2048, "composite_backward: n_samples=%d out of range [1,2048]", s);
+  DMN_CHECK(c >= 5 && c <= 4 + DMNERF_MAX_INS + 1, "composite_backward: channels=%d out of range", c);
+  if (n == 0) return 0;
+  const size_t smem = (size_t)CB_WARPS * 5 * s * sizeof(float);
+  if (smem > 48 * 1024)
+    DMN_CUDA(cudaFuncSetAttribute(composite_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  composite_backward_kernel<<<(unsigned)((n + CB_WARPS - 1) / CB_WARPS), CB_WARPS * 32, smem, st>>>(
+      raw, z, rays_d, n, s, c, keep_all, g_rgb, g_depth, g_acc, g_ins, g_weights, d_raw, accumulate);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+// ================================================================================================ fp32 GEMMs
+constexpr int GT = 64;      // output tile GT x GT
+constexpr int GK = 16;      // inner chunk
+
+// C[m, k] (= | +=) sum_n A[m, n] B[n, k];  optionally C = (mask[m, k] > 0) ? C : 0   (mask shares ldc).
+__global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                      float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int accumulate,
+                                                      const float* __restrict__ mask) {
+  __shared__ float As[GK][GT + 1];
+  __shared__ float Bs[GK][GT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GT;
+  const int k0 = blockIdx.y * GT;
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < N; n0 += GK) {
+    for (int idx = tid; idx < GT * GK; idx += 256) {           // A tile [GT rows][GK inner], coalesced along inner
+      const int r = idx / GK, c = idx % GK;
+      const int64_t m = m0 + r;
+      As[c][r] = (m < M && n0 + c < N) ? A[m * lda + n0 + c] : 0.0f;
+    }
+    for (int idx = tid; idx < GK * GT; idx += 256) {           // B tile [GK inner][GT cols]
+      const int r = idx / GT, c = idx % GT;
+      Bs[r][c] = (n0 + r < N && k0 + c < K) ? B[(size_t)(n0 + r) * ldb + k0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx + 16 * j;
+      if (k >= K) continue;
+      float v = acc[i][j];
+      if (accumulate) v += Cm[m * ldc + k];
+      if (mask && !(mask[m * ldc + k] > 0.0f)) v = 0.0f;
+      Cm[m * ldc + k] = v;
+    }
+  }
+}
+
+// C[n, k] += sum_{m in split} A[m, n] B[m, k]   (C zero-initialised by the caller; fp32 atomics across splits)
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                      float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int64_t rows_per_split) {
+  __shared__ float As[GK][GT];
+  __shared__ float Bs[GK][GT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * GT, k0 = blockIdx.y * GT;
+  const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t me = (mb + rows_per_split < M) ? mb + rows_per_split : M;
+  float acc[4][4] = {};
+  for (int64_t m0 = mb; m0 < me; m0 += GK) {
+    for (int idx = tid; idx < GK * GT; idx += 256) {
+      const int r = idx / GT, c = idx % GT;
+      const int64_t m = m0 + r;
+      As[r][c] = (m < me && n0 + c < N) ? A[m * lda + n0 + c] : 0.0f;
+      Bs[r][c] = (m < me && k0 + c < K) ? B[m * ldb + k0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int nn = n0 + ty + 16 * i;
+    if (nn >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx + 16 * j;
+      if (k < K) atomicAdd(&Cm[(size_t)nn * ldc + k], acc[i][j]);
+    }
+  }
+}
+
+// out[n] += sum_m A[m, n]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int lda, float* __restrict__ out, int64_t M, int N,
+                                                     int64_t rows_per_block) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  const int64_t mb = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t me = (mb + rows_per_block < M) ? mb + rows_per_block : M;
+  float s = 0.0f;
+  if (c < N)
+    for (int64_t m = mb + r; m < me; m += 8) s += A[m * lda + c];
+  red[r][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (r == 0 && c < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    atomicAdd(&out[c], t);
+  }
+}
+
+static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, int accumulate,
+                   const float* mask, cudaStream_t st) {
+  dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((K + GT - 1) / GT));
+  gemm_nn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, mask);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st) {
+  const int tiles = ((N + GT - 1) / GT) * ((K + GT - 1) / GT);
+  int64_t splits = (4 * 148 + tiles - 1) / tiles;
+  int64_t rows = (M + splits - 1) / splits;
+  rows = ((rows + GK - 1) / GK) * GK;
+  if (rows < 256) rows = 256;
+  splits = (M + rows - 1) / rows;
+  dim3 grid((unsigned)((N + GT - 1) / GT), (unsigned)((K + GT - 1) / GT), (unsigned)splits);
+  gemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rows);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStream_t st) {
+  const int64_t rows = 2048;
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + rows - 1) / rows));
+  colsum_kernel<<<grid, 256, 0, st>>>(A, lda, out, M, N, rows);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (2 * 128 + 4 * 256); }
+
+// grads: 30 device pointers in state_dict order (weight, bias per layer); overwritten with the gradient of this call.
+int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads, float* scratch,
+                        cudaStream_t st) {
+  DMN_CHECK(p.bound, "mlp_backward: weights not bound");
+  const int ins1 = p.ins_num + 1, C = 4 + ins1;
+  for (int l = 0; l < N_LAYERS; ++l) {
+    DMN_CHECK(grads[2 * l] && grads[2 * l + 1], "mlp_backward: gradient buffer %d is NULL", 2 * l);
+    DMN_CUDA(cudaMemsetAsync(grads[2 * l], 0, (size_t)layer_out(l, p.ins_num) * layer_in(l) * sizeof(float), st));
+    DMN_CUDA(cudaMemsetAsync(grads[2 * l + 1], 0, (size_t)layer_out(l, p.ins_num) * sizeof(float), st));
+  }
+  if (m == 0) return 0;
+  const ActPlanes ap = act_planes(acts, m);
+  float* S1 = scratch;                  // d rgb_hid  [m,128]
+  float* S2 = S1 + m * 128;             // d ins_hid  [m,128]
+  float* S3 = S2 + m * 128;             // d rgb_feat [m,256]
+  float* S4 = S3 + m * 256;             // d ins_feat [m,256]
+  float* G = S4 + m * 256;              // d h (masked), ping
+  float* G2 = G + m * 256;              //               pong
+  auto gw = [&](int l) { return grads[2 * l]; };
+  auto gb = [&](int l) { return grads[2 * l + 1]; };
+  int rc = 0;
+#define R(x) do { if ((rc = (x))) return rc; } while (0)
+  const float* d_rgb = d_out;           // [m, 3]       lda = C
+  const float* d_sig = d_out + 3;       // [m, 1]
+  const float* d_ins = d_out + 4;       // [m, ins1]
+  // ---- output layers (dm_nerf.py:101-103)
+  R(gemm_tn(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, m, 3, 128, st));     R(colsum(d_rgb, C, gb(L_RGB_OUT), m, 3, st));
+  R(gemm_tn(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, m, ins1, 128, st));  R(colsum(d_ins, C, gb(L_INS_OUT), m, ins1, st));
+  R(gemm_tn(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, m, 1, 256, st));        R(colsum(d_sig, C, gb(L_DENSITY), m, 1, st));
+  R(gemm_nn(d_rgb, C, p.w[L_RGB_OUT], 128, S1, 128, m, 3, 128, 0, ap.rgb_hid, st));       // through ReLU of rgb_hid
+  R(gemm_nn(d_ins, C, p.w[L_INS_OUT], 128, S2, 128, m, ins1, 128, 0, ap.ins_hid, st));    // through ReLU of ins_hid
+  // ---- hidden head layers (dm_nerf.py:90-99)
+  R(gemm_tn(S1, 128, ap.rgb_feat, 256, gw(L_RGB_HID), 283, m, 128, 256, st));
+  R(gemm_tn(S1, 128, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));
+  R(colsum(S1, 128, gb(L_RGB_HID), m, 128, st));
+  R(gemm_tn(S2, 128, ap.ins_feat, 256, gw(L_INS_HID), 256, m, 128, 256, st));   R(colsum(S2, 128, gb(L_INS_HID), m, 128, st));
+  R(gemm_nn(S1, 128, p.w[L_RGB_HID], 283, S3, 256, m, 128, 256, 0, nullptr, st));         // d rgb_feature (no activation)
+  R(gemm_nn(S2, 128, p.w[L_INS_HID], 256, S4, 256, m, 128, 256, 0, nullptr, st));         // d ins_feature
+  // ---- feature layers on the final trunk activation (dm_nerf.py:89,95-96)
+  R(gemm_tn(S3, 256, ap.h[7], 256, gw(L_RGB_FEAT), 256, m, 256, 256, st));      R(colsum(S3, 256, gb(L_RGB_FEAT), m, 256, st));
+  R(gemm_tn(S4, 256, ap.h[7], 256, gw(L_INS_FEAT), 256, m, 256, 256, st));      R(colsum(S4, 256, gb(L_INS_FEAT), m, 256, st));
+  // d h8 = d sigma (x) w_density + d rgb_feat W_rgb_feat   (the instance branch saw h.detach()), then ReLU mask of layer 7
+  R(gemm_nn(d_sig, C, p.w[L_DENSITY], 256, G, 256, m, 1, 256, 0, nullptr, st));
+  R(gemm_nn(S3, 256, p.w[L_RGB_FEAT], 256, G, 256, m, 256, 256, 1, ap.h[7], st));
+  // ---- trunk, layers 7..0 (dm_nerf.py:83-87)
+  float* cur = G;
+  float* nxt = G2;
+  for (int l = 7; l >= 0; --l) {
+    const int kin = layer_in(l);
+    if (l == 0) {
+      R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st));
+    } else {
+      R(gemm_tn(cur, 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st));
+      if (l == 5) R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));   // skip input [h, pts]
+    }
+    R(colsum(cur, 256, gb(l), m, 256, st));
+    if (l > 0) {
+      R(gemm_nn(cur, 256, p.w[l], kin, nxt, 256, m, 256, 256, 0, ap.h[l - 1], st));
+      float* t = cur; cur = nxt; nxt = t;
+    }
+  }
+#undef R
+  return 0;
+}
+
+}  // namespace dmnerf

@@ -45,6 +45,24 @@ __host__ __device__ inline int layer_in(int l) {
   return l == 0 ? CH_POS : (l == 5 ? W_HID + CH_POS : (l == L_RGB_HID ? W_HID + CH_DIR : (l >= L_INS_OUT ? W_HID / 2 : W_HID)));
 }
 
+// Activations saved by the training forward of one network (planes of row-major [M, width] matrices, in this order):
+//   emb [M,90] | H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128]
+constexpr int ACT_FLOATS_PER_SAMPLE = CH_IN + 8 * W_HID + 2 * W_HID + 2 * (W_HID / 2);   // 2906
+struct ActPlanes {
+  float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid;
+};
+__host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
+  ActPlanes a;
+  float* p = base;
+  a.emb = p; p += m * CH_IN;
+  for (int l = 0; l < 8; ++l) { a.h[l] = p; p += m * W_HID; }
+  a.rgb_feat = p; p += m * W_HID;
+  a.ins_feat = p; p += m * W_HID;
+  a.rgb_hid = p; p += m * (W_HID / 2);
+  a.ins_hid = p;
+  return a;
+}
+
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 
@@ -84,6 +102,13 @@ int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64
                        cudaStream_t st);
 // MLP, SIMT fp32 path.  Exactly one of x / (rays_o, rays_d, z) is used.
 int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
-                    int64_t m, int s, float* out, cudaStream_t st);
+                    int64_t m, int s, float* out, float* acts, cudaStream_t st);
+// Backward (backward.cu)
+int launch_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all,
+                              const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_ins,
+                              const float* g_weights, float* d_raw, int accumulate, cudaStream_t st);
+int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads,
+                        float* scratch, cudaStream_t st);
+size_t mlp_backward_scratch_floats(int64_t m);
 
 }  // namespace dmnerf

@@ -23,7 +23,7 @@ constexpr size_t SMEM_BYTES = (size_t)(TM * LDE + TM * LDX + TM * LDB + KC * 256
 // registers until every thread has finished reading X).
 template <bool RELU>
 __device__ void layer(const float* Xs, int ldx, int K, const float* __restrict__ W, const float* __restrict__ bias,
-                      int N, float* Ys, int ldy, float* Wt) {
+                      int N, float* Ys, int ldy, float* Wt, float* __restrict__ Yg = nullptr, int rows_valid = 0) {
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   float acc[8][8];
 #pragma unroll
@@ -66,6 +66,7 @@ __device__ void layer(const float* Xs, int ldx, int K, const float* __restrict__
         float v = acc[i][j] + bv;
         if (RELU) v = fmaxf(v, 0.0f);
         Ys[(ty * 8 + i) * ldy + c] = v;
+        if (Yg != nullptr && ty * 8 + i < rows_valid) Yg[(size_t)(ty * 8 + i) * N + c] = v;   // training: keep the activation
       }
     }
   }
@@ -89,7 +90,7 @@ __device__ void head(const float* Xs, int ldx, int K, const float* __restrict__ 
 __global__ void __launch_bounds__(NT, 1)
 mlp_simt_kernel(NetParams p, const float* __restrict__ x, const float* __restrict__ rays_o,
                 const float* __restrict__ rays_d, const float* __restrict__ z, int64_t m, int S,
-                float* __restrict__ out) {
+                float* __restrict__ out, float* __restrict__ acts) {
   extern __shared__ float smem[];
   float* E = smem;                      // [TM][LDE]  [emb_pos 63 | emb_dir 27]
   float* X = E + TM * LDE;              // [TM][LDX]
@@ -136,41 +137,49 @@ mlp_simt_kernel(NetParams p, const float* __restrict__ x, const float* __restric
       }
     }
     __syncthreads();
+    const bool save = acts != nullptr;
+    ActPlanes ap;
+    if (save) {
+      ap = act_planes(acts, m);
+      for (int idx = tid; idx < rows_valid * CH_IN; idx += NT) ap.emb[row0 * CH_IN + idx] = E[(idx / CH_IN) * LDE + idx % CH_IN];
+    }
+#define ACT(plane, width) (save ? (plane) + row0 * (width) : nullptr), rows_valid
 
     // ---- trunk (dm_nerf.py:83-87)
-    layer<true>(E, LDE, CH_POS, p.w[0], p.b[0], W_HID, X, LDX, Wt);
-    for (int l = 1; l <= 4; ++l) layer<true>(X, LDX, W_HID, p.w[l], p.b[l], W_HID, X, LDX, Wt);
+    layer<true>(E, LDE, CH_POS, p.w[0], p.b[0], W_HID, X, LDX, Wt, ACT(ap.h[0], W_HID));
+    for (int l = 1; l <= 4; ++l) layer<true>(X, LDX, W_HID, p.w[l], p.b[l], W_HID, X, LDX, Wt, ACT(ap.h[l], W_HID));
     for (int idx = tid; idx < TM * CH_POS; idx += NT) {           // skip: h = cat([h, pts])
       const int r = idx / CH_POS, c = idx % CH_POS;
       X[r * LDX + W_HID + c] = E[r * LDE + c];
     }
     __syncthreads();
-    layer<true>(X, LDX, W_HID + CH_POS, p.w[5], p.b[5], W_HID, X, LDX, Wt);
-    layer<true>(X, LDX, W_HID, p.w[6], p.b[6], W_HID, X, LDX, Wt);
-    layer<true>(X, LDX, W_HID, p.w[7], p.b[7], W_HID, X, LDX, Wt);
+    layer<true>(X, LDX, W_HID + CH_POS, p.w[5], p.b[5], W_HID, X, LDX, Wt, ACT(ap.h[5], W_HID));
+    layer<true>(X, LDX, W_HID, p.w[6], p.b[6], W_HID, X, LDX, Wt, ACT(ap.h[6], W_HID));
+    layer<true>(X, LDX, W_HID, p.w[7], p.b[7], W_HID, X, LDX, Wt, ACT(ap.h[7], W_HID));
 
     float* orow = out + row0 * C;
     // ---- density (dm_nerf.py:101) -> channel 3
     head(X, LDX, W_HID, p.w[L_DENSITY], p.b[L_DENSITY], 1, orow, C, 3, rows_valid);
     // ---- instance branch (dm_nerf.py:95-99,103) -> channels 4..
-    layer<false>(X, LDX, W_HID, p.w[L_INS_FEAT], p.b[L_INS_FEAT], W_HID, B, LDB, Wt);
+    layer<false>(X, LDX, W_HID, p.w[L_INS_FEAT], p.b[L_INS_FEAT], W_HID, B, LDB, Wt, ACT(ap.ins_feat, W_HID));
     // ---- colour branch (dm_nerf.py:89-93,102) -> channels 0..2   (h is dead after this layer: in place)
-    layer<false>(X, LDX, W_HID, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], W_HID, X, LDX, Wt);
+    layer<false>(X, LDX, W_HID, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], W_HID, X, LDX, Wt, ACT(ap.rgb_feat, W_HID));
     for (int idx = tid; idx < TM * CH_DIR; idx += NT) {            // cat([rgb_feature, input_dirs])
       const int r = idx / CH_DIR, c = idx % CH_DIR;
       X[r * LDX + W_HID + c] = E[r * LDE + CH_POS + c];
     }
     __syncthreads();
-    layer<true>(X, LDX, W_HID + CH_DIR, p.w[L_RGB_HID], p.b[L_RGB_HID], W_HID / 2, X, LDX, Wt);
+    layer<true>(X, LDX, W_HID + CH_DIR, p.w[L_RGB_HID], p.b[L_RGB_HID], W_HID / 2, X, LDX, Wt, ACT(ap.rgb_hid, W_HID / 2));
     head(X, LDX, W_HID / 2, p.w[L_RGB_OUT], p.b[L_RGB_OUT], 3, orow, C, 0, rows_valid);
-    layer<true>(B, LDB, W_HID, p.w[L_INS_HID], p.b[L_INS_HID], W_HID / 2, B, LDB, Wt);
+    layer<true>(B, LDB, W_HID, p.w[L_INS_HID], p.b[L_INS_HID], W_HID / 2, B, LDB, Wt, ACT(ap.ins_hid, W_HID / 2));
+#undef ACT
     head(B, LDB, W_HID / 2, p.w[L_INS_OUT], p.b[L_INS_OUT], p.ins_num + 1, orow, C, 4, rows_valid);
   }
 }
 }  // namespace simt
 
 int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
-                    int64_t m, int s, float* out, cudaStream_t st) {
+                    int64_t m, int s, float* out, float* acts, cudaStream_t st) {
   DMN_CHECK(p.bound, "mlp: weights not bound (call dmnerf_set_weights first)");
   DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr && z != nullptr),
             "mlp: pass either x or (rays_o, rays_d, z)");
@@ -186,7 +195,7 @@ int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, con
   DMN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t tiles = (m + simt::TM - 1) / simt::TM;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  simt::mlp_simt_kernel<<<grid, simt::NT, simt::SMEM_BYTES, st>>>(p, x, rays_o, rays_d, z, m, s, out);
+  simt::mlp_simt_kernel<<<grid, simt::NT, simt::SMEM_BYTES, st>>>(p, x, rays_o, rays_d, z, m, s, out, acts);
   DMN_LAUNCH_OK();
   return 0;
 }

@@ -109,6 +109,41 @@ DMNERF_API int dmnerf_sample_pdf(const float* bins, const float* weights, int64_
 /* torch.sort(torch.cat([a, b], -1), -1).values, networks/render.py:70.  a [N,na], b [N,nb] -> [N,na+nb]. */
 DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int na, int nb, float* out, void* stream);
 
+/* Coarse depths, networks/render.py:40-47: z_out[n, i] = z_in row (shared when z_row_stride = 0), jittered inside its
+ * stratum by t_rand [N,S] when given. */
+DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,
+                    void* stream);
+
+/* networks/render.py:66-70 in one launch: z_mid, sample_pdf on weights[1:-1] (u [N,I] or NULL = deterministic), concat with
+ * the coarse depths and sort.  z_c [N,S], w_c [N,S] -> z_fine [N,S+I]. */
+DMNERF_API int dmnerf_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int n_importance,
+                       float* z_fine, void* stream);
+
+/* ---- training (BASELINE config 4; reference train_dmsr.py:62-64 total_loss.backward()) -------------------------------
+ * The training forward evaluates the network in exact fp32 and keeps the activations the backward needs:
+ * dmnerf_act_floats_per_sample() floats per sample in `acts` (device buffer owned by the caller). */
+DMNERF_API int dmnerf_act_floats_per_sample(void);
+DMNERF_API int64_t dmnerf_mlp_backward_scratch_floats(int64_t m);
+
+/* DM_NeRF.forward with saved activations.  Pass either x [M,90] (rays_* NULL) or rays_o/rays_d [N,3] + z [N,S] (x NULL,
+ * m = N*S).  out [M,C]. */
+DMNERF_API int dmnerf_mlp_forward_train(dmnerf_ctx* ctx, int net, const float* x, const float* rays_o, const float* rays_d,
+                             const float* z, int64_t m, int s, float* out, float* acts, void* stream);
+
+/* Gradient of a scalar loss w.r.t. the 30 parameters of network `net` given d_out = dL/d(out) [M,C] and the activations
+ * saved by dmnerf_mlp_forward_train.  grads: 30 device buffers (state_dict order, parameter shapes), overwritten.
+ * Gradient routing follows the reference (networks/dm_nerf.py:95: the instance branch reads h.detach()).
+ * scratch: dmnerf_mlp_backward_scratch_floats(m) floats. */
+DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const float* d_out, int64_t m, float* const* grads,
+                        float* scratch, void* stream);
+
+/* Backward of render_train (networks/render.py:6-28): upstream gradients of rgb_map [N,3], depth_map [N], acc_map [N],
+ * ins_map [N, C-5 | C-4] and weights [N,S] (any may be NULL) -> d_raw [N,S,C] (added to d_raw when accumulate != 0).
+ * The instance map sees detached weights unless keep_all_ins (render.py:22-23 vs manipulator.py:100). */
+DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c,
+                              int keep_all_ins, const float* g_rgb, const float* g_depth, const float* g_acc,
+                              const float* g_ins, const float* g_weights, float* d_raw, int accumulate, void* stream);
+
 /* dm_nerf(), networks/render.py:31-96, whole per-ray pipeline on device buffers. */
 DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n_rays, int n_coarse,
                           int n_importance, int flags, int impl, void* stream);
