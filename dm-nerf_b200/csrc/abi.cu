@@ -49,6 +49,7 @@ struct dmnerf_ctx {
   Scratch ws_raw_c, ws_raw_f, ws_z_c, ws_z_f, ws_w_c, ws_w_f;
   Scratch host_in, host_out;      // device staging for the *_host entry point
   bool profiling = false;
+  bool last_fused = false;       // the last render call took the single-kernel path
   bool profile_valid = false;
   cudaEvent_t ev[DMNERF_N_STAGES + 1] = {};
   dmnerf_ctx() { memset(net, 0, sizeof(net)); }
@@ -220,6 +221,21 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
   const int C = 4 + ctx->net[0].ins_num + 1, F = S + NI;
   const int keep = (flags & DMNERF_FLAG_KEEP_INS) ? 1 : 0;
   DMN_CUDA(cudaSetDevice(ctx->device));
+
+  // ---- fully fused path: one launch, no intermediate tensor in HBM
+  const bool can_fuse = impl != DMNERF_IMPL_SIMT && S == 64 && NI == 128 && !io->raw_coarse && !io->raw_fine &&
+                        umma_available(ctx->packed[0]) && umma_available(ctx->packed[1]);
+  if (can_fuse) {
+    const bool prof = ctx->profiling;
+    if (prof) DMN_CUDA(cudaEventRecord(ctx->ev[0], st));
+    int rc = launch_render_umma(ctx->packed[0], ctx->packed[1], io, n, flags, st);
+    if (rc) return rc;
+    if (prof) for (int i = 1; i <= DMNERF_N_STAGES; ++i) DMN_CUDA(cudaEventRecord(ctx->ev[i], st));
+    ctx->profile_valid = prof;
+    ctx->last_fused = true;
+    return 0;
+  }
+  ctx->last_fused = false;
 
   // scratch for whatever the caller does not want back
   float* z_c = io->z_vals_coarse;

@@ -51,7 +51,8 @@ constexpr uint32_t SM_E = 3 * SLOT_BYTES;
 constexpr uint32_t SM_D = SM_E + CHUNK_BYTES;
 constexpr uint32_t SM_RING = SM_D + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = SM_MISC + 2048 + 1024;      // misc block + alignment slack
+constexpr uint32_t SM_FUSED = SM_MISC + 2048;                   // per-unit state of the fused render kernel
+constexpr uint32_t SMEM_BYTES = SM_FUSED + 9216 + 1024;         // + alignment slack
 
 enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..5 = slot*2 + half
 
@@ -80,9 +81,31 @@ struct Misc {                  // lives at SM_MISC
   float dens[2][TILE_M];
 };
 
+// Shared state of the fused render kernel: one work unit = 2 rays = 1 coarse tile (2 x 64 samples) + 3 fine tiles (2 x 192).
+constexpr int FS = 64, FI = 128, FF = FS + FI;        // the fused path is specialised for 64 + 128 samples
+constexpr int ACC_W = 5 + DMNERF_MAX_INS + 1 + 3;      // rgb3, depth, acc, ins_num+1 (padded)
+struct Fused {
+  float ray[2][8];            // o(3), d(3), |d|, valid
+  float zc[2][FS];            // coarse depths (after jitter)
+  float zf[2][FF];            // fine depths (sorted union)
+  float w[TILE_M];            // compositing weights of the current tile's rows
+  float tot[4];               // per-warp transmittance products of the current tile
+  float carry[4][2];          // transmittance entering fine tile j (rays A, B)
+  float accum[2][ACC_W];      // per-ray running sums: rgb3, depth, acc, instance logits
+  float bins[2][FS], cdf[2][FS], vals[2][FF];
+};
+static_assert(sizeof(Fused) <= 9216, "Fused state does not fit its shared-memory block");
+
 struct KArgs {
-  const uint8_t* image;        // packed bf16 operand image
+  const uint8_t* image;        // packed bf16 operand image (fused: coarse network)
   const float* bias;           // [N_STEPS][128] + wd[256] + bd
+  const uint8_t* image_fine;   // fused: fine network
+  const float* bias_fine;
+  // fused render inputs / outputs (any output may be NULL)
+  const float* z_in; int64_t z_stride; const float* t_rand; const float* u;
+  int64_t n_rays; int32_t keep_all_ins;
+  float* rgb_c; float* rgb_f; float* depth_c; float* depth_f; float* acc_c; float* acc_f; float* ins_c; float* ins_f;
+  float* zc_out; float* zf_out; float* wc_out; float* wf_out;
   const float* x;              // [M, 90] or nullptr
   const float* rays_o; const float* rays_d; const float* z;   // rays mode
   int64_t m;
@@ -193,13 +216,17 @@ __device__ __forceinline__ void store_split32(const float* vals, uint8_t* slab, 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+template <bool FUSED>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_constant__ Program prog, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t n_tiles = (a.m + TILE_M - 1) / TILE_M;
-  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // RAW: work item = one 128-row tile of a.m samples.  FUSED: work item = ray pair = 4 tiles (1 coarse + 3 fine).
+  const int64_t n_items = FUSED ? (a.n_rays + 1) / 2 : (a.m + TILE_M - 1) / TILE_M;
+  const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = FUSED ? 4 * my_items : my_items;
+  Fused* fz = reinterpret_cast<Fused*>(smem + SM_FUSED);
   const int C = 4 + prog.ins_num + 1;
 
   if (tid == 0) {
@@ -220,12 +247,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     Ring ring{0, 0};
     const int n_stages = prog.n_stages;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const uint8_t* image = (FUSED && (ti & 3) != 0) ? a.image_fine : a.image;
       for (int si = 0; si < n_stages; ++si) {
         const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
         if (!wait_or_abort(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status)) goto done;
         if (elect_one()) {
           mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
-          bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, a.image + off, bytes, &misc->full[ring.slot]);
+          bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, image + off, bytes, &misc->full[ring.slot]);
         }
         __syncwarp();
         ring.advance();
@@ -325,14 +353,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     uint8_t* e_slab = smem + SM_E;
     uint8_t* d_slab = smem + SM_D;
     float dens_acc = 0.0f;
+    const int n_ins1 = prog.ins_num + 1;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      const int64_t tile = blockIdx.x + ti * gridDim.x;
-      const int64_t row = tile * TILE_M + r;
-      const bool valid = row < a.m;
+      // ---- which rows does this tile hold
+      const int j = FUSED ? (int)(ti & 3) : 0;                            // fused: 0 = coarse tile, 1..3 = fine tiles
+      const int64_t item = blockIdx.x + (FUSED ? (ti >> 2) : ti) * gridDim.x;
+      int64_t row = 0;                                                    // RAW: global sample row
+      int rl = 0, si = 0, S = 0;                                          // fused: local ray (0/1), sample index, samples per ray
+      bool valid;
+      if constexpr (FUSED) {
+        if (j == 0) {
+          // unit start: ray data, running sums and carries
+          if (et < 2) {
+            const int64_t ray = item * 2 + et;
+            const bool ok = ray < a.n_rays;
+            float* rs = fz->ray[et];
+            float nrm = 1.0f;
+            for (int c = 0; c < 3; ++c) { rs[c] = ok ? a.rays_o[ray * 3 + c] : 0.0f; rs[3 + c] = ok ? a.rays_d[ray * 3 + c] : 0.0f; }
+            nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
+            rs[6] = nrm; rs[7] = ok ? 1.0f : 0.0f;
+          }
+          for (int k = et; k < 2 * ACC_W; k += EPI_THREADS) fz->accum[k / ACC_W][k % ACC_W] = 0.0f;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          rl = r >> 6; si = r & 63; S = FS;
+        } else {
+          const int gr = (j - 1) * TILE_M + r;
+          rl = gr / FF; si = gr % FF; S = FF;
+        }
+        valid = fz->ray[rl][7] != 0.0f;
+      } else {
+        row = item * TILE_M + r;
+        valid = row < a.m;
+      }
+      const float* bias_base = (FUSED && j != 0) ? a.bias_fine : a.bias;
       // ---------------- prologue: points, embeddings -> E / D operands (hi: TMEM, lo: smem)
       {
         float vals[32];
-        if (a.x) {
+        if (!FUSED && a.x) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int e = 32 * q + i;
@@ -347,13 +404,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         } else {
           float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
           if (valid) {
-            const int64_t ray = row / a.s;
-            const float zz = a.z[row];
-            const float d0 = a.rays_d[ray * 3], d1 = a.rays_d[ray * 3 + 1], d2 = a.rays_d[ray * 3 + 2];
-            pt[0] = __fadd_rn(a.rays_o[ray * 3 + 0], __fmul_rn(d0, zz));      // render.py:49
-            pt[1] = __fadd_rn(a.rays_o[ray * 3 + 1], __fmul_rn(d1, zz));
-            pt[2] = __fadd_rn(a.rays_o[ray * 3 + 2], __fmul_rn(d2, zz));
-            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+            float o0, o1, o2, d0, d1, d2, nrm, zz;
+            if constexpr (FUSED) {
+              const float* rs = fz->ray[rl];
+              o0 = rs[0]; o1 = rs[1]; o2 = rs[2]; d0 = rs[3]; d1 = rs[4]; d2 = rs[5]; nrm = rs[6];
+              if (j == 0) {
+                // render.py:40-47: shared / per-ray coarse row, jittered inside its stratum when t_rand is given
+                const int64_t ray = item * 2 + rl;
+                const float* zr = a.z_in + ray * a.z_stride;
+                zz = zr[si];
+                if (a.t_rand) {
+                  const float lower = (si == 0) ? zz : __fmul_rn(0.5f, __fadd_rn(zz, zr[si - 1]));
+                  const float upper = (si == FS - 1) ? zz : __fmul_rn(0.5f, __fadd_rn(zr[si + 1], zz));
+                  zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[ray * FS + si]));
+                }
+                if (q == 0) {
+                  fz->zc[rl][si] = zz;
+                  if (a.zc_out) a.zc_out[ray * FS + si] = zz;
+                }
+              } else {
+                zz = fz->zf[rl][si];
+              }
+            } else {
+              const int64_t ray = row / a.s;
+              zz = a.z[row];
+              o0 = a.rays_o[ray * 3]; o1 = a.rays_o[ray * 3 + 1]; o2 = a.rays_o[ray * 3 + 2];
+              d0 = a.rays_d[ray * 3]; d1 = a.rays_d[ray * 3 + 1]; d2 = a.rays_d[ray * 3 + 2];
+              nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+            }
+            pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
+            pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
+            pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
             vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
           }
           if (q == 0) {
@@ -390,12 +471,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         if (!wait_or_abort(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status)) goto done;
         tc_fence_after();
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
-        const float* bias = a.bias + t * 128;
+        const float* bias = bias_base + t * 128;
         if (st.out_slot >= 0) {
           // hidden half-step: 64 columns per thread -> bias, (ReLU), split, store into the destination slot
           const int slot = st.out_slot;
           uint8_t* slab = smem + SM_SLOT + slot * SLOT_BYTES + q * CHUNK_BYTES;     // this thread's 64 columns = chunk q
-          const uint32_t lo_addr = tbase + lane_sel + TC_SLOT + slot * 64 + q * 32;
+          const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * 64 + q * 32;
           const bool is_l7 = (t == 14 || t == 15);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -405,29 +486,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             float f[32];
             const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + h * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(b4 + j);
-              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 bb = __ldg(b4 + jj);
+              f[4 * jj + 0] = __uint_as_float(v[4 * jj + 0]) + bb.x;
+              f[4 * jj + 1] = __uint_as_float(v[4 * jj + 1]) + bb.y;
+              f[4 * jj + 2] = __uint_as_float(v[4 * jj + 2]) + bb.z;
+              f[4 * jj + 3] = __uint_as_float(v[4 * jj + 3]) + bb.w;
             }
             if (st.relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.0f);
             }
             if (is_l7) {        // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
-              const float4* w4 = reinterpret_cast<const float4*>(a.bias + N_STEPS * 128 + (t - 14) * 128 + q * 64 + h * 32);
+              const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + q * 64 + h * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 ww = __ldg(w4 + j);
-                dens_acc = fmaf(f[4 * j + 0], ww.x, dens_acc);
-                dens_acc = fmaf(f[4 * j + 1], ww.y, dens_acc);
-                dens_acc = fmaf(f[4 * j + 2], ww.z, dens_acc);
-                dens_acc = fmaf(f[4 * j + 3], ww.w, dens_acc);
+              for (int jj = 0; jj < 8; ++jj) {
+                const float4 ww = __ldg(w4 + jj);
+                dens_acc = fmaf(f[4 * jj + 0], ww.x, dens_acc);
+                dens_acc = fmaf(f[4 * jj + 1], ww.y, dens_acc);
+                dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
+                dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
               }
             }
-            store_split32(f, slab, r, h * 32, lo_addr + h * 16);
+            store_split32(f, slab, r, h * 32, hi_addr + h * 16);
           }
           if (t == 15) {         // publish this column-half's partial sum of the density dot product; the rgb-head
             misc->dens[q][r] = dens_acc;   // epilogue (3 barrier hops later) adds the two halves
@@ -435,37 +516,140 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           }
           fence_proxy_async_smem();
           tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&misc->epi_done[acc]);
         } else if (t == N_STEPS - 2) {
-          // rgb head (N=16: 3 live columns) + density -> out[:, 0:4]          (dm_nerf.py:101-102,105)
+          // rgb head (N=16: 3 live columns) + density                          (dm_nerf.py:101-102,105)
+          uint32_t v[16];
           if (q == 0) {
-            uint32_t v[16];
             tmem_ld_x16(acc_addr, v);
             tmem_ld_wait();
-            if (valid) {
-              float* o = a.out + row * C;
-              o[0] = __uint_as_float(v[0]) + __ldg(bias + 0);
-              o[1] = __uint_as_float(v[1]) + __ldg(bias + 1);
-              o[2] = __uint_as_float(v[2]) + __ldg(bias + 2);
-              o[3] = misc->dens[0][r] + misc->dens[1][r] + __ldg(a.bias + N_STEPS * 128 + 256);
+          }
+          tc_fence_before();
+          mbar_arrive(&misc->epi_done[acc]);             // accumulator drained: the next tile's first half-step may start
+          if (q == 0) {
+            const float c0 = __uint_as_float(v[0]) + __ldg(bias + 0), c1 = __uint_as_float(v[1]) + __ldg(bias + 1),
+                        c2 = __uint_as_float(v[2]) + __ldg(bias + 2);
+            const float sigma = misc->dens[0][r] + misc->dens[1][r] + __ldg(bias_base + N_STEPS * 128 + 256);
+            if constexpr (!FUSED) {
+              if (valid) {
+                float* o = a.out + row * C;
+                o[0] = c0; o[1] = c1; o[2] = c2; o[3] = sigma;
+              }
+            } else {
+              // ---- sigma -> alpha -> transmittance (render.py:7-18): warp scan + cross-warp carry
+              const float* zs = (j == 0) ? fz->zc[rl] : fz->zf[rl];
+              const float zi = zs[si];
+              float dist = (si == S - 1) ? 1e10f : __fsub_rn(zs[si + 1], zi);
+              dist = __fmul_rn(dist, fz->ray[rl][6]);
+              const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sigma, 0.0f), dist)));
+              const float f = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+              const int lane_i = r & 31, wi = r >> 5;
+              const float incl = warp_scan_mul(f, lane_i);
+              float excl = __shfl_up_sync(FULL, incl, 1);
+              if (lane_i == 0) excl = 1.0f;
+              if (lane_i == 31) fz->tot[wi] = incl;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              // transmittance entering this warp = carry of the ray x products of earlier warps of the same ray in this tile
+              const int first_w = (j == 0) ? (rl * 2) : ((j == 2) ? (rl * 2) : 0);   // first warp of my ray inside this tile
+              float pre = (FUSED && j >= 2) ? fz->carry[j][rl] : 1.0f;
+              for (int w2 = first_w; w2 < wi; ++w2) pre = __fmul_rn(pre, fz->tot[w2]);
+              const float wgt = valid ? __fmul_rn(alpha, __fmul_rn(pre, excl)) : 0.0f;
+              fz->w[r] = wgt;
+              if (j >= 1 && j <= 2 && wi == 0 && lane_i < 2) {
+                // carry into the next fine tile for ray `lane_i` (ray A ends inside tile 2, ray B starts there)
+                float cpre = (j == 2) ? fz->carry[2][lane_i] : 1.0f;
+                const int wa = (j == 1) ? (lane_i == 0 ? 0 : 4) : (lane_i == 0 ? 0 : 2);    // warps of that ray in this tile
+                const int wb = (j == 1) ? (lane_i == 0 ? 4 : 4) : (lane_i == 0 ? 2 : 4);
+                for (int w2 = wa; w2 < wb; ++w2) cpre = __fmul_rn(cpre, fz->tot[w2]);
+                fz->carry[j + 1][lane_i] = cpre;
+              }
+              if (j == 0 && a.wc_out && valid) a.wc_out[(item * 2 + rl) * FS + si] = wgt;
+              if (j != 0 && a.wf_out && valid) a.wf_out[(item * 2 + rl) * FF + si] = wgt;
+              // ---- weighted sums (render.py:19-20 + acc): warp reduce, one shared-memory atomic per warp and channel
+              float p0 = __fmul_rn(wgt, sigmoidf_acc(c0)), p1 = __fmul_rn(wgt, sigmoidf_acc(c1)), p2 = __fmul_rn(wgt, sigmoidf_acc(c2));
+              float p3 = __fmul_rn(wgt, zi), p4 = wgt;
+              p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3); p4 = warp_sum(p4);
+              if (lane_i == 0) {
+                float* ac = fz->accum[rl];
+                atomicAdd(ac + 0, p0); atomicAdd(ac + 1, p1); atomicAdd(ac + 2, p2); atomicAdd(ac + 3, p3); atomicAdd(ac + 4, p4);
+              }
             }
           }
         } else {
-          // instance head (N = pad16(ins_num+1)) -> out[:, 4:]                  (dm_nerf.py:103,105)
-          const int n_ins = prog.ins_num + 1;
-          for (int c0 = q * 64; c0 < st.n && c0 < q * 64 + 64; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_x16(acc_addr + c0, v);
-            tmem_ld_wait();
-            if (valid) {
-              float* o = a.out + row * C + 4;
+          // instance head (N = pad16(ins_num+1))                                 (dm_nerf.py:103,105)
+          if constexpr (!FUSED) {
+            for (int c0 = q * 64; c0 < st.n && c0 < q * 64 + 64; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld_x16(acc_addr + c0, v);
+              tmem_ld_wait();
+              if (valid) {
+                float* o = a.out + row * C + 4;
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < n_ins) o[c0 + j] = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
+                for (int jj = 0; jj < 16; ++jj)
+                  if (c0 + jj < n_ins1) o[c0 + jj] = __uint_as_float(v[jj]) + __ldg(bias + c0 + jj);
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc]);
+          } else {
+            // instance logits weighted by the (detached) weights: sum_i w_i raw_i[4+k]   (render.py:22-24)
+            asm volatile("bar.sync 2, 256;" ::: "memory");     // weights of this tile (fz->w) are complete
+            const float wgt = fz->w[r];
+            const int lane_i = r & 31;
+            for (int c0 = q * 64; c0 < st.n && c0 < q * 64 + 64; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld_x16(acc_addr + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                float pv = (c0 + jj < n_ins1) ? __fmul_rn(wgt, __uint_as_float(v[jj]) + __ldg(bias + c0 + jj)) : 0.0f;
+                pv = warp_sum(pv);
+                if (lane_i == 0 && c0 + jj < n_ins1) atomicAdd(&fz->accum[rl][5 + c0 + jj], pv);
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc]);
+            asm volatile("bar.sync 2, 256;" ::: "memory");     // all running sums of this tile are in
+            // ---- rays that end in this tile: write their maps (render.py:19-26) and clear the sums
+            const int done_lo = (j == 0) ? 0 : ((j == 2) ? 0 : ((j == 3) ? 1 : 2));
+            const int done_hi = (j == 0) ? 2 : ((j == 2) ? 1 : ((j == 3) ? 2 : 2));
+            for (int rr = done_lo; rr < done_hi; ++rr) {
+              const int64_t ray = item * 2 + rr;
+              if (fz->ray[rr][7] != 0.0f && et < 5 + n_ins1) {
+                const float vsum = fz->accum[rr][et];
+                float* o_rgb = (j == 0) ? a.rgb_c : a.rgb_f;
+                float* o_dep = (j == 0) ? a.depth_c : a.depth_f;
+                float* o_acc = (j == 0) ? a.acc_c : a.acc_f;
+                float* o_ins = (j == 0) ? a.ins_c : a.ins_f;
+                const int n_out = a.keep_all_ins ? n_ins1 : n_ins1 - 1;
+                if (et < 3) { if (o_rgb) o_rgb[ray * 3 + et] = vsum; }
+                else if (et == 3) { if (o_dep) o_dep[ray] = vsum; }
+                else if (et == 4) { if (o_acc) o_acc[ray] = vsum; }
+                else if (et - 5 < n_out) { if (o_ins) o_ins[ray * n_out + (et - 5)] = sigmoidf_acc(vsum); }
+              }
+              if (et < 5 + n_ins1) fz->accum[rr][et] = 0.0f;
+            }
+            if (j == 0) {
+              // ---- hierarchical sampling (render.py:66-70): one warp per ray, results stay in shared memory
+              if (et < 64) {
+                const int rr = et >> 5, ln = et & 31;
+                for (int k = ln; k < FS; k += 32) fz->vals[rr][k] = fz->zc[rr][k];
+                __syncwarp();
+                for (int k = ln; k < FS - 1; k += 32) fz->bins[rr][k] = __fmul_rn(0.5f, __fadd_rn(fz->zc[rr][k + 1], fz->zc[rr][k]));
+                __syncwarp();
+                const int64_t ray = item * 2 + rr;
+                const float* wr = fz->w + rr * FS;
+                const float* uu = (a.u && fz->ray[rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
+                ray_sample_pdf(fz->bins[rr], [&](int k) { return wr[k + 1]; }, FS - 1, FI, uu, fz->cdf[rr], fz->vals[rr] + FS, ln);
+                ray_rank_sort(fz->vals[rr], FF, fz->zf[rr], ln);
+                if (a.zf_out && fz->ray[rr][7] != 0.0f)
+                  for (int k = ln; k < FF; k += 32) a.zf_out[ray * FF + k] = fz->zf[rr][k];
+              }
+              asm volatile("bar.sync 2, 256;" ::: "memory");   // fine depths visible to every prologue thread
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&misc->epi_done[acc]);
       }
     }
   }
@@ -686,7 +870,7 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   UmmaExtra* ex = extra_of(w);
   static bool attr_set = false;
   if (!attr_set) {
-    DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -694,10 +878,48 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   DMN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t tiles = (m + TILE_M - 1) / TILE_M;
   KArgs a;
+  memset(&a, 0, sizeof(a));
   a.image = (const uint8_t*)w.image; a.bias = w.bias; a.x = x; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.m = m; a.s = s; a.out = out; a.status = ex->d_status;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  mlp_umma_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
+  mlp_umma_kernel<false><<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+// Whole dm_nerf() pipeline (render.py:31-96) in ONE launch: coarse network -> composite -> importance sampling -> fine
+// network -> composite, per pair of rays, nothing but rays in and per-ray maps out crossing HBM.  64 + 128 samples only.
+int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmnerf_render_io* io, int64_t n, int flags,
+                       cudaStream_t st) {
+  using namespace uk;
+  DMN_CHECK(wc.ready && wf.ready && wc.extra && wf.extra, "render(umma): weights not packed");
+  DMN_CHECK(wc.ins_num == wf.ins_num, "render(umma): coarse/fine ins_num differ");
+  if (n == 0) return 0;
+  UmmaExtra* ex = extra_of(wc);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  DMN_CUDA(cudaGetDevice(&dev));
+  DMN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.image = (const uint8_t*)wc.image; a.bias = wc.bias;
+  a.image_fine = (const uint8_t*)wf.image; a.bias_fine = wf.bias;
+  a.rays_o = io->rays_o; a.rays_d = io->rays_d;
+  a.z_in = io->z_coarse; a.z_stride = io->z_row_stride;
+  const bool perturb = (flags & DMNERF_FLAG_PERTURB) != 0;
+  a.t_rand = perturb ? io->t_rand : nullptr; a.u = perturb ? io->u : nullptr;
+  a.n_rays = n; a.keep_all_ins = (flags & DMNERF_FLAG_KEEP_INS) ? 1 : 0;
+  a.rgb_c = io->rgb_coarse; a.rgb_f = io->rgb_fine; a.depth_c = io->depth_coarse; a.depth_f = io->depth_fine;
+  a.acc_c = io->acc_coarse; a.acc_f = io->acc_fine; a.ins_c = io->ins_coarse; a.ins_f = io->ins_fine;
+  a.zc_out = io->z_vals_coarse; a.zf_out = io->z_vals_fine; a.wc_out = io->weights_coarse; a.wf_out = io->weights_fine;
+  a.status = ex->d_status;
+  const int64_t units = (n + 1) / 2;
+  const unsigned grid = (unsigned)(units < sms ? units : sms);
+  mlp_umma_kernel<true><<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
   DMN_LAUNCH_OK();
   return 0;
 }

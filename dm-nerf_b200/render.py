@@ -99,6 +99,40 @@ def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb
     return out
 
 
+class LazyRenderDict(dict):
+    """Result of an inference dm_nerf() call.  The per-ray maps come from the single fused kernel; the per-sample tensors
+    the reference also returns (`raw_fine`, `raw_coarse`: consumed only by the training-time penalizer) are produced on
+    first access by re-rendering through the unfused kernels with the same random draws, after which every entry is
+    replaced by that consistent set."""
+    LAZY = ("raw_fine", "raw_coarse")
+
+    def __init__(self, data, rerender):
+        super().__init__(data)
+        self._rerender = rerender
+
+    def _materialise(self):
+        if self._rerender is not None:
+            full, self._rerender = self._rerender(), None
+            super().update(full)
+
+    def __missing__(self, key):
+        if key in self.LAZY and self._rerender is not None:
+            self._materialise()
+            return super().__getitem__(key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return super().__contains__(key) or (key in self.LAZY and self._rerender is not None)
+
+    def keys(self):
+        self._materialise()
+        return super().keys()
+
+    def items(self):
+        self._materialise()
+        return super().items()
+
+
 def dm_nerf(rays, position_embedder, view_embedder, model_coarse, model_fine, z_vals_coarse, args):
     """Same signature and return dict as reference networks/render.py:31-96."""
     from .autograd import _needs_grad
@@ -109,7 +143,15 @@ def dm_nerf(rays, position_embedder, view_embedder, model_coarse, model_fine, z_
         from .backward import render_rays_grad
         out = render_rays_grad(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb, args.N_importance)
     else:
-        out = render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb, args.N_importance)
+        t_rand = u = None
+        if perturb > 0.0:          # the reference's two draws, in its order (render.py:46, helpers.py:135)
+            n, S = rays_o.reshape(-1, 3).shape[0], z_vals_coarse.shape[-1]
+            t_rand = torch.rand((n, S), device=rays_o.device)
+            u = torch.rand((n, args.N_importance), device=rays_o.device)
+        kw = dict(perturb=perturb, N_importance=args.N_importance, t_rand=t_rand, u=u)
+        fused = render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, want_raw=False, **kw)
+        out = LazyRenderDict(fused, lambda: render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse,
+                                                        want_raw=True, **kw))
     if getattr(args, "is_train", False) and getattr(args, "N_ins", None) is not None:      # render.py:88-90
         out["ins_fine"] = out["ins_fine"][-args.N_ins:]
         out["ins_coarse"] = out["ins_coarse"][-args.N_ins:]
