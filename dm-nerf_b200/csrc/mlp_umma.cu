@@ -52,7 +52,7 @@ constexpr uint32_t SM_D = SM_E + CHUNK_BYTES;
 constexpr uint32_t SM_RING = SM_D + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
 constexpr uint32_t SM_FUSED = SM_MISC + 2048;                   // per-unit state of the fused render kernel
-constexpr uint32_t SMEM_BYTES = SM_FUSED + 9216 + 1024;         // + alignment slack
+constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
 
 enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..5 = slot*2 + half
 
@@ -91,10 +91,11 @@ struct Fused {
   float w[TILE_M];            // compositing weights of the current tile's rows
   float tot[4];               // per-warp transmittance products of the current tile
   float carry[4][2];          // transmittance entering fine tile j (rays A, B)
-  float accum[2][ACC_W];      // per-ray running sums: rgb3, depth, acc, instance logits
+  float accum[2][6][ACC_W];   // per ray and 32-sample chunk: partial sums of rgb3, depth, acc, instance logits (each slot has
+                              // exactly one writer and the chunks are added in order: bit-reproducible, no atomics)
   float bins[2][FS], cdf[2][FS], vals[2][FF];
 };
-static_assert(sizeof(Fused) <= 9216, "Fused state does not fit its shared-memory block");
+static_assert(sizeof(Fused) <= 12288, "Fused state does not fit its shared-memory block");
 
 struct KArgs {
   const uint8_t* image;        // packed bf16 operand image (fused: coarse network)
@@ -116,21 +117,21 @@ struct KArgs {
 
 // ------------------------------------------------------------------------------------------------ bounded waits
 // Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
-__device__ __noinline__ bool slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+// On a timeout the abort flag is raised and execution simply continues: every later wait returns at once, the kernel
+// drains (with garbage results) and the host sees the status word -- no divergent early exits in the role loops.
+__device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (*(volatile int32_t*)&misc->abort_flag) return false;
+    if (*(volatile int32_t*)&misc->abort_flag) return;
     if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
       atomicExch(&misc->abort_flag, code);
       atomicCAS(status, 0, code);
-      return false;
+      return;
     }
   }
-  return true;
 }
-__device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
-  if (mbar_try_wait(bar, parity)) return true;
-  return slow_wait(bar, parity, misc, code, status);
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  if (!mbar_try_wait(bar, parity)) slow_wait(bar, parity, misc, code, status);
 }
 
 // Position in the weight ring (warp-uniform).
@@ -144,37 +145,30 @@ struct Ring {
 // One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi on the TS path, A_lo*W_hi on the SS path) and
 // the W_lo stage (A_hi*W_lo, TS).  Executed by the whole (converged) MMA warp; one elected lane issues.
 template <int KS>
-__device__ __forceinline__ bool issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
+__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
                                             uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status) {
-  {
-    if (!wait_or_abort(&misc->full[ring.slot], ring.phase, misc, 204, status)) return false;
-    tc_fence_after();
-    const uint64_t w = make_sdesc_sw128(ring_base + ring.slot * STAGE_BYTES);
-    if (elect_one()) {
+  const uint32_t s_hi = ring.slot, p_hi = ring.phase;
+  ring.advance();
+  const uint32_t s_lo = ring.slot, p_lo = ring.phase;
+  ring.advance();
+  wait_bar(&misc->full[s_hi], p_hi, misc, 204, status);
+  wait_bar(&misc->full[s_lo], p_lo, misc, 205, status);
+  tc_fence_after();
+  const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
+  const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
+  if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
-        mma_ts(d_tmem, a_tmem + k * 8, w + 2 * k, idesc, k == 0 ? accum : 1u);
-        mma_ss(d_tmem, a_desc + 2 * k, w + 2 * k, idesc, 1u);
-      }
-      mma_commit(&misc->empty[ring.slot]);
+    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
+      mma_ts(d_tmem, a_tmem + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+      mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
     }
-    __syncwarp();
-    ring.advance();
-  }
-  {
-    if (!wait_or_abort(&misc->full[ring.slot], ring.phase, misc, 205, status)) return false;
-    tc_fence_after();
-    const uint64_t w = make_sdesc_sw128(ring_base + ring.slot * STAGE_BYTES);
-    if (elect_one()) {
+    mma_commit(&misc->empty[s_hi]);
 #pragma unroll
-      for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, w + 2 * k, idesc, 1u);
-      mma_commit(&misc->empty[ring.slot]);
-    }
-    __syncwarp();
-    ring.advance();
+    for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, wl + 2 * k, idesc, 1u);
+    mma_commit(&misc->empty[s_lo]);
   }
+  __syncwarp();
   accum = 1;
-  return true;
 }
 
 // ------------------------------------------------------------------------------------------------ prologue helpers
@@ -218,8 +212,9 @@ __device__ __forceinline__ void store_split32(const float* vals, uint8_t* slab, 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool FUSED>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_constant__ Program prog, const KArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // The kernel has no static shared memory, so the dynamic block starts at offset 0 of the CTA's shared window and
+  // is 1024-aligned by construction (checked below); addresses derived from it stay compile-time / uniform.
+  extern __shared__ __align__(1024) uint8_t smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // RAW: work item = one 128-row tile of a.m samples.  FUSED: work item = ray pair = 4 tiles (1 coarse + 3 fine).
@@ -240,7 +235,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = misc->tmem_base;
+  // This CTA owns the whole tensor memory of its SM (512 columns, 1 CTA/SM), so the allocation starts at column 0.
+  // Treating the base as the constant 0 keeps every TMEM address in uniform registers / immediates.
+  constexpr uint32_t tbase = 0;
+  if (misc->tmem_base != 0 || (smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0) { atomicExch(&misc->abort_flag, 901); atomicCAS(a.status, 0, 901); }
+  }
 
   if (warp == 0) {
     // =========================================================== weight producer (converged warp, one elected lane issues)
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       const uint8_t* image = (FUSED && (ti & 3) != 0) ? a.image_fine : a.image;
       for (int si = 0; si < n_stages; ++si) {
         const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
-        if (!wait_or_abort(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status)) goto done;
+        wait_bar(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status);
         if (elect_one()) {
           mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
           bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, image + off, bytes, &misc->full[ring.slot]);
@@ -270,19 +270,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t idesc_ins = make_idesc_bf16(128, prog.step[N_STEPS - 1].n);
     // epilogue of global step gd finished (its output slot is readable, its accumulator is drained)
-    auto need_epi = [&](uint32_t gd) -> bool {
+    auto need_epi = [&](uint32_t gd) {
       uint32_t& seen = (gd & 1) ? seen1 : seen0;
       const uint32_t need = gd / 2 + 1;
       while (seen < need) {
-        if (!wait_or_abort(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status)) return false;
+        wait_bar(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status);
         ++seen;
       }
       tc_fence_after();
-      return true;
     };
-    auto slot_chunk = [&](int slot, int j, uint32_t d_tmem, uint32_t idesc, uint32_t& accum) -> bool {
-      return issue_chunk<4>(misc, ring, ring_base, make_sdesc_sw128(slot_base + (slot * 2 + j) * CHUNK_BYTES),
-                            tbase + TC_SLOT + (slot * 2 + j) * 32, d_tmem, idesc, accum, a.status);
+    auto slot_chunk = [&](int slot, int j, uint32_t d_tmem, uint32_t idesc, uint32_t& accum) {
+      issue_chunk<4>(misc, ring, ring_base, make_sdesc_sw128(slot_base + (slot * 2 + j) * CHUNK_BYTES),
+                     tbase + TC_SLOT + (slot * 2 + j) * 32, d_tmem, idesc, accum, a.status);
     };
     auto finish = [&](uint32_t acc) {
       if (elect_one()) mma_commit(&misc->acc_full[acc]);
@@ -293,14 +292,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       // ---- layer 0: E -> slots 0, 1
       for (uint32_t h = 0; h < 2; ++h) {
         const uint32_t g = g0 + h;
-        if (g >= 2 && !need_epi(g - 2)) goto done;
+        if (g >= 2) need_epi(g - 2);
         while (seen_in < (uint32_t)ti + 1) {
-          if (!wait_or_abort(&misc->inputs_ready, seen_in & 1, misc, 202, a.status)) goto done;
+          wait_bar(&misc->inputs_ready, seen_in & 1, misc, 202, a.status);
           ++seen_in;
         }
         tc_fence_after();
         uint32_t accum = 0;
-        if (!issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, tbase + TC_ACC + h * 128, idesc128, accum, a.status)) goto done;
+        issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, tbase + TC_ACC + h * 128, idesc128, accum, a.status);
         finish(h);
       }
       int sa = 0, sb = 1, sf = 2;                    // slots holding K-halves 0 / 1 of the activation, free slot
@@ -308,12 +307,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       for (int l = 1; l < 8; ++l) {
         for (uint32_t h = 0; h < 2; ++h) {
           const uint32_t g = g0 + 2 * l + h, d_tmem = tbase + TC_ACC + h * 128;
-          if (!need_epi(g - 2)) goto done;
+          need_epi(g - 2);
           uint32_t accum = 0;
-          if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
-          if (h == 0 && !need_epi(g - 1)) goto done;
-          if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
-          if (l == 5 && !issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, d_tmem, idesc128, accum, a.status)) goto done;
+          slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+          if (h == 0) need_epi(g - 1);
+          slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+          if (l == 5) issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, d_tmem, idesc128, accum, a.status);
           finish(h);
         }
         const int t = sb; sb = sa; sa = sf; sf = t;   // (a, b, f) <- (f, a, b)
@@ -321,26 +320,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       {
         // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> free slot
         uint32_t accum = 0, d_tmem = tbase + TC_ACC;
-        if (!need_epi(g0 + 14)) goto done;
-        if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
-        if (!need_epi(g0 + 15)) goto done;
-        if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
-        if (!issue_chunk<2>(misc, ring, ring_base, d_desc, tbase + TC_D, d_tmem, idesc128, accum, a.status)) goto done;
+        need_epi(g0 + 14);
+        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+        need_epi(g0 + 15);
+        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+        issue_chunk<2>(misc, ring, ring_base, d_desc, tbase + TC_D, d_tmem, idesc128, accum, a.status);
         finish(0);
         // ---- folded instance hidden layer (step 17, acc 1): h -> slot of K-half 0
         accum = 0; d_tmem = tbase + TC_ACC + 128;
-        if (!slot_chunk(sa, 0, d_tmem, idesc128, accum) || !slot_chunk(sa, 1, d_tmem, idesc128, accum)) goto done;
-        if (!slot_chunk(sb, 0, d_tmem, idesc128, accum) || !slot_chunk(sb, 1, d_tmem, idesc128, accum)) goto done;
+        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
         finish(1);
         // ---- rgb head (step 18, acc 0, N=16) on the colour hidden slot
         accum = 0; d_tmem = tbase + TC_ACC;
-        if (!need_epi(g0 + 16)) goto done;
-        if (!slot_chunk(sf, 0, d_tmem, idesc16, accum) || !slot_chunk(sf, 1, d_tmem, idesc16, accum)) goto done;
+        need_epi(g0 + 16);
+        slot_chunk(sf, 0, d_tmem, idesc16, accum); slot_chunk(sf, 1, d_tmem, idesc16, accum);
         finish(0);
         // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden slot
         accum = 0; d_tmem = tbase + TC_ACC + 128;
-        if (!need_epi(g0 + 17)) goto done;
-        if (!slot_chunk(sa, 0, d_tmem, idesc_ins, accum) || !slot_chunk(sa, 1, d_tmem, idesc_ins, accum)) goto done;
+        need_epi(g0 + 17);
+        slot_chunk(sa, 0, d_tmem, idesc_ins, accum); slot_chunk(sa, 1, d_tmem, idesc_ins, accum);
         finish(1);
       }
     }
@@ -373,7 +372,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
             rs[6] = nrm; rs[7] = ok ? 1.0f : 0.0f;
           }
-          for (int k = et; k < 2 * ACC_W; k += EPI_THREADS) fz->accum[k / ACC_W][k % ACC_W] = 0.0f;
           asm volatile("bar.sync 2, 256;" ::: "memory");
           rl = r >> 6; si = r & 63; S = FS;
         } else {
@@ -468,7 +466,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       for (int t = 0; t < N_STEPS; ++t) {
         const Step& st = prog.step[t];
         const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
-        if (!wait_or_abort(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status)) goto done;
+        wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status);
         tc_fence_after();
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
         const float* bias = bias_base + t * 128;
@@ -571,8 +569,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               float p3 = __fmul_rn(wgt, zi), p4 = wgt;
               p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2); p3 = warp_sum(p3); p4 = warp_sum(p4);
               if (lane_i == 0) {
-                float* ac = fz->accum[rl];
-                atomicAdd(ac + 0, p0); atomicAdd(ac + 1, p1); atomicAdd(ac + 2, p2); atomicAdd(ac + 3, p3); atomicAdd(ac + 4, p4);
+                float* ac = fz->accum[rl][si >> 5];
+                ac[0] = p0; ac[1] = p1; ac[2] = p2; ac[3] = p3; ac[4] = p4;
               }
             }
           }
@@ -605,7 +603,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               for (int jj = 0; jj < 16; ++jj) {
                 float pv = (c0 + jj < n_ins1) ? __fmul_rn(wgt, __uint_as_float(v[jj]) + __ldg(bias + c0 + jj)) : 0.0f;
                 pv = warp_sum(pv);
-                if (lane_i == 0 && c0 + jj < n_ins1) atomicAdd(&fz->accum[rl][5 + c0 + jj], pv);
+                if (lane_i == 0 && c0 + jj < n_ins1) fz->accum[rl][si >> 5][5 + c0 + jj] = pv;
               }
             }
             tc_fence_before();
@@ -617,7 +615,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             for (int rr = done_lo; rr < done_hi; ++rr) {
               const int64_t ray = item * 2 + rr;
               if (fz->ray[rr][7] != 0.0f && et < 5 + n_ins1) {
-                const float vsum = fz->accum[rr][et];
+                float vsum = 0.0f;
+                for (int cj = 0; cj < S / 32; ++cj) vsum = __fadd_rn(vsum, fz->accum[rr][cj][et]);
                 float* o_rgb = (j == 0) ? a.rgb_c : a.rgb_f;
                 float* o_dep = (j == 0) ? a.depth_c : a.depth_f;
                 float* o_acc = (j == 0) ? a.acc_c : a.acc_f;
@@ -628,7 +627,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 else if (et == 4) { if (o_acc) o_acc[ray] = vsum; }
                 else if (et - 5 < n_out) { if (o_ins) o_ins[ray * n_out + (et - 5)] = sigmoidf_acc(vsum); }
               }
-              if (et < 5 + n_ins1) fz->accum[rr][et] = 0.0f;
             }
             if (j == 0) {
               // ---- hierarchical sampling (render.py:66-70): one warp per ray, results stay in shared memory
@@ -653,10 +651,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       }
     }
   }
-done:
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tbase, 512);
+  if (warp == 2) tmem_dealloc(misc->tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host: program

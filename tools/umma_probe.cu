@@ -71,9 +71,10 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
       // shared-memory copy of A_hi (two 16-byte units)
       const int slab = k0 / 64, kk = k0 % 64;
       uint8_t* base = sA + (size_t)slab * 128 * 128;
-      *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk + 8)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-      if (p.mode == 1) tmem_st_x8(tA + lane_sel + k0 / 2, hi);
+      const uint32_t* sm = (p.mode == 4) ? lo : hi;      // mode 4: A_lo in shared memory, A_hi in tensor memory
+      *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk)) = make_uint4(sm[0], sm[1], sm[2], sm[3]);
+      *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk + 8)) = make_uint4(sm[4], sm[5], sm[6], sm[7]);
+      if (p.mode == 1 || p.mode == 4) tmem_st_x8(tA + lane_sel + k0 / 2, hi);
       if (p.mode == 2) tmem_st_x8(tA + lane_sel + k0 / 2, lo);
     }
   }
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
         for (int j = 0; j < 4; ++j) split_bf16x2(brow[k0 + 2 * j], brow[k0 + 2 * j + 1], hi[j], lo[j]);
         const int slab = k0 / 64, kk = k0 % 64;
         *reinterpret_cast<uint4*>(sBhi + (size_t)slab * N * 128 + sw128_offset(n, kk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (p.mode == 2)
+        if (p.mode == 2 || p.mode == 4)
           *reinterpret_cast<uint4*>(sBlo + (size_t)slab * N * 128 + sw128_offset(n, kk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
@@ -120,11 +121,25 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
           mma_ss(tD, da, dbh, idesc, acc);
         } else if (p.mode == 1) {
           mma_ts(tD, tA + k0 / 2, dbh, idesc, acc);
-        } else {
+        } else if (p.mode == 2) {
           const uint64_t dbl = make_sdesc_sw128(smem_u32(sBlo + (size_t)slab * N * 128) + kk * 2);
           mma_ss(tD, da, dbh, idesc, acc);
           mma_ss(tD, da, dbl, idesc, 1u);
           mma_ts(tD, tA + k0 / 2, dbh, idesc, 1u);
+        } else {
+          // mode 4: the production schedule of mlp_umma.cu -- per 64-wide chunk: 4x (A_hi*B_hi TS, A_lo*B_hi SS), then 4x A_hi*B_lo TS
+          if (kk == 0) {
+            for (int q2 = 0; q2 < 4; ++q2) {
+              const uint64_t dh = make_sdesc_sw128(smem_u32(sBhi + (size_t)slab * N * 128) + q2 * 32);
+              const uint64_t dl = make_sdesc_sw128(smem_u32(sA + (size_t)slab * 128 * 128) + q2 * 32);
+              mma_ts(tD, tA + (k0 + q2 * 16) / 2, dh, idesc, (rep > 0 || k0 > 0 || q2 > 0) ? 1u : 0u);
+              mma_ss(tD, dl, dh, idesc, 1u);
+            }
+            for (int q2 = 0; q2 < 4; ++q2) {
+              const uint64_t dlo = make_sdesc_sw128(smem_u32(sBlo + (size_t)slab * N * 128) + q2 * 32);
+              mma_ts(tD, tA + (k0 + q2 * 16) / 2, dlo, idesc, 1u);
+            }
+          }
         }
       }
     }
@@ -186,7 +201,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps, bool che
   CK(cudaMemcpy(dImg, img.data(), img.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xFF, (size_t)128 * N * 4)); CK(cudaMemset(dStatus, 0, 4)); CK(cudaMemset(dCyc, 0, 8));
   Params p{dA, dB, dImg, dD, N, K, mode, reps, dCyc, dStatus};
-  const size_t smem = (size_t)(K / 64) * 128 * 128 + (size_t)(K / 64) * N * 128 * (mode == 2 ? 2 : 1) + 1024;
+  const size_t smem = (size_t)(K / 64) * 128 * 128 + (size_t)(K / 64) * N * 128 * ((mode == 2 || mode == 4) ? 2 : 1) + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_kernel<<<1, 128, smem>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
@@ -201,7 +216,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps, bool che
   CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&status, dStatus, 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dImg); cudaFree(dCyc); cudaFree(dStatus);
-  const int n_mma = reps * (K / 16) * (mode == 2 ? 3 : 1);
+  const int n_mma = reps * (K / 16) * ((mode == 2 || mode == 4) ? 3 : 1);
   if (status) {
     printf("%-34s FAIL  status=%d (barrier timeout)\n", name, status);
     return 1;
@@ -216,7 +231,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps, bool che
       double ref = 0;
       for (int k = 0; k < K; ++k) {
         double a = A[(size_t)m * K + k], b = B[(size_t)n * K + k];
-        if (mode != 2) { a = bf16_round((float)a); b = bf16_round((float)b); }
+        if (mode != 2 && mode != 4) { a = bf16_round((float)a); b = bf16_round((float)b); }
         ref += a * b;
       }
       ref *= reps;
@@ -225,7 +240,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps, bool che
       sum_sq_err += err * err; sum_sq_ref += ref * ref;
     }
   const double rel_l2 = sqrt(sum_sq_err / sum_sq_ref);
-  const double tol = (mode == 2) ? 5e-5 : 2e-5;   // vs bf16-exact inputs (modes 0,1,3) / vs fp64 of fp32 inputs (mode 2)
+  const double tol = (mode == 2 || mode == 4) ? 5e-5 : 2e-5;   // vs bf16-exact inputs (modes 0,1,3) / vs fp64 of fp32 inputs (mode 2)
   const bool ok = std::isfinite(rel_l2) && rel_l2 < tol;
   printf("%-34s %s  relL2=%.3e maxabs=%.3e (max|ref|=%.3f)  %lld cyc for %d MMA\n", name, ok ? "PASS" : "FAIL", rel_l2,
          max_err, max_ref, cyc, n_mma);
@@ -250,6 +265,11 @@ int main() {
   run_case("time TS N=256 K=256 x64", 1, 256, 256, 64, false);
   run_case("time SS N=128 K=256 x64", 0, 128, 256, 64, false);
   run_case("time x3 N=256 K=128 x64", 2, 256, 128, 64, false);
+  fails += run_case("prod N=128 K=128 (TS hi, SS lo)", 4, 128, 128, 1, true);
+  run_case("time TS   N=128 K=256 x64", 1, 128, 256, 64, false);
+  run_case("time prod N=128 K=128 x64", 4, 128, 128, 64, false);
+  run_case("time prod N=256 K=128 x64", 4, 256, 128, 64, false);
+  run_case("time prod N=64  K=128 x64", 4, 64, 128, 64, false);
   printf("umma_probe: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }
