@@ -29,7 +29,7 @@ namespace uk {
 using namespace umma;
 
 constexpr int TILE_M = 128;
-constexpr int NS = 5;                      // weight ring stages
+constexpr int NS = 6;                      // weight ring stages
 constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
 constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
 constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;
@@ -44,12 +44,12 @@ constexpr uint32_t TC_ACC = 0;             // two accumulators: [0,128) and [128
 constexpr uint32_t TC_SLOT = 256;          // bf16-hi halves of the three slots: 64 columns each
 constexpr uint32_t TC_E = 448;             // bf16-hi of the position embedding (64 K -> 32 columns)
 constexpr uint32_t TC_D = 480;             // bf16-hi of the direction embedding (32 K -> 16 columns)
+constexpr uint32_t TC_D_LO = 496;          // bf16-lo of the direction embedding (kept in TMEM too: frees a 16 KB slab)
 
 // shared-memory map (offsets from the 1024-aligned base)
 constexpr uint32_t SM_SLOT = 0;
 constexpr uint32_t SM_E = 3 * SLOT_BYTES;
-constexpr uint32_t SM_D = SM_E + CHUNK_BYTES;
-constexpr uint32_t SM_RING = SM_D + CHUNK_BYTES;
+constexpr uint32_t SM_RING = SM_E + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
 constexpr uint32_t SM_FUSED = SM_MISC + 2048;                   // per-unit state of the fused render kernel
 constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
@@ -144,25 +144,29 @@ struct Ring {
 
 // One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi on the TS path, A_lo*W_hi on the SS path) and
 // the W_lo stage (A_hi*W_lo, TS).  Executed by the whole (converged) MMA warp; one elected lane issues.
-template <int KS>
+// A_LO_TMEM: the bf16-lo half of the A operand also lives in tensor memory (direction embedding), otherwise in shared memory.
+template <int KS, bool A_LO_TMEM = false>
 __device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
-                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status) {
+                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status,
+                                            uint32_t a_lo_tmem = 0) {
   const uint32_t s_hi = ring.slot, p_hi = ring.phase;
   ring.advance();
   const uint32_t s_lo = ring.slot, p_lo = ring.phase;
   ring.advance();
-  wait_bar(&misc->full[s_hi], p_hi, misc, 204, status);
-  wait_bar(&misc->full[s_lo], p_lo, misc, 205, status);
-  tc_fence_after();
   const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
   const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
   if (elect_one()) {
+    wait_bar(&misc->full[s_hi], p_hi, misc, 204, status);
+    tc_fence_after();
 #pragma unroll
     for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
       mma_ts(d_tmem, a_tmem + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-      mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
+      if (A_LO_TMEM) mma_ts(d_tmem, a_lo_tmem + k * 8, wh + 2 * k, idesc, 1u);
+      else mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
     }
     mma_commit(&misc->empty[s_hi]);
+    wait_bar(&misc->full[s_lo], p_lo, misc, 205, status);
+    tc_fence_after();
 #pragma unroll
     for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, wl + 2 * k, idesc, 1u);
     mma_commit(&misc->empty[s_lo]);
@@ -207,6 +211,15 @@ __device__ __forceinline__ void store_split32(const float* vals, uint8_t* slab, 
   for (int u = 0; u < 4; ++u)
     *reinterpret_cast<uint4*>(slab + sw128_offset(row, k0 + 8 * u)) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
   tmem_st_x16(tmem_addr, hi);
+}
+
+// 32 fp32 values -> bf16 hi and bf16 lo, both into TMEM (16 columns each).
+__device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t tmem_hi, uint32_t tmem_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  tmem_st_x16(tmem_hi, hi);
+  tmem_st_x16(tmem_lo, lo);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     Ring ring{0, 0};
     uint32_t seen0 = 0, seen1 = 0, seen_in = 0;
     const uint32_t slot_base = smem_u32(smem + SM_SLOT), ring_base = smem_u32(smem + SM_RING);
-    const uint64_t e_desc = make_sdesc_sw128(smem_u32(smem + SM_E)), d_desc = make_sdesc_sw128(smem_u32(smem + SM_D));
+    const uint64_t e_desc = make_sdesc_sw128(smem_u32(smem + SM_E));
     const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t idesc_ins = make_idesc_bf16(128, prog.step[N_STEPS - 1].n);
     // epilogue of global step gd finished (its output slot is readable, its accumulator is drained)
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
         need_epi(g0 + 15);
         slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
-        issue_chunk<2>(misc, ring, ring_base, d_desc, tbase + TC_D, d_tmem, idesc128, accum, a.status);
+        issue_chunk<2, true>(misc, ring, ring_base, 0, tbase + TC_D, d_tmem, idesc128, accum, a.status, tbase + TC_D_LO);
         finish(0);
         // ---- folded instance hidden layer (step 17, acc 1): h -> slot of K-half 0
         accum = 0; d_tmem = tbase + TC_ACC + 128;
@@ -350,7 +363,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     const int r = et & 127;                   // tile row == TMEM lane
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* e_slab = smem + SM_E;
-    uint8_t* d_slab = smem + SM_D;
     float dens_acc = 0.0f;
     const int n_ins1 = prog.ins_num + 1;
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
@@ -397,7 +409,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           if (q == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) vals[i] = (valid && i < CH_DIR) ? a.x[row * CH_IN + CH_POS + i] : 0.0f;
-            store_split32(vals, d_slab, r, 0, tbase + lane_sel + TC_D);
+            store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
           }
         } else {
           float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
             }
-            store_split32(vals, d_slab, r, 0, tbase + lane_sel + TC_D);
+            store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
           } else {
             fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
             if (!valid) {

@@ -241,6 +241,7 @@ def test_fused_render_matches_unfused(n_rays, perturb):
     if perturb:
         kw = dict(t_rand=torch.rand((n_rays, 64), device=DEV, generator=gen), u=torch.rand((n_rays, 128), device=DEV, generator=gen))
     with torch.no_grad():
+        get_context(DEV).bind(0, nc); get_context(DEV).bind(1, nf)                # weight packing launches happen here
         before = _lib.launch_count()
         fused = render_rays(ro, rd, nc, nf, z, perturb=perturb, want_raw=False, impl=_lib.IMPL_UMMA, **kw)
         assert _lib.launch_count() - before == 1                                   # ONE kernel for the whole pipeline
