@@ -112,8 +112,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "rays/sec (64c+128f samples)", "value": value, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DM-SR 'study' 640x480, 64+128 hierarchical, coarse+fine+object head (ins_num=%d); "
-                               "CPU arm renders a bounded sample of 1024-ray chunks per step" % wl["ins_num"]},
+        "config": {"workload": "DM-SR 'study' 640x480 full render, 64+128 hierarchical, coarse+fine+object head "
+                               "(ins_num=%d), one frame (%d rays) per GPU per step" % (wl["ins_num"], wl["rays_o"].shape[0]),
+                   "name": args.workload, "rays_per_step_per_gpu": int(wl["rays_o"].shape[0]),
+                   "note": "CPU arm: each step renders a bounded sample of that frame (1024-ray chunks, as the reference's "
+                           "tester.py chunk loop would) and reports rays/s"},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "%d rays per step in 1024-ray chunks, torch CPU fp32, %d threads" % (rates[-1][1], threads)},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -271,6 +274,41 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
 
+    # ---- BASELINE config 4 (informational): training step, 1024 random rays, forward + backward through the native path
+    train = None
+    if world == 1:
+        import types
+        from dmnerf_b200.render import dm_nerf
+        from dmnerf_b200.embedder import get_embedder
+        sel = torch.from_numpy(np.random.Generator(np.random.PCG64(0)).choice(n_rays, 1024, replace=False)).to(dev)
+        rays = torch.stack([ro[sel], rd[sel]], 0)
+        targs = types.SimpleNamespace(perturb=1.0, N_importance=N_IMPORTANCE, is_train=True, N_ins=None)
+        pe, ve = get_embedder(10)[0], get_embedder(4)[0]
+        zc = z[None].expand(1024, N_COARSE)
+        tgt = torch.rand(1024, 3, device=dev)
+        nc.train(); nf.train()
+        opt = torch.optim.Adam(list(nc.parameters()) + list(nf.parameters()), lr=5e-4)
+
+        def train_step():
+            out = dm_nerf(rays, pe, ve, nc, nf, zc, targs)
+            loss = ((out["rgb_fine"] - tgt) ** 2).mean() + ((out["rgb_coarse"] - tgt) ** 2).mean() + out["ins_fine"].mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        for _ in range(2):
+            train_step()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            train_step()
+        torch.cuda.synchronize(dev)
+        tms = 1e3 * (time.perf_counter() - t0) / 5
+        train = {"rays_per_step": 1024, "ms_per_step": tms, "rays_per_s": 1024 / (tms * 1e-3),
+                 "what": "dm_nerf(perturb=1) forward (fp32 CUDA-core kernel, saved activations) + backward (composite reverse scan, "
+                         "fp32 GEMM kernels) + Adam step; wall clock"}
+        nc.eval(); nf.eval()
+
     total_rays = n_rays * world * args.steps
     value = total_rays / (dev_ms * 1e-3)
     e2e_value = total_rays / (e2e_ms * 1e-3)
@@ -300,7 +338,7 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("fine_mlp_dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch") if fused else None
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": peak_src,
@@ -333,6 +371,8 @@ def run_ours(args):
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if train:
+        line["train_step"] = train
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

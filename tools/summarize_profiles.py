@@ -32,34 +32,43 @@ if os.path.exists(lp):
             f.write("| `%s` | %d | %.3f | %.1f%% | %s | %s |\n" % (k, n, t / 1e6, 100 * t / tot, g, b))
     print("wrote launches summary")
 
-# 2. full-set capture of the fine-network kernel -> key metrics
-rp = os.path.join(go, "prof_umma.ncu-rep")
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-            "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.sum",
-            "lts__t_sectors_srcunit_tex.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "sm__inst_executed.sum"]
-    got = {}
-    for h, u, v in zip(hdr, units, vals):
-        for w in want:
-            if h == w or h.endswith("." + w):
-                got[w] = (v, u)
-    with open(os.path.join(out, "%s_ncu_fine_mlp.md" % tag), "w") as f:
-        f.write("# ncu --set full, one launch of `mlp_umma_kernel` (fine network, 37 888 rays x 192 samples = 56 832 tiles)\n\n"
-                "Captured with `tools/gpu_prof.sh` (`--clock-control none --import-source on`); the .ncu-rep stays in gpurun_out/.\n\n"
-                "| metric | value | unit |\n|---|---|---|\n")
-        for w in want:
-            if w in got:
-                f.write("| %s | %s | %s |\n" % (w, got[w][0], got[w][1]))
-        try:
-            dr = float(got["dram__bytes_read.sum"][0].replace(",", "")); dw = float(got["dram__bytes_write.sum"][0].replace(",", ""))
-            f.write("\nDRAM traffic per launch: read %s %s + write %s %s.\n" % (got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"]))
-        except Exception:
-            pass
-    print("wrote ncu summary")
+# 2. full-set captures -> key metrics
+for rep, fname, title in (("prof_fused.ncu-rep", "ncu_fused_render", "one launch of `mlp_umma_kernel<true>`: the fused render kernel over one "
+                           "640x480 frame (307 200 rays, 64+128 samples) as launched by bench.py"),
+                          ("prof_umma.ncu-rep", "ncu_fine_mlp", "one launch of `mlp_umma_kernel<false>` (unfused fine network, 37 888 rays x 192 samples)")):
+  rp = os.path.join(go, rep)
+  if os.path.exists(rp):
+      raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+      rows = list(csv.reader(raw.splitlines()))
+      hdr, units, vals = rows[0], rows[1], rows[2]
+      want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+              "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+              "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.sum",
+              "lts__t_sectors_srcunit_tex.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+              "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+              "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+              "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "sm__inst_executed.sum"]
+      got = {}
+      for h, u, v in zip(hdr, units, vals):
+          for w in want:
+              if h == w or h.endswith("." + w):
+                  got[w] = (v, u)
+      with open(os.path.join(out, "%s_%s.md" % (tag, fname)), "w") as f:
+          f.write("# ncu --set full, " + title + "\n\n"
+                  "Captured with `tools/gpu_prof.sh` (`--clock-control none`); the .ncu-rep stays in gpurun_out/.\n\n"
+                  "| metric | value | unit |\n|---|---|---|\n")
+          for w in want:
+              if w in got:
+                  f.write("| %s | %s | %s |\n" % (w, got[w][0], got[w][1]))
+          try:
+              scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+              dr = float(got["dram__bytes_read.sum"][0].replace(",", "")) * scale[got["dram__bytes_read.sum"][1]]
+              dw = float(got["dram__bytes_write.sum"][0].replace(",", "")) * scale[got["dram__bytes_write.sum"][1]]
+              if fname == "ncu_fused_render":
+                  json.dump({"kernel": "mlp_umma_kernel<true> (fused render, one 640x480 frame)", "dram_bytes_per_launch": dr + dw,
+                             "dram_read_bytes": dr, "dram_write_bytes": dw, "source": "%s_%s.md" % (tag, fname)},
+                            open(os.path.join(out, "traffic.json"), "w"), indent=1)
+              f.write("\nDRAM traffic per launch: read %s %s + write %s %s.\n" % (got["dram__bytes_read.sum"] + got["dram__bytes_write.sum"]))
+          except Exception:
+              pass
+      print("wrote ncu summary")
