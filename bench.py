@@ -198,7 +198,7 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_device():
-        out = render_rays(ro, rd, nc, nf, z, want_raw=False, want_coarse=False, impl=impl)
+        out = render_rays(ro, rd, nc, nf, z, want_raw=False, want_coarse=False, want_samples=False, impl=impl)
         if world > 1:
             return gather_image(out, world)
         return out

@@ -45,8 +45,14 @@ def _check_embedders(position_embedder, view_embedder):
 
 
 def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb=0.0, N_importance=128,
-                t_rand=None, u=None, want_raw=True, want_coarse=True, keep_all_ins=False, impl=_lib.IMPL_AUTO):
-    """Whole per-ray pipeline on the device.  Returns the reference's 10-key dict plus acc / weights maps."""
+                t_rand=None, u=None, want_raw=True, want_coarse=True, want_samples=None, keep_all_ins=False,
+                impl=_lib.IMPL_AUTO):
+    """Whole per-ray pipeline on the device.  Returns the reference's dict keys plus acc / weights maps.
+    want_raw: per-sample network outputs raw_* (forces the stage-by-stage kernels); want_samples: per-sample depths and
+    weights (z_vals_*, weights_*; default = want_raw); want_coarse: the coarse pass' maps.  With want_raw=False and
+    64 + 128 samples the whole call is ONE kernel and only the requested per-ray maps are written."""
+    if want_samples is None:
+        want_samples = want_raw
     dev = rays_o.device
     if dev.type != "cuda":
         raise RuntimeError("dm_nerf: expected CUDA tensors (no CPU fallback)")
@@ -82,11 +88,13 @@ def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb
         flags |= _lib.FLAG_KEEP_INS
     n_ins_out = ins_num + 1 if keep_all_ins else ins_num
     e = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
-    out = {"rgb_fine": e(n, 3), "ins_fine": e(n, n_ins_out), "z_vals_fine": e(n, F), "depth_fine": e(n),
-           "acc_fine": e(n), "weights_fine": e(n, F), "z_vals_coarse": e(n, S)}
+    out = {"rgb_fine": e(n, 3), "ins_fine": e(n, n_ins_out), "depth_fine": e(n), "acc_fine": e(n)}
+    if want_samples or want_raw:
+        out.update({"z_vals_fine": e(n, F), "weights_fine": e(n, F), "z_vals_coarse": e(n, S)})
     if want_coarse:
-        out.update({"rgb_coarse": e(n, 3), "ins_coarse": e(n, n_ins_out), "depth_coarse": e(n), "acc_coarse": e(n),
-                    "weights_coarse": e(n, S)})
+        out.update({"rgb_coarse": e(n, 3), "ins_coarse": e(n, n_ins_out), "depth_coarse": e(n), "acc_coarse": e(n)})
+        if want_samples or want_raw:
+            out["weights_coarse"] = e(n, S)
     if want_raw:
         out.update({"raw_fine": e(n, F, C), "raw_coarse": e(n, S, C)})
     io = _lib.RenderIO()
@@ -101,10 +109,10 @@ def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb
 
 class LazyRenderDict(dict):
     """Result of an inference dm_nerf() call.  The per-ray maps come from the single fused kernel; the per-sample tensors
-    the reference also returns (`raw_fine`, `raw_coarse`: consumed only by the training-time penalizer) are produced on
+    the reference also returns (`raw_*`, `z_vals_*`: consumed only by the training-time penalizer) are produced on
     first access by re-rendering through the unfused kernels with the same random draws, after which every entry is
     replaced by that consistent set."""
-    LAZY = ("raw_fine", "raw_coarse")
+    LAZY = ("raw_fine", "raw_coarse", "z_vals_fine", "z_vals_coarse", "weights_fine", "weights_coarse")
 
     def __init__(self, data, rerender):
         super().__init__(data)
@@ -149,7 +157,7 @@ def dm_nerf(rays, position_embedder, view_embedder, model_coarse, model_fine, z_
             t_rand = torch.rand((n, S), device=rays_o.device)
             u = torch.rand((n, args.N_importance), device=rays_o.device)
         kw = dict(perturb=perturb, N_importance=args.N_importance, t_rand=t_rand, u=u)
-        fused = render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, want_raw=False, **kw)
+        fused = render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, want_raw=False, want_samples=False, **kw)
         out = LazyRenderDict(fused, lambda: render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse,
                                                         want_raw=True, **kw))
     if getattr(args, "is_train", False) and getattr(args, "N_ins", None) is not None:      # render.py:88-90

@@ -210,8 +210,8 @@ def test_full_frame_properties_and_chunk_invariance():
     z = torch.linspace(0, 1, 64, device=DEV) * (wl["far"] - wl["near"]) + wl["near"]
     n = 40960                                                                    # 10 reference chunks (N_test=4096)
     with torch.no_grad():
-        full = render_rays(ro[:n], rd[:n], nc, nf, z, want_raw=False)
-        part = render_rays(ro[4096:8192], rd[4096:8192], nc, nf, z, want_raw=False)
+        full = render_rays(ro[:n], rd[:n], nc, nf, z, want_raw=False, want_samples=True)
+        part = render_rays(ro[4096:8192], rd[4096:8192], nc, nf, z, want_raw=False, want_samples=True)
     zf = full["z_vals_fine"]
     assert bool((zf[:, 1:] >= zf[:, :-1]).all())
     assert float(zf.min()) >= wl["near"] - 1e-4 and float(zf.max()) <= wl["far"] + 1e-4
@@ -243,7 +243,7 @@ def test_fused_render_matches_unfused(n_rays, perturb):
     with torch.no_grad():
         get_context(DEV).bind(0, nc); get_context(DEV).bind(1, nf)                # weight packing launches happen here
         before = _lib.launch_count()
-        fused = render_rays(ro, rd, nc, nf, z, perturb=perturb, want_raw=False, impl=_lib.IMPL_UMMA, **kw)
+        fused = render_rays(ro, rd, nc, nf, z, perturb=perturb, want_raw=False, want_samples=True, impl=_lib.IMPL_UMMA, **kw)
         assert _lib.launch_count() - before == 1                                   # ONE kernel for the whole pipeline
         ref = render_rays(ro, rd, nc, nf, z, perturb=perturb, want_raw=True, impl=_lib.IMPL_UMMA, **kw)
         get_context(DEV).sync_check()

@@ -19,6 +19,6 @@ ro, rd = torch.from_numpy(wl["rays_o"][:n]).to(dev), torch.from_numpy(wl["rays_d
 z = (torch.linspace(0, 1, 64) * (wl["far"] - wl["near"]) + wl["near"]).to(dev)
 with torch.no_grad():
     for _ in range(3):
-        out = render_rays(ro, rd, nc, nf, z, want_raw=False, want_coarse=False)
+        out = render_rays(ro, rd, nc, nf, z, want_raw=False, want_coarse=False, want_samples=False)
 get_context(dev).sync_check()
 print("done", n, float(out["acc_fine"].mean()))
