@@ -85,7 +85,7 @@ struct Misc {                  // lives at SM_MISC
 constexpr int FS = 64, FI = 128, FF = FS + FI;        // the fused path is specialised for 64 + 128 samples
 constexpr int ACC_W = 5 + DMNERF_MAX_INS + 1 + 3;      // rgb3, depth, acc, ins_num+1 (padded)
 struct Fused {
-  float ray[2][8];            // o(3), d(3), |d|, valid
+  float ray[2][2][8];         // [pair parity][ray]: o(3), d(3), |d|, valid (the next pair is loaded while this one finishes)
   float zc[2][FS];            // coarse depths (after jitter)
   float zf[2][FF];            // fine depths (sorted union)
   float w[TILE_M];            // compositing weights of the current tile's rows
@@ -365,115 +365,135 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     uint8_t* e_slab = smem + SM_E;
     float dens_acc = 0.0f;
     const int n_ins1 = prog.ins_num + 1;
+    // Operands (points, embeddings) of tile `tp`: hi halves into TMEM, lo halves into shared memory, then inputs_ready.
+    // Called EARLY -- during the previous tile, right after the last reader of E / D (half-step 16) has completed -- so the
+    // next tile's first MMAs never wait for sin/cos; only the first tile of a CTA and the first fine tile of a ray pair
+    // (whose depths come out of this tile's importance sampling) are prepared late.
+    auto prologue = [&](int64_t tp) {
+      const int jp = FUSED ? (int)(tp & 3) : 0;
+      const int64_t itemp = blockIdx.x + (FUSED ? (tp >> 2) : tp) * gridDim.x;
+      const int up = FUSED ? (int)((tp >> 2) & 1) : 0;                   // ray-data buffer of that ray pair
+      int64_t rowp = 0;
+      int rlp = 0, sip = 0;
+      bool validp;
+      if constexpr (FUSED) {
+        if (jp == 0) {
+          if (et < 2) {
+            const int64_t ray = itemp * 2 + et;
+            const bool ok = ray < a.n_rays;
+            float* rs = fz->ray[up][et];
+            for (int c = 0; c < 3; ++c) { rs[c] = ok ? a.rays_o[ray * 3 + c] : 0.0f; rs[3 + c] = ok ? a.rays_d[ray * 3 + c] : 0.0f; }
+            rs[6] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
+            rs[7] = ok ? 1.0f : 0.0f;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          rlp = r >> 6; sip = r & 63;
+        } else {
+          const int gr = (jp - 1) * TILE_M + r;
+          rlp = gr / FF; sip = gr % FF;
+        }
+        validp = fz->ray[up][rlp][7] != 0.0f;
+      } else {
+        rowp = itemp * TILE_M + r;
+        validp = rowp < a.m;
+      }
+      float vals[32];
+      if (!FUSED && a.x) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int e = 32 * q + i;
+          vals[i] = (validp && e < CH_POS) ? a.x[rowp * CH_IN + e] : 0.0f;
+        }
+        store_split32(vals, e_slab, r, 32 * q, tbase + lane_sel + TC_E + 16 * q);
+        if (q == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vals[i] = (validp && i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + i] : 0.0f;
+          store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
+        }
+      } else {
+        float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
+        if (validp) {
+          float o0, o1, o2, d0, d1, d2, nrm, zz;
+          if constexpr (FUSED) {
+            const float* rs = fz->ray[up][rlp];
+            o0 = rs[0]; o1 = rs[1]; o2 = rs[2]; d0 = rs[3]; d1 = rs[4]; d2 = rs[5]; nrm = rs[6];
+            if (jp == 0) {
+              // render.py:40-47: shared / per-ray coarse row, jittered inside its stratum when t_rand is given
+              const int64_t ray = itemp * 2 + rlp;
+              const float* zr = a.z_in + ray * a.z_stride;
+              zz = zr[sip];
+              if (a.t_rand) {
+                const float lower = (sip == 0) ? zz : __fmul_rn(0.5f, __fadd_rn(zz, zr[sip - 1]));
+                const float upper = (sip == FS - 1) ? zz : __fmul_rn(0.5f, __fadd_rn(zr[sip + 1], zz));
+                zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[ray * FS + sip]));
+              }
+              if (q == 0) {
+                fz->zc[rlp][sip] = zz;
+                if (a.zc_out) a.zc_out[ray * FS + sip] = zz;
+              }
+            } else {
+              zz = fz->zf[rlp][sip];
+            }
+          } else {
+            const int64_t ray = rowp / a.s;
+            zz = a.z[rowp];
+            o0 = a.rays_o[ray * 3]; o1 = a.rays_o[ray * 3 + 1]; o2 = a.rays_o[ray * 3 + 2];
+            d0 = a.rays_d[ray * 3]; d1 = a.rays_d[ray * 3 + 1]; d2 = a.rays_d[ray * 3 + 2];
+            nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+          }
+          pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
+          pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
+          pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
+          vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
+        }
+        if (q == 0) {
+          fill_embedding<0, 32, L_POS>(pt, vals);
+          if (!validp) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+          }
+          store_split32(vals, e_slab, r, 0, tbase + lane_sel + TC_E);
+          fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
+          if (!validp) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+          }
+          store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
+        } else {
+          fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
+          if (!validp) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
+          }
+          store_split32(vals, e_slab, r, 32, tbase + lane_sel + TC_E + 16);
+        }
+      }
+      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&misc->inputs_ready);
+    };
+    // may tile tp be prepared during tile tp-1?  (the first fine tile of a pair needs this tile's importance samples)
+    auto early_ok = [&](int64_t tp) { return tp < my_tiles && (!FUSED || (tp & 3) != 1); };
+
+    if (my_tiles > 0) prologue(0);
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       // ---- which rows does this tile hold
       const int j = FUSED ? (int)(ti & 3) : 0;                            // fused: 0 = coarse tile, 1..3 = fine tiles
       const int64_t item = blockIdx.x + (FUSED ? (ti >> 2) : ti) * gridDim.x;
+      const int u_cur = FUSED ? (int)((ti >> 2) & 1) : 0;
       int64_t row = 0;                                                    // RAW: global sample row
       int rl = 0, si = 0, S = 0;                                          // fused: local ray (0/1), sample index, samples per ray
       bool valid;
       if constexpr (FUSED) {
-        if (j == 0) {
-          // unit start: ray data, running sums and carries
-          if (et < 2) {
-            const int64_t ray = item * 2 + et;
-            const bool ok = ray < a.n_rays;
-            float* rs = fz->ray[et];
-            float nrm = 1.0f;
-            for (int c = 0; c < 3; ++c) { rs[c] = ok ? a.rays_o[ray * 3 + c] : 0.0f; rs[3 + c] = ok ? a.rays_d[ray * 3 + c] : 0.0f; }
-            nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
-            rs[6] = nrm; rs[7] = ok ? 1.0f : 0.0f;
-          }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          rl = r >> 6; si = r & 63; S = FS;
-        } else {
-          const int gr = (j - 1) * TILE_M + r;
-          rl = gr / FF; si = gr % FF; S = FF;
-        }
-        valid = fz->ray[rl][7] != 0.0f;
+        if (j == 0) { rl = r >> 6; si = r & 63; S = FS; }
+        else { const int gr = (j - 1) * TILE_M + r; rl = gr / FF; si = gr % FF; S = FF; }
+        valid = fz->ray[u_cur][rl][7] != 0.0f;
       } else {
         row = item * TILE_M + r;
         valid = row < a.m;
       }
       const float* bias_base = (FUSED && j != 0) ? a.bias_fine : a.bias;
-      // ---------------- prologue: points, embeddings -> E / D operands (hi: TMEM, lo: smem)
-      {
-        float vals[32];
-        if (!FUSED && a.x) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int e = 32 * q + i;
-            vals[i] = (valid && e < CH_POS) ? a.x[row * CH_IN + e] : 0.0f;
-          }
-          store_split32(vals, e_slab, r, 32 * q, tbase + lane_sel + TC_E + 16 * q);
-          if (q == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vals[i] = (valid && i < CH_DIR) ? a.x[row * CH_IN + CH_POS + i] : 0.0f;
-            store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
-          }
-        } else {
-          float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
-          if (valid) {
-            float o0, o1, o2, d0, d1, d2, nrm, zz;
-            if constexpr (FUSED) {
-              const float* rs = fz->ray[rl];
-              o0 = rs[0]; o1 = rs[1]; o2 = rs[2]; d0 = rs[3]; d1 = rs[4]; d2 = rs[5]; nrm = rs[6];
-              if (j == 0) {
-                // render.py:40-47: shared / per-ray coarse row, jittered inside its stratum when t_rand is given
-                const int64_t ray = item * 2 + rl;
-                const float* zr = a.z_in + ray * a.z_stride;
-                zz = zr[si];
-                if (a.t_rand) {
-                  const float lower = (si == 0) ? zz : __fmul_rn(0.5f, __fadd_rn(zz, zr[si - 1]));
-                  const float upper = (si == FS - 1) ? zz : __fmul_rn(0.5f, __fadd_rn(zr[si + 1], zz));
-                  zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[ray * FS + si]));
-                }
-                if (q == 0) {
-                  fz->zc[rl][si] = zz;
-                  if (a.zc_out) a.zc_out[ray * FS + si] = zz;
-                }
-              } else {
-                zz = fz->zf[rl][si];
-              }
-            } else {
-              const int64_t ray = row / a.s;
-              zz = a.z[row];
-              o0 = a.rays_o[ray * 3]; o1 = a.rays_o[ray * 3 + 1]; o2 = a.rays_o[ray * 3 + 2];
-              d0 = a.rays_d[ray * 3]; d1 = a.rays_d[ray * 3 + 1]; d2 = a.rays_d[ray * 3 + 2];
-              nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
-            }
-            pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
-            pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
-            pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
-            vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
-          }
-          if (q == 0) {
-            fill_embedding<0, 32, L_POS>(pt, vals);
-            if (!valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-            }
-            store_split32(vals, e_slab, r, 0, tbase + lane_sel + TC_E);
-            fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
-            if (!valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-            }
-            store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
-          } else {
-            fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
-            if (!valid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-            }
-            store_split32(vals, e_slab, r, 32, tbase + lane_sel + TC_E + 16);
-          }
-        }
-        fence_proxy_async_smem();
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&misc->inputs_ready);
-      }
       // ---------------- epilogues of the 20 half-steps
       for (int t = 0; t < N_STEPS; ++t) {
         const Step& st = prog.step[t];
@@ -528,6 +548,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&misc->epi_done[acc]);
+          // E / D were last read by half-step 16 (complete: we are past 17's accumulator): prepare the next tile now
+          if (t == 17 && early_ok(ti + 1)) prologue(ti + 1);
         } else if (t == N_STEPS - 2) {
           // rgb head (N=16: 3 live columns) + density                          (dm_nerf.py:101-102,105)
           uint32_t v[16];
@@ -551,7 +573,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               const float* zs = (j == 0) ? fz->zc[rl] : fz->zf[rl];
               const float zi = zs[si];
               float dist = (si == S - 1) ? 1e10f : __fsub_rn(zs[si + 1], zi);
-              dist = __fmul_rn(dist, fz->ray[rl][6]);
+              dist = __fmul_rn(dist, fz->ray[u_cur][rl][6]);
               const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sigma, 0.0f), dist)));
               const float f = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
               const int lane_i = r & 31, wi = r >> 5;
@@ -626,7 +648,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             const int done_hi = (j == 0) ? 2 : ((j == 2) ? 1 : ((j == 3) ? 2 : 2));
             for (int rr = done_lo; rr < done_hi; ++rr) {
               const int64_t ray = item * 2 + rr;
-              if (fz->ray[rr][7] != 0.0f && et < 5 + n_ins1) {
+              if (fz->ray[u_cur][rr][7] != 0.0f && et < 5 + n_ins1) {
                 float vsum = 0.0f;
                 for (int cj = 0; cj < S / 32; ++cj) vsum = __fadd_rn(vsum, fz->accum[rr][cj][et]);
                 float* o_rgb = (j == 0) ? a.rgb_c : a.rgb_f;
@@ -650,10 +672,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 __syncwarp();
                 const int64_t ray = item * 2 + rr;
                 const float* wr = fz->w + rr * FS;
-                const float* uu = (a.u && fz->ray[rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
+                const float* uu = (a.u && fz->ray[u_cur][rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
                 ray_sample_pdf(fz->bins[rr], [&](int k) { return wr[k + 1]; }, FS - 1, FI, uu, fz->cdf[rr], fz->vals[rr] + FS, ln);
                 ray_rank_sort(fz->vals[rr], FF, fz->zf[rr], ln);
-                if (a.zf_out && fz->ray[rr][7] != 0.0f)
+                if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
                   for (int k = ln; k < FF; k += 32) a.zf_out[ray * FF + k] = fz->zf[rr][k];
               }
               asm volatile("bar.sync 2, 256;" ::: "memory");   // fine depths visible to every prologue thread
@@ -661,6 +683,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           }
         }
       }
+      if (ti + 1 < my_tiles && !early_ok(ti + 1)) prologue(ti + 1);
     }
   }
   tc_fence_before();

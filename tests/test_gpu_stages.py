@@ -267,3 +267,54 @@ def test_errors_are_loud():
     lib = _lib.load()
     rc = lib.dmnerf_posenc(None, 5, 10, None, None)
     assert rc != 0 and b"NULL" in lib.dmnerf_last_error()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_baseline_config1_coarse_only_1024_rays(impl):
+    """BASELINE configs[0]: DM-SR 'study', 1024-ray chunk, 64 coarse samples, coarse MLP only -- against the oracle run
+    on the host (the reference's CPU-runnable case)."""
+    from dmnerf_b200.render import composite
+    from dmnerf_b200.autograd import mlp_forward_rays
+    from dmnerf_b200.testing import make_models
+    from oracle import dmnerf_oracle as O
+    wl = synth.workload("dmsr_study")
+    nc, _, wc, _ = make_models(101, 202, 13, DEV)
+    ro, rd = torch.from_numpy(wl["rays_o"][:1024]), torch.from_numpy(wl["rays_d"][:1024])
+    z = O.z_val_sample(1024, wl["near"], wl["far"], 64)
+    with torch.no_grad():
+        x, shp = O._net_inputs(ro, rd, rd / rd.norm(dim=-1, keepdim=True), z)
+        raw_ref = O.mlp_forward(O.to_torch(wc), x).reshape(1024, 64, -1)
+        rgb_ref, w_ref, d_ref, ins_ref, acc_ref = O.composite(raw_ref, z, rd)
+        raw = mlp_forward_rays(nc, ro.to(DEV), rd.to(DEV), z.contiguous().to(DEV), impl)
+        rgb, w, depth, ins, acc = composite(raw, z.contiguous().to(DEV), rd.to(DEV))
+    assert max(raw_errs(raw.cpu().numpy(), raw_ref.numpy())) <= TOL
+    assert max_rel_err(rgb.cpu(), rgb_ref, 1e-2) <= TOL
+    assert max_rel_err(depth.cpu(), d_ref, 1e-1) <= TOL
+    assert max_rel_err(ins.cpu(), ins_ref, 1e-2) <= TOL
+    assert max_rel_err(w.cpu(), w_ref, 1e-3) <= 2 * TOL
+
+
+@pytest.mark.parametrize("name", ["replica_room0", "replica_room0_93", "replica_office2"])
+def test_baseline_replica_configs_full_width_object_head(name):
+    """BASELINE configs[2] / [4] shapes: Replica intrinsics, near 0, 59 / 93 / 69 objects (C = 64 / 98 / 74 channels): the
+    fused render against the stage-by-stage path on 2048 rays, plus range properties."""
+    from dmnerf_b200.render import render_rays
+    from dmnerf_b200.testing import make_models
+    wl = synth.workload(name)
+    ins = wl["ins_num"]
+    nc, nf, _, _ = make_models(31, 32, ins, DEV)
+    sel = np.linspace(0, 307199, 2048).astype(np.int64)
+    ro, rd = cu(wl["rays_o"][sel]), cu(wl["rays_d"][sel])
+    z = torch.linspace(0, 1, 64, device=DEV) * (wl["far"] - wl["near"]) + wl["near"]
+    with torch.no_grad():
+        fused = render_rays(ro, rd, nc, nf, z, want_raw=False, want_samples=True)
+        ref = render_rays(ro, rd, nc, nf, z, want_raw=True)
+    assert fused["ins_fine"].shape == (2048, ins) and ref["raw_fine"].shape == (2048, 192, 4 + ins + 1)
+    same = (fused["z_vals_fine"] - ref["z_vals_fine"]).abs().amax(-1) <= 1e-5
+    assert float(same.float().mean()) >= 0.98
+    for k in ("rgb_fine", "ins_fine", "depth_fine", "acc_fine", "rgb_coarse", "ins_coarse"):
+        a, b = fused[k][same] if k.endswith("fine") else fused[k], ref[k][same] if k.endswith("fine") else ref[k]
+        assert torch.isfinite(a).all()
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=5e-5, err_msg=k)
+    assert bool(((fused["ins_fine"] > 0) & (fused["ins_fine"] < 1)).all())
+    assert float(fused["acc_fine"].max()) <= 1.0 + 1e-4
