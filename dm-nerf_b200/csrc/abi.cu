@@ -160,6 +160,11 @@ DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int
   return launch_sort_concat(a, b, n, na, nb, out, (cudaStream_t)stream);
 }
 
+DMNERF_API int dmnerf_get_rays(const float* K_host, const float* c2w_host, int H, int W, float* rays_o, float* rays_d, void* stream) {
+  DMN_CHECK(K_host && c2w_host && rays_o && rays_d, "get_rays: NULL argument");
+  return launch_rays(K_host, c2w_host, H, W, rays_o, rays_d, (cudaStream_t)stream);
+}
+
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,
                                void* stream) {
   DMN_CHECK(n >= 0 && s >= 1, "stratify: bad sizes");

@@ -100,6 +100,7 @@ int launch_prep_z(const float* z_in, int64_t z_stride, const float* t_rand, int6
                   cudaStream_t st);
 int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int ni, float* z_fine,
                        cudaStream_t st);
+int launch_rays(const float* K9, const float* c2w12, int H, int W, float* rays_o, float* rays_d, cudaStream_t st);
 // MLP, SIMT fp32 path.  Exactly one of x / (rays_o, rays_d, z) is used.
 int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
                     int64_t m, int s, float* out, float* acts, cudaStream_t st);

@@ -674,7 +674,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 const float* wr = fz->w + rr * FS;
                 const float* uu = (a.u && fz->ray[u_cur][rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
                 ray_sample_pdf(fz->bins[rr], [&](int k) { return wr[k + 1]; }, FS - 1, FI, uu, fz->cdf[rr], fz->vals[rr] + FS, ln);
-                ray_rank_sort(fz->vals[rr], FF, fz->zf[rr], ln);
+                if (!uu && ray_is_sorted(fz->vals[rr] + FS, FI, ln) && ray_is_sorted(fz->vals[rr], FS, ln))
+                  ray_merge_sorted(fz->vals[rr], FS, fz->vals[rr] + FS, FI, fz->zf[rr], ln);
+                else ray_rank_sort(fz->vals[rr], FF, fz->zf[rr], ln);
                 if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
                   for (int k = ln; k < FF; k += 32) a.zf_out[ray * FF + k] = fz->zf[rr][k];
               }

@@ -196,7 +196,10 @@ __global__ void hier_sample_kernel(const float* __restrict__ z_c, const float* _
   for (int j = lane; j < nb; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(vals[j + 1], vals[j]));   // render.py:66
   __syncwarp();
   ray_sample_pdf(bins, [&](int j) { return wr[j + 1]; }, nb, NI, u ? u + ray * NI : nullptr, cdf, vals + S, lane);
-  ray_rank_sort(vals, T, z_fine + ray * T, lane);
+  // deterministic u gives two ascending runs (merge by binary search); random u -- or a last-bit inversion at a bin
+  // boundary -- takes the general rank sort
+  if (!u && ray_is_sorted(vals + S, NI, lane) && ray_is_sorted(vals, S, lane)) ray_merge_sorted(vals, S, vals + S, NI, z_fine + ray * T, lane);
+  else ray_rank_sort(vals, T, z_fine + ray * T, lane);
 }
 
 int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int ni, float* z_fine,
@@ -208,6 +211,35 @@ int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64
     DMN_CUDA(cudaFuncSetAttribute(hier_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hier_sample_kernel<<<(unsigned)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem, st>>>(
       z_c, w_c, u, n, s, ni, z_fine);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- get_rays_k (helpers.py:50-61)
+struct Camera { float K[9]; float c2w[12]; };   // row-major 3x3 intrinsics, top 3x4 of the camera-to-world pose
+
+__global__ void rays_kernel(Camera cam, int H, int W, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)H * W) return;
+  const float i = (float)(idx % W), j = (float)(idx / W);                      // pixel column / row (exact linspace values)
+  const float dx = __fdiv_rn(__fsub_rn(i, cam.K[2]), cam.K[0]);
+  const float dy = __fdiv_rn(__fsub_rn(j, cam.K[5]), cam.K[4]);
+  const float dz = cam.K[8];                                                    // K[2,2] * 1
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* R = cam.c2w + 4 * r;
+    rays_d[idx * 3 + r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(dz, R[2]));
+    rays_o[idx * 3 + r] = R[3];
+  }
+}
+
+int launch_rays(const float* K9, const float* c2w12, int H, int W, float* rays_o, float* rays_d, cudaStream_t st) {
+  DMN_CHECK(H >= 1 && W >= 1 && (int64_t)H * W <= (1LL << 31), "get_rays: bad image size %dx%d", H, W);
+  Camera cam;
+  for (int i = 0; i < 9; ++i) cam.K[i] = K9[i];
+  for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w12[i];
+  const int64_t total = (int64_t)H * W;
+  rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cam, H, W, rays_o, rays_d);
   DMN_LAUNCH_OK();
   return 0;
 }

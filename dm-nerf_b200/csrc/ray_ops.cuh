@@ -71,9 +71,20 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
 }
 
+// Additive inclusive warp scan.
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float o = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
 // Inverse-CDF sampling for one ray (networks/helpers.py:123-155).
 //   bins: [nb] (shared), wts: accessor for nb-1 weights, cdf: shared scratch [nb], out: [ns].
-//   u == nullptr => deterministic linspace.
+//   u == nullptr => deterministic linspace.  The cdf is a warp prefix sum (the reference's GPU cumsum is a parallel fp32
+//   scan as well; its CPU cumsum differs from either by ~1e-7, far below the 1e-5 bin-mass threshold of helpers.py:151).
 template <class WFn>
 __device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int nb, int ns, const float* u, float* cdf,
                                                float* out, int lane) {
@@ -81,15 +92,14 @@ __device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int n
   float part = 0.0f;
   for (int j = lane; j < nw; j += 32) part += __fadd_rn(wts(j), 1e-5f);      // helpers.py:125
   const float total = warp_sum(part);
-  __syncwarp();
-  if (lane == 0) {
-    // torch's CPU cumsum accumulates in double and rounds every prefix to float (helpers.py:127-128)
-    double run = 0.0;
-    cdf[0] = 0.0f;
-    for (int j = 0; j < nw; ++j) {
-      run += (double)__fdiv_rn(__fadd_rn(wts(j), 1e-5f), total);
-      cdf[j + 1] = (float)run;
-    }
+  float carry = 0.0f;
+  if (lane == 0) cdf[0] = 0.0f;
+  for (int base = 0; base < nw; base += 32) {                                 // helpers.py:126-128
+    const int j = base + lane;
+    const float pdf = (j < nw) ? __fdiv_rn(__fadd_rn(wts(j), 1e-5f), total) : 0.0f;
+    const float incl = warp_scan_add(pdf, lane);
+    if (j < nw) cdf[j + 1] = carry + incl;
+    carry += __shfl_sync(FULL, incl, 31);
   }
   __syncwarp();
   for (int s = lane; s < ns; s += 32) {
@@ -107,6 +117,33 @@ __device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int n
     const float t = __fdiv_rn(__fsub_rn(us, cb), denom);
     const float bb = bins[below], ba = bins[above];
     out[s] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                  // helpers.py:153
+  }
+  __syncwarp();
+}
+
+// Warp-uniform: is v[0..n) (shared) non-decreasing?
+__device__ __forceinline__ bool ray_is_sorted(const float* v, int n, int lane) {
+  bool ok = true;
+  for (int i = lane + 1; i < n; i += 32) ok = ok && (v[i] >= v[i - 1]);
+  return __all_sync(FULL, ok);
+}
+
+// Merge of two ASCENDING runs a[0..na) and b[0..nb) (shared) into out[0..na+nb): each element's output position is its own
+// index plus the number of elements of the other run that precede it (binary search; ties: run a first).  This is
+// sort(cat(a, b)) (networks/render.py:70) when both inputs are sorted -- always true for the coarse depths, and true for
+// the importance samples whenever u is non-decreasing (the deterministic linspace).
+__device__ __forceinline__ void ray_merge_sorted(const float* a, int na, const float* b, int nb, float* out, int lane) {
+  for (int e = lane; e < na + nb; e += 32) {
+    const bool from_a = e < na;
+    const float v = from_a ? a[e] : b[e - na];
+    const float* other = from_a ? b : a;
+    int lo = 0, hi = from_a ? nb : na;
+    while (lo < hi) {                                   // from_a: count other < v ; from_b: count other <= v
+      const int mid = (lo + hi) >> 1;
+      const float o = other[mid];
+      if (from_a ? (o < v) : (o <= v)) lo = mid + 1; else hi = mid;
+    }
+    out[(from_a ? e : e - na) + lo] = v;
   }
   __syncwarp();
 }

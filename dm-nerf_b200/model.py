@@ -5,33 +5,34 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import get_context
+from .engine import get_context   # noqa: F401
+from .synth import layer_table
 
 
 class DM_NeRF(nn.Module):
+    """Parameter container + forward.  The layers are created from synth.layer_table(), whose entries carry the reference's
+    state_dict names (`mlps.3`, `rgb_feature_linears.0`, ...): a dotted name becomes a slot of an nn.ModuleList."""
+
     def __init__(self, D=8, W=256, input_ch_pts=3, input_ch_views=3, skips=[4], ins_num=None):
         super().__init__()
-        self.skips = skips
-        self.input_ch_pts = input_ch_pts
-        self.input_ch_views = input_ch_views
-        self.mlps = nn.ModuleList(
-            [nn.Linear(input_ch_pts, W)]
-            + [nn.Linear(W + input_ch_pts, W) if i in skips else nn.Linear(W, W) for i in range(D - 1)])
-        self.rgb_feature_linear = nn.Linear(W, W)
-        self.ins_feature_linear = nn.Linear(W, W)
-        self.rgb_feature_linears = nn.ModuleList([nn.Linear(W + input_ch_views, W // 2)])
-        self.ins_feature_linears = nn.ModuleList([nn.Linear(W, W // 2)])
-        self.density_linear = nn.Linear(W, 1)
-        self.ins_linear = nn.Linear(W // 2, ins_num + 1)
-        self.rgb_linear = nn.Linear(W // 2, 3)
-        self._check_shape(D, W)
-
-    def _check_shape(self, D, W):
-        if not (D == 8 and W == 256 and self.input_ch_pts == 63 and self.input_ch_views == 27
-                and list(self.skips) == [4]):
+        self.skips, self.input_ch_pts, self.input_ch_views = skips, input_ch_pts, input_ch_views
+        if not (D == 8 and W == 256 and input_ch_pts == 63 and input_ch_views == 27 and list(skips) == [4]):
             raise NotImplementedError(
                 "the B200 kernels are specialised for DM_NeRF(D=8, W=256, input_ch_pts=63, input_ch_views=27, "
                 "skips=[4]) -- the only configuration config.create_nerf builds (config.py:126-138)")
+        if ins_num is None or not (1 <= int(ins_num) <= _lib.N_PARAMS * 0 + 127):
+            raise ValueError("ins_num must be in [1, 127], got %r" % (ins_num,))
+        # layers are created and registered in table order == the reference's construction order, so the state_dict /
+        # optimizer parameter order and the default-init RNG stream are the reference's
+        for name, fan_out, fan_in in layer_table(int(ins_num), W, D, input_ch_pts, input_ch_views, tuple(skips)):
+            layer = nn.Linear(fan_in, fan_out)
+            if "." in name:
+                list_name = name.split(".")[0]
+                if not hasattr(self, list_name):
+                    setattr(self, list_name, nn.ModuleList())
+                getattr(self, list_name).append(layer)
+            else:
+                setattr(self, name, layer)
 
     @property
     def ins_num(self):

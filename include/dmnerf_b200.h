@@ -109,6 +109,10 @@ DMNERF_API int dmnerf_sample_pdf(const float* bins, const float* weights, int64_
 /* torch.sort(torch.cat([a, b], -1), -1).values, networks/render.py:70.  a [N,na], b [N,nb] -> [N,na+nb]. */
 DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int na, int nb, float* out, void* stream);
 
+/* get_rays_k, networks/helpers.py:50-61: K (HOST, row-major 3x3) and c2w (HOST, row-major, at least its top 3x4 = 12 floats)
+ * -> rays_o, rays_d [H*W, 3] on the device, pixel-major like the reference's reshape(-1, 3). */
+DMNERF_API int dmnerf_get_rays(const float* K_host, const float* c2w_host, int H, int W, float* rays_o, float* rays_d, void* stream);
+
 /* Coarse depths, networks/render.py:40-47: z_out[n, i] = z_in row (shared when z_row_stride = 0), jittered inside its
  * stratum by t_rand [N,S] when given. */
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,

@@ -291,7 +291,7 @@ def test_baseline_config1_coarse_only_1024_rays(impl):
     assert max_rel_err(rgb.cpu(), rgb_ref, 1e-2) <= TOL
     assert max_rel_err(depth.cpu(), d_ref, 1e-1) <= TOL
     assert max_rel_err(ins.cpu(), ins_ref, 1e-2) <= TOL
-    assert max_rel_err(w.cpu(), w_ref, 1e-3) <= 2 * TOL
+    assert float((w.cpu() - w_ref).abs().max()) <= TOL          # weights live in [0, 1]
 
 
 @pytest.mark.parametrize("name", ["replica_room0", "replica_room0_93", "replica_office2"])
@@ -318,3 +318,16 @@ def test_baseline_replica_configs_full_width_object_head(name):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=5e-5, err_msg=k)
     assert bool(((fused["ins_fine"] > 0) & (fused["ins_fine"] < 1)).all())
     assert float(fused["acc_fine"].max()) <= 1.0 + 1e-4
+
+
+def test_get_rays_k_kernel_matches_reference(golden_dir):
+    """ray generation (networks/helpers.py:50-61) as a kernel, against the reference's own rays."""
+    from dmnerf_b200.helpers import get_rays_k
+    g = load(golden_dir, "rays.npz")
+    o, d = get_rays_k(480, 640, g["K"], cu(g["c2w"]))
+    assert o.shape == (480, 640, 3) and d.shape == (480, 640, 3)
+    np.testing.assert_allclose(d.reshape(-1, 3)[g["idx"]].cpu().numpy(), g["rays_d"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(o.reshape(-1, 3)[g["idx"]].cpu().numpy(), g["rays_o"])
+    wl = synth.workload("replica_room0")
+    o2, d2 = get_rays_k(wl["H"], wl["W"], wl["K"], cu(wl["c2w"]))
+    np.testing.assert_allclose(d2.reshape(-1, 3).cpu().numpy(), wl["rays_d"], rtol=1e-6, atol=1e-7)

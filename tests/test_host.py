@@ -103,11 +103,3 @@ def test_z_val_sample_matches_reference_formula(golden_dir):
     assert z.shape == (7, 64) and z.stride(0) == 0
     np.testing.assert_array_equal(z[3].numpy(), g["z"])
     np.testing.assert_array_equal(z_val_sample(2, 0.0, 6.5, 64)[1].numpy(), g["z_replica"])
-
-
-def test_get_rays_k_matches_reference(golden_dir):
-    from dmnerf_b200.helpers import get_rays_k
-    g = dict(np.load(os.path.join(golden_dir, "rays.npz")))
-    o, d = get_rays_k(480, 640, g["K"], torch.from_numpy(g["c2w"]))
-    np.testing.assert_allclose(d.reshape(-1, 3)[g["idx"]].numpy(), g["rays_d"], rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(o.reshape(-1, 3)[g["idx"]].numpy(), g["rays_o"], rtol=0, atol=0)
