@@ -69,9 +69,10 @@ struct Step {
 
 // One 64-wide K chunk of a half-step as the MMA issuer sees it.  Everything is a host-computed constant (the kernel owns
 // shared memory from offset 0 and tensor memory from column 0), so the issuer's loop reads it with uniform constant-bank
-// loads and stays small enough to live in the instruction cache.
+// loads and stays small enough to live in the instruction cache (shared-memory offsets are relative to the dynamic block).
 struct ChunkEnt {
-  uint32_t a_lo_desc;   // low word of the shared-memory descriptor of the A-lo slab (unused when lo_tmem)
+  uint32_t a_lo_desc;   // low word of the shared-memory descriptor of the A-lo slab, relative to the kernel's dynamic
+                        // shared block (the issuer adds the block's base >> 4); unused when lo_tmem
   uint32_t a_hi_tmem;   // TMEM address of the A-hi operand
   uint32_t a_lo_tmem;   // TMEM address of the A-lo operand (direction embedding)
   uint32_t d_tmem;      // accumulator
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     Ring ring{0, 0};
     uint32_t seen0 = 0, seen1 = 0, seen_in = 0;
     const uint32_t ring_base = smem_u32(smem + SM_RING);
+    const uint32_t smem_base16 = smem_u32(smem) >> 4;       // the dynamic block does not start at shared address 0
     const int n_chunks = prog.n_chunks;
     constexpr uint32_t DESC_HI = 0x40004040u;        // SBO 1024 B, version 1, SWIZZLE_128B (see make_sdesc_sw128)
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         ring.advance();
         const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
         const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
-        const uint64_t a_desc = ((uint64_t)DESC_HI << 32) | e.a_lo_desc;
+        const uint64_t a_desc = ((uint64_t)DESC_HI << 32) | (e.a_lo_desc + smem_base16);   // table holds the offset inside our block
         const uint32_t d_tmem = e.d_tmem, a_hi = e.a_hi_tmem, a_lo = e.a_lo_tmem, idesc = e.idesc;
         const uint32_t accum = e.first ? 0u : 1u;
         if (elect_one()) {
