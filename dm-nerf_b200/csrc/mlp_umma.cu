@@ -16,7 +16,6 @@
 //
 // Warp roles: warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 prologue (points +
 // positional encoding) and epilogue.  All waits are bounded: a protocol bug raises an error code, never a hang.
-#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -67,31 +66,8 @@ struct Step {
   int16_t n;                  // MMA N (multiple of 16, <= 128)
 };
 
-// One 64-wide K chunk of a half-step as the MMA issuer sees it.  Everything is a host-computed constant (the kernel owns
-// shared memory from offset 0 and tensor memory from column 0), so the issuer's loop reads it with uniform constant-bank
-// loads and stays small enough to live in the instruction cache (shared-memory offsets are relative to the dynamic block).
-struct ChunkEnt {
-  uint32_t a_lo_desc;   // low word of the shared-memory descriptor of the A-lo slab, relative to the kernel's dynamic
-                        // shared block (the issuer adds the block's base >> 4); unused when lo_tmem
-  uint32_t a_hi_tmem;   // TMEM address of the A-hi operand
-  uint32_t a_lo_tmem;   // TMEM address of the A-lo operand (direction embedding)
-  uint32_t d_tmem;      // accumulator
-  uint32_t idesc;
-  int8_t ks;            // K/16 MMAs per pass (4, or 2 for the direction embedding)
-  int8_t lo_tmem;       // A-lo comes from TMEM
-  int8_t first, last;   // first / last chunk of its half-step
-  int8_t acc;           // accumulator index (for the acc_full commit)
-  int8_t wait_step;     // tile-relative half-step whose epilogue must be complete first (may be -2 / -1 = previous tile); NO_WAIT = none
-  int8_t wait_inputs;   // needs this tile's E / D operands
-  int8_t pad;
-};
-constexpr int8_t NO_WAIT = -100;
-constexpr int MAX_TILE_CHUNKS = 80;
-
 struct Program {
   Step step[N_STEPS];
-  ChunkEnt chunk[MAX_TILE_CHUNKS];
-  int32_t n_chunks;
   uint32_t stage_off[MAX_STAGES];     // byte offset of every weight stage in the packed image
   int32_t n_stages;
   int32_t ins_num;
@@ -129,7 +105,6 @@ struct KArgs {
   // fused render inputs / outputs (any output may be NULL)
   const float* z_in; int64_t z_stride; const float* t_rand; const float* u;
   int64_t n_rays; int32_t keep_all_ins;
-  int32_t dbg_flags;           // measurement experiments only (env DMNERF_DBG): 1 = do not stream weights (stale operands)
   float* rgb_c; float* rgb_f; float* depth_c; float* depth_f; float* acc_c; float* acc_f; float* ins_c; float* ins_f;
   float* zc_out; float* zf_out; float* wc_out; float* wf_out;
   const float* x;              // [M, 90] or nullptr
@@ -166,6 +141,39 @@ struct Ring {
     if (++slot == NS) { slot = 0; phase ^= 1; }
   }
 };
+
+// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi on the TS path, A_lo*W_hi on the SS path) and
+// the W_lo stage (A_hi*W_lo, TS).  Executed by the whole (converged) MMA warp; one elected lane issues.
+// A_LO_TMEM: the bf16-lo half of the A operand also lives in tensor memory (direction embedding), otherwise in shared memory.
+template <int KS, bool A_LO_TMEM = false>
+__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
+                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status,
+                                            uint32_t a_lo_tmem = 0) {
+  const uint32_t s_hi = ring.slot, p_hi = ring.phase;
+  ring.advance();
+  const uint32_t s_lo = ring.slot, p_lo = ring.phase;
+  ring.advance();
+  const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
+  const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
+  if (elect_one()) {
+    wait_bar(&misc->full[s_hi], p_hi, misc, 204, status);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
+      mma_ts(d_tmem, a_tmem + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+      if (A_LO_TMEM) mma_ts(d_tmem, a_lo_tmem + k * 8, wh + 2 * k, idesc, 1u);
+      else mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
+    }
+    mma_commit(&misc->empty[s_hi]);
+    wait_bar(&misc->full[s_lo], p_lo, misc, 205, status);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, wl + 2 * k, idesc, 1u);
+    mma_commit(&misc->empty[s_lo]);
+  }
+  __syncwarp();
+  accum = 1;
+}
 
 // ------------------------------------------------------------------------------------------------ prologue helpers
 // Element e of the embedding [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)] given precomputed sin/cos.
@@ -257,12 +265,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
         wait_bar(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status);
         if (elect_one()) {
-          if ((a.dbg_flags & 1) && ti > 0) {
-            mbar_arrive(&misc->full[ring.slot]);          // experiment: pretend the stage arrived (no L2 / fill traffic)
-          } else {
-            mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
-            bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, image + off, bytes, &misc->full[ring.slot]);
-          }
+          mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
+          bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, image + off, bytes, &misc->full[ring.slot]);
         }
         __syncwarp();
         ring.advance();
@@ -270,76 +274,86 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer (converged warp, one elected lane issues)
-    // Table-driven: prog.chunk[] lists the 73 K-chunks of a tile in consumption order (two weight stages each).
+    // The per-tile schedule is written out structurally (it mirrors build_program(), which drives the producer, the
+    // epilogue and the weight packing): 8 trunk layers x 2 half-steps, two folded hidden heads, two output heads.
     Ring ring{0, 0};
     uint32_t seen0 = 0, seen1 = 0, seen_in = 0;
-    const uint32_t ring_base = smem_u32(smem + SM_RING);
-    const uint32_t smem_base16 = smem_u32(smem) >> 4;       // the dynamic block does not start at shared address 0
-    const int n_chunks = prog.n_chunks;
-    constexpr uint32_t DESC_HI = 0x40004040u;        // SBO 1024 B, version 1, SWIZZLE_128B (see make_sdesc_sw128)
+    const uint32_t slot_base = smem_u32(smem + SM_SLOT), ring_base = smem_u32(smem + SM_RING);
+    const uint64_t e_desc = make_sdesc_sw128(smem_u32(smem + SM_E));
+    const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc16 = make_idesc_bf16(128, 16);
+    const uint32_t idesc_ins = make_idesc_bf16(128, prog.step[N_STEPS - 1].n);
+    // epilogue of global step gd finished (its output slot is readable, its accumulator is drained)
+    auto need_epi = [&](uint32_t gd) {
+      uint32_t& seen = (gd & 1) ? seen1 : seen0;
+      const uint32_t need = gd / 2 + 1;
+      while (seen < need) {
+        wait_bar(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status);
+        ++seen;
+      }
+      tc_fence_after();
+    };
+    auto slot_chunk = [&](int slot, int j, uint32_t d_tmem, uint32_t idesc, uint32_t& accum) {
+      issue_chunk<4>(misc, ring, ring_base, make_sdesc_sw128(slot_base + (slot * 2 + j) * CHUNK_BYTES),
+                     tbase + TC_SLOT + (slot * 2 + j) * 32, d_tmem, idesc, accum, a.status);
+    };
+    auto finish = [&](uint32_t acc) {
+      if (elect_one()) mma_commit(&misc->acc_full[acc]);
+      __syncwarp();
+    };
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      const int g0 = (int)ti * N_STEPS;
-      for (int c = 0; c < n_chunks; ++c) {
-        const ChunkEnt& e = prog.chunk[c];
-        if (e.wait_step != NO_WAIT) {                 // epilogue of global half-step gd finished (slot readable, acc drained)
-          const int gd = g0 + e.wait_step;
-          if (gd >= 0) {
-            uint32_t& seen = (gd & 1) ? seen1 : seen0;
-            const uint32_t need = (uint32_t)gd / 2 + 1;
-            while (seen < need) {
-              wait_bar(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status);
-              ++seen;
-            }
-            tc_fence_after();
-          }
+      const uint32_t g0 = (uint32_t)ti * N_STEPS;
+      // ---- layer 0: E -> slots 0, 1
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t g = g0 + h;
+        if (g >= 2) need_epi(g - 2);
+        while (seen_in < (uint32_t)ti + 1) {
+          wait_bar(&misc->inputs_ready, seen_in & 1, misc, 202, a.status);
+          ++seen_in;
         }
-        if (e.wait_inputs) {
-          while (seen_in < (uint32_t)ti + 1) {
-            wait_bar(&misc->inputs_ready, seen_in & 1, misc, 202, a.status);
-            ++seen_in;
-          }
-          tc_fence_after();
+        tc_fence_after();
+        uint32_t accum = 0;
+        issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, tbase + TC_ACC + h * 128, idesc128, accum, a.status);
+        finish(h);
+      }
+      int sa = 0, sb = 1, sf = 2;                    // slots holding K-halves 0 / 1 of the activation, free slot
+      // ---- layers 1..7
+      for (int l = 1; l < 8; ++l) {
+        for (uint32_t h = 0; h < 2; ++h) {
+          const uint32_t g = g0 + 2 * l + h, d_tmem = tbase + TC_ACC + h * 128;
+          need_epi(g - 2);
+          uint32_t accum = 0;
+          slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+          if (h == 0) need_epi(g - 1);
+          slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+          if (l == 5) issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, d_tmem, idesc128, accum, a.status);
+          finish(h);
         }
-        const uint32_t s_hi = ring.slot, p_hi = ring.phase;
-        ring.advance();
-        const uint32_t s_lo = ring.slot, p_lo = ring.phase;
-        ring.advance();
-        const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
-        const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
-        const uint64_t a_desc = ((uint64_t)DESC_HI << 32) | (e.a_lo_desc + smem_base16);   // table holds the offset inside our block
-        const uint32_t d_tmem = e.d_tmem, a_hi = e.a_hi_tmem, a_lo = e.a_lo_tmem, idesc = e.idesc;
-        const uint32_t accum = e.first ? 0u : 1u;
-        if (elect_one()) {
-          wait_bar(&misc->full[s_hi], p_hi, misc, 204, a.status);
-          tc_fence_after();
-          if (e.ks == 4 && !e.lo_tmem) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {             // +2 on a descriptor = +32 bytes = 16 bf16 along K
-              mma_ts(d_tmem, a_hi + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-              mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
-            }
-            mma_commit(&misc->empty[s_hi]);
-            wait_bar(&misc->full[s_lo], p_lo, misc, 205, a.status);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ts(d_tmem, a_hi + k * 8, wl + 2 * k, idesc, 1u);
-            mma_commit(&misc->empty[s_lo]);
-          } else {                                     // direction embedding: K = 32, both halves in TMEM
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              mma_ts(d_tmem, a_hi + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-              mma_ts(d_tmem, a_lo + k * 8, wh + 2 * k, idesc, 1u);
-            }
-            mma_commit(&misc->empty[s_hi]);
-            wait_bar(&misc->full[s_lo], p_lo, misc, 205, a.status);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 2; ++k) mma_ts(d_tmem, a_hi + k * 8, wl + 2 * k, idesc, 1u);
-            mma_commit(&misc->empty[s_lo]);
-          }
-          if (e.last) mma_commit(&misc->acc_full[e.acc]);
-        }
-        __syncwarp();
+        const int t = sb; sb = sa; sa = sf; sf = t;   // (a, b, f) <- (f, a, b)
+      }
+      {
+        // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> free slot
+        uint32_t accum = 0, d_tmem = tbase + TC_ACC;
+        need_epi(g0 + 14);
+        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+        need_epi(g0 + 15);
+        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+        issue_chunk<2, true>(misc, ring, ring_base, 0, tbase + TC_D, d_tmem, idesc128, accum, a.status, tbase + TC_D_LO);
+        finish(0);
+        // ---- folded instance hidden layer (step 17, acc 1): h -> slot of K-half 0
+        accum = 0; d_tmem = tbase + TC_ACC + 128;
+        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
+        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+        finish(1);
+        // ---- rgb head (step 18, acc 0, N=16) on the colour hidden slot
+        accum = 0; d_tmem = tbase + TC_ACC;
+        need_epi(g0 + 16);
+        slot_chunk(sf, 0, d_tmem, idesc16, accum); slot_chunk(sf, 1, d_tmem, idesc16, accum);
+        finish(0);
+        // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden slot
+        accum = 0; d_tmem = tbase + TC_ACC + 128;
+        need_epi(g0 + 17);
+        slot_chunk(sa, 0, d_tmem, idesc_ins, accum); slot_chunk(sa, 1, d_tmem, idesc_ins, accum);
+        finish(1);
       }
     }
   } else if (warp >= 4) {
@@ -723,30 +737,6 @@ static void build_program(Program& P, int ins_num) {
     for (int c = 0; c < 2 * P.step[i].n_chunks; ++c) { P.stage_off[si++] = off; off += (uint32_t)P.step[i].n * 128u; }
   P.stage_off[si] = off;               // sentinel: total image size
   P.n_stages = si;
-  // chunk table for the MMA issuer (same order as the stages: two stages per chunk)
-  int nc = 0;
-  for (int i = 0; i < N_STEPS; ++i) {
-    const Step& s = P.step[i];
-    for (int c = 0; c < s.n_chunks; ++c, ++nc) {
-      ChunkEnt& e = P.chunk[nc];
-      memset(&e, 0, sizeof(e));
-      const int kind = s.chunk[c];
-      uint32_t lo_smem = 0;
-      if (kind == CK_E) { lo_smem = SM_E; e.a_hi_tmem = TC_E; }
-      else if (kind == CK_D) { e.lo_tmem = 1; e.a_hi_tmem = TC_D; e.a_lo_tmem = TC_D_LO; }
-      else { lo_smem = SM_SLOT + kind * CHUNK_BYTES; e.a_hi_tmem = TC_SLOT + kind * 32; }
-      e.a_lo_desc = ((lo_smem & 0x3FFFFu) >> 4) | (1u << 16);
-      e.d_tmem = TC_ACC + (i & 1) * 128;
-      e.idesc = umma::make_idesc_bf16(128, s.n);
-      e.ks = s.ksteps[c];
-      e.first = (c == 0); e.last = (c == s.n_chunks - 1); e.acc = (int8_t)(i & 1);
-      e.wait_step = NO_WAIT;
-      if (c == 0) e.wait_step = (int8_t)(i - 2);                             // accumulator free (+ K-half 0 ready)
-      else if (c == 2 && (i % 2 == 0) && i >= 2 && i <= 16) e.wait_step = (int8_t)(i - 1);   // K-half 1 just produced
-      e.wait_inputs = (s.dep[c] < 0);
-    }
-  }
-  P.n_chunks = nc;
 }
 
 // ------------------------------------------------------------------------------------------------ host: packing
@@ -925,7 +915,6 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   memset(&a, 0, sizeof(a));
   a.image = (const uint8_t*)w.image; a.bias = w.bias; a.x = x; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.m = m; a.s = s; a.out = out; a.status = ex->d_status;
-  a.dbg_flags = getenv("DMNERF_DBG") ? atoi(getenv("DMNERF_DBG")) : 0;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   mlp_umma_kernel<false><<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
   DMN_LAUNCH_OK();
@@ -962,7 +951,6 @@ int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmner
   a.acc_c = io->acc_coarse; a.acc_f = io->acc_fine; a.ins_c = io->ins_coarse; a.ins_f = io->ins_fine;
   a.zc_out = io->z_vals_coarse; a.zf_out = io->z_vals_fine; a.wc_out = io->weights_coarse; a.wf_out = io->weights_fine;
   a.status = ex->d_status;
-  a.dbg_flags = getenv("DMNERF_DBG") ? atoi(getenv("DMNERF_DBG")) : 0;
   const int64_t units = (n + 1) / 2;
   const unsigned grid = (unsigned)(units < sms ? units : sms);
   mlp_umma_kernel<true><<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
