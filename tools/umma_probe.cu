@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
       const uint32_t* sm = (p.mode == 4) ? lo : hi;      // mode 4: A_lo in shared memory, A_hi in tensor memory
       *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk)) = make_uint4(sm[0], sm[1], sm[2], sm[3]);
       *reinterpret_cast<uint4*>(base + sw128_offset(tid, kk + 8)) = make_uint4(sm[4], sm[5], sm[6], sm[7]);
-      if (p.mode == 1 || p.mode == 4) tmem_st_x8(tA + lane_sel + k0 / 2, hi);
+      if (p.mode == 1 || p.mode == 4 || p.mode == 5) tmem_st_x8(tA + lane_sel + k0 / 2, hi);
       if (p.mode == 2) tmem_st_x8(tA + lane_sel + k0 / 2, lo);
     }
   }
@@ -105,12 +105,25 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
 
   const uint32_t idesc = make_idesc_bf16(128, N);
   long long t0 = 0, t1 = 0;
-  if (tid == 0) {
+  if (warp == 0) {                                   // converged warp, one elected lane issues (uniform-register operands)
     bool ok = true;
     if (p.mode == 3) ok = mbar_wait(&bar_load, 0);
     if (!ok) atomicExch(p.status, 10);
     tc_fence_after();
     t0 = clock64();
+    if (elect_one()) {
+    if (p.mode == 5 || p.mode == 6) {
+      // raw tensor-pipe rate: 32 MMAs per iteration, operands fixed, no address arithmetic between issues
+      const uint64_t db = make_sdesc_sw128(smem_u32(sBhi));
+      const uint64_t da0 = make_sdesc_sw128(smem_u32(sA));
+      for (int rep = 0; rep < p.reps; ++rep) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          if (p.mode == 5) mma_ts(tD, tA + (u & 3) * 8, db + 2 * (u & 3), idesc, (rep | u) ? 1u : 0u);
+          else mma_ss(tD, da0 + 2 * (u & 3), db + 2 * (u & 3), idesc, (rep | u) ? 1u : 0u);
+        }
+      }
+    } else
     for (int rep = 0; rep < p.reps; ++rep) {
       for (int k0 = 0; k0 < K; k0 += 16) {
         const int slab = k0 / 64, kk = k0 % 64;
@@ -144,6 +157,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
       }
     }
     mma_commit(&bar_mma);
+    }
+    __syncwarp();
   }
   const bool done = mbar_wait(&bar_mma, 0);
   if (tid == 0) {
@@ -216,7 +231,7 @@ static int run_case(const char* name, int mode, int N, int K, int reps, bool che
   CK(cudaMemcpy(&cyc, dCyc, 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&status, dStatus, 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dImg); cudaFree(dCyc); cudaFree(dStatus);
-  const int n_mma = reps * (K / 16) * ((mode == 2 || mode == 4) ? 3 : 1);
+  const int n_mma = (mode == 5 || mode == 6) ? reps * 32 : reps * (K / 16) * ((mode == 2 || mode == 4) ? 3 : 1);
   if (status) {
     printf("%-34s FAIL  status=%d (barrier timeout)\n", name, status);
     return 1;
@@ -270,6 +285,12 @@ int main() {
   run_case("time prod N=128 K=128 x64", 4, 128, 128, 64, false);
   run_case("time prod N=256 K=128 x64", 4, 256, 128, 64, false);
   run_case("time prod N=64  K=128 x64", 4, 64, 128, 64, false);
+  run_case("raw TS N=256 (unrolled x32)", 5, 256, 64, 64, false);
+  run_case("raw TS N=128 (unrolled x32)", 5, 128, 64, 64, false);
+  run_case("raw TS N=64  (unrolled x32)", 5, 64, 64, 64, false);
+  run_case("raw SS N=256 (unrolled x32)", 6, 256, 64, 64, false);
+  run_case("raw SS N=128 (unrolled x32)", 6, 128, 64, 64, false);
+  run_case("raw SS N=64  (unrolled x32)", 6, 64, 64, 64, false);
   printf("umma_probe: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }
