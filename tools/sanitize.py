@@ -1,0 +1,35 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dmnerf_b200 import synth, _lib                      # noqa: E402
+from dmnerf_b200.engine import get_context               # noqa: E402
+from dmnerf_b200.testing import make_models              # noqa: E402
+from dmnerf_b200.render import render_rays, dm_nerf      # noqa: E402
+from dmnerf_b200.backward import render_rays_grad        # noqa: E402
+from dmnerf_b200.helpers import get_rays_k, sample_pdf   # noqa: E402
+
+dev = "cuda"
+wl = synth.workload("dmsr_study")
+nc, nf, _, _ = make_models(1, 2, 13, dev)
+n = 37
+sel = np.linspace(0, 307199, n).astype(np.int64)
+ro, rd = torch.from_numpy(wl["rays_o"][sel]).to(dev), torch.from_numpy(wl["rays_d"][sel]).to(dev)
+z = (torch.linspace(0, 1, 64) * 11 + 4).to(dev)
+with torch.no_grad():
+    a = render_rays(ro, rd, nc, nf, z, want_raw=False, want_samples=True)          # fused kernel, odd ray count
+    b = render_rays(ro, rd, nc, nf, z, want_raw=True, impl=_lib.IMPL_UMMA)         # unfused tcgen05 + stage kernels
+    c = render_rays(ro, rd, nc, nf, z, want_raw=True, impl=_lib.IMPL_SIMT)         # fp32 kernels
+    o, d = get_rays_k(48, 64, wl["K"], torch.from_numpy(wl["c2w"]).to(dev))
+    s = sample_pdf(torch.sort(torch.rand(5, 63, device=dev)).values, torch.rand(5, 62, device=dev), 128, det=False)
+nc.train(); nf.train()
+out = render_rays_grad(ro, rd, nc, nf, z, perturb=1.0)
+(out["rgb_fine"].sum() + out["ins_fine"].sum() + out["raw_coarse"].sum() * 1e-3).backward()
+get_context(dev).sync_check()
+print("sanitize run ok", float(a["rgb_fine"].sum()), float(b["rgb_fine"].sum()), float(c["rgb_fine"].sum()))
