@@ -110,8 +110,8 @@ def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb
 class LazyRenderDict(dict):
     """Result of an inference dm_nerf() call.  The per-ray maps come from the single fused kernel; the per-sample tensors
     the reference also returns (`raw_*`, `z_vals_*`: consumed only by the training-time penalizer) are produced on
-    first access by re-rendering through the unfused kernels with the same random draws, after which every entry is
-    replaced by that consistent set."""
+    first access by re-rendering through the stage-by-stage kernels with the same random draws; entries that already exist
+    (the per-ray maps, possibly sliced by the caller) are left untouched."""
     LAZY = ("raw_fine", "raw_coarse", "z_vals_fine", "z_vals_coarse", "weights_fine", "weights_coarse")
 
     def __init__(self, data, rerender):
@@ -121,7 +121,9 @@ class LazyRenderDict(dict):
     def _materialise(self):
         if self._rerender is not None:
             full, self._rerender = self._rerender(), None
-            super().update(full)
+            for k, v in full.items():
+                if not super().__contains__(k):
+                    super().__setitem__(k, v)
 
     def __missing__(self, key):
         if key in self.LAZY and self._rerender is not None:

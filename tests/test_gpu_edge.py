@@ -1,0 +1,111 @@
+"""GPU: edge cases of the call surface -- empty / ragged batches, per-ray coarse depths, the ScanNet N_ins slice,
+the widest object head, keep-all-instance-channels, no_grad + perturb through dm_nerf, non-contiguous inputs."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from dmnerf_b200 import synth, _lib
+from dmnerf_b200.testing import make_models
+
+DEV = "cuda"
+
+
+def _rays(n, name="dmsr_study"):
+    wl = synth.workload(name)
+    sel = np.linspace(0, 307199, max(n, 1)).astype(np.int64)[:n]
+    return wl, torch.from_numpy(wl["rays_o"][sel]).to(DEV), torch.from_numpy(wl["rays_d"][sel]).to(DEV)
+
+
+def test_empty_batch_and_single_ray():
+    from dmnerf_b200.render import render_rays
+    wl, ro, rd = _rays(3)
+    nc, nf, _, _ = make_models(1, 2, 13, DEV)
+    z = torch.linspace(4, 15, 64, device=DEV)
+    with torch.no_grad():
+        for want_raw in (False, True):
+            out = render_rays(ro[:0], rd[:0], nc, nf, z, want_raw=want_raw)
+            assert out["rgb_fine"].shape == (0, 3) and out["ins_fine"].shape == (0, 13)
+            one = render_rays(ro[:1], rd[:1], nc, nf, z, want_raw=want_raw)
+            three = render_rays(ro, rd, nc, nf, z, want_raw=want_raw)
+            assert torch.isfinite(one["rgb_fine"]).all()
+            if not want_raw:
+                assert torch.equal(one["rgb_fine"], three["rgb_fine"][:1])       # rays are independent units
+
+
+@pytest.mark.parametrize("want_raw", [False, True])
+def test_per_ray_coarse_depths_match_shared_row(want_raw):
+    """z_vals_coarse may be a real [N,S] tensor (reference: any tensor broadcastable in render.py:49) or the stride-0
+    expand that z_val_sample returns: both must give the same render."""
+    from dmnerf_b200.render import render_rays
+    from dmnerf_b200.helpers import z_val_sample
+    wl, ro, rd = _rays(130)
+    nc, nf, _, _ = make_models(1, 2, 13, DEV)
+    zs = z_val_sample(130, wl["near"], wl["far"], 64, device=DEV)
+    with torch.no_grad():
+        a = render_rays(ro, rd, nc, nf, zs, want_raw=want_raw)
+        b = render_rays(ro, rd, nc, nf, zs.contiguous(), want_raw=want_raw)          # materialised [N,S]
+    for k in ("rgb_fine", "depth_fine", "ins_fine", "rgb_coarse"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_scannet_n_ins_slice_and_perturb_without_grad():
+    """render.py:88-90: with args.is_train and args.N_ins only the last N_ins rays keep instance maps; perturb > 0 under
+    no_grad (manipulator-style) must consume the two uniform draws in the reference's order."""
+    from dmnerf_b200.render import dm_nerf
+    from dmnerf_b200.embedder import get_embedder
+    from dmnerf_b200.helpers import z_val_sample
+    wl, ro, rd = _rays(64)
+    nc, nf, _, _ = make_models(1, 2, 13, DEV)
+    pe, ve = get_embedder(10)[0], get_embedder(4)[0]
+    zc = z_val_sample(64, wl["near"], wl["far"], 64, device=DEV)
+    args = types.SimpleNamespace(perturb=1.0, N_importance=128, is_train=True, N_ins=20)
+    with torch.no_grad():
+        torch.manual_seed(11)
+        out = dm_nerf(torch.stack([ro, rd], 0), pe, ve, nc, nf, zc, args)
+        torch.manual_seed(11)
+        t_rand, u = torch.rand((64, 64), device=DEV), torch.rand((64, 128), device=DEV)
+        from dmnerf_b200.render import render_rays
+        ref = render_rays(ro, rd, nc, nf, zc, perturb=1.0, t_rand=t_rand, u=u, want_raw=False)
+    assert out["ins_fine"].shape == (20, 13) and out["ins_coarse"].shape == (20, 13) and out["rgb_fine"].shape == (64, 3)
+    assert torch.equal(out["rgb_fine"], ref["rgb_fine"]) and torch.equal(out["ins_fine"], ref["ins_fine"][-20:])
+    zf = out["z_vals_fine"]                                             # lazily materialised per-sample outputs
+    assert zf.shape == (64, 192) and bool((zf[:, 1:] >= zf[:, :-1]).all())
+
+
+def test_widest_object_head_and_keep_all_channels():
+    from dmnerf_b200.render import render_rays
+    wl, ro, rd = _rays(70)
+    nc, nf, _, _ = make_models(5, 6, 127, DEV)                           # ins_num + 1 = 128 output columns: the maximum
+    z = torch.linspace(4, 15, 64, device=DEV)
+    with torch.no_grad():
+        fused = render_rays(ro, rd, nc, nf, z, want_raw=False)
+        staged = render_rays(ro, rd, nc, nf, z, want_raw=True)
+        keep = render_rays(ro, rd, nc, nf, z, want_raw=False, keep_all_ins=True)
+    assert fused["ins_fine"].shape == (70, 127) and staged["raw_fine"].shape == (70, 192, 132) and keep["ins_fine"].shape == (70, 128)
+    np.testing.assert_allclose(fused["ins_coarse"].cpu().numpy(), staged["ins_coarse"].cpu().numpy(), rtol=1e-4, atol=5e-6)
+    np.testing.assert_allclose(keep["ins_fine"][:, :-1].cpu().numpy(), fused["ins_fine"].cpu().numpy(), rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        from dmnerf_b200.model import DM_NeRF
+        DM_NeRF(8, 256, 63, 27, [4], 128)
+
+
+def test_non_contiguous_and_batched_inputs():
+    from dmnerf_b200.render import render_train
+    from dmnerf_b200.embedder import get_embedder
+    from dmnerf_b200.helpers import sample_pdf
+    raw = torch.randn(6, 40, 18 * 2, device=DEV)[..., ::2]                # non-contiguous channel stride
+    z = torch.sort(torch.rand(6, 40, device=DEV) * 5 + 1).values
+    rd = torch.randn(6, 3, device=DEV)
+    a = render_train(raw, z, rd)
+    b = render_train(raw.contiguous(), z, rd)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    x = torch.randn(2, 5, 7, 3, device=DEV)                               # leading dims are preserved
+    assert get_embedder(10)[0].embed(x).shape == (2, 5, 7, 63)
+    bins = torch.sort(torch.rand(2, 3, 63, device=DEV)).values
+    s = sample_pdf(bins, torch.rand(2, 3, 62, device=DEV), 16, det=True)
+    assert s.shape == (2, 3, 16) and bool((s[..., 1:] >= s[..., :-1] - 1e-6).all())
+    assert isinstance(get_embedder(0, -1)[0], torch.nn.Identity)
