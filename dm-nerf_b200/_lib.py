@@ -53,8 +53,9 @@ PROTOTYPES = {
     "dmnerf_act_floats_per_sample": (C.c_int, []),
     "dmnerf_mlp_backward_scratch_floats": (C.c_int64, [C.c_int64]),
     "dmnerf_mlp_forward_train": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_int, _f32p, _f32p,
-                                           C.c_void_p]),
-    "dmnerf_mlp_backward": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.POINTER(C.c_void_p), _f32p, C.c_void_p]),
+                                           C.c_int, C.c_void_p]),
+    "dmnerf_mlp_backward": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.POINTER(C.c_void_p), _f32p, C.c_int,
+                                      C.c_void_p]),
     "dmnerf_composite_backward": (C.c_int, [_f32p, _f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p,
                                             _f32p, _f32p, C.c_int, C.c_void_p]),
     "dmnerf_render_forward": (C.c_int, [C.c_void_p, C.POINTER(RenderIO), C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

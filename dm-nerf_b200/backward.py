@@ -1,17 +1,25 @@
 """Differentiable entry points (torch.autograd.Function over the native forward/backward kernels).
 
-The training forward evaluates the networks with the exact-fp32 CUDA-core kernel and keeps the activations the backward
-needs (dmnerf_mlp_forward_train); the backward is composite_backward (closed-form reverse scan) followed by the per-layer
-GEMMs of dmnerf_mlp_backward.  Gradient topology is the reference's: no gradient through sample_pdf
+The training forward evaluates the networks with the tensor-core kernel (or the exact-fp32 CUDA-core kernel, see
+TRAIN_IMPL) and keeps the activations the backward needs (dmnerf_mlp_forward_train); the backward is composite_backward
+(closed-form reverse scan) followed by the per-layer GEMMs of dmnerf_mlp_backward.  Gradient topology is the reference's: no gradient through sample_pdf
 (render.py:68), the instance map sees detached weights (render.py:22-23), the instance branch sees h.detach()
 (dm_nerf.py:95), rays / depths carry no gradient.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 from .engine import get_context, ordered_params
+
+# Kernel used by the training forward: the tensor-core kernel by default ("umma"), or the exact-fp32 CUDA-core kernel ("simt").
+TRAIN_IMPL = _lib.IMPL_SIMT if os.environ.get("DMNERF_TRAIN_IMPL", "umma").lower() == "simt" else _lib.IMPL_UMMA
+
+
+def _train_impl(impl):
+    return TRAIN_IMPL if impl == _lib.IMPL_AUTO else impl
 
 
 def _f32(t):
@@ -22,13 +30,13 @@ def _zeros_like_params(params):
     return [torch.empty_like(p) for p in params]
 
 
-def _mlp_backward(ctx, slot, acts, d_out, m, params):
+def _mlp_backward(ctx, slot, acts, d_out, m, params, feats_missing):
     grads = _zeros_like_params(params)
     n_scratch = int(ctx.lib.dmnerf_mlp_backward_scratch_floats(m))
     scratch = torch.empty(max(n_scratch, 1), device=d_out.device, dtype=torch.float32)
     arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
     _lib.check(ctx.lib.dmnerf_mlp_backward(ctx.handle, slot, _lib.ptr(acts), _lib.ptr(d_out), m, arr, _lib.ptr(scratch),
-                                           ctx.stream()), "dmnerf_mlp_backward")
+                                           int(feats_missing), ctx.stream()), "dmnerf_mlp_backward")
     return grads
 
 
@@ -45,9 +53,10 @@ class MLPFunction(torch.autograd.Function):
         m = x2.shape[0]
         out = torch.empty((m, 4 + ins_num + 1), device=x.device, dtype=torch.float32)
         acts = torch.empty(max(m * ctx.lib.dmnerf_act_floats_per_sample(), 1), device=x.device, dtype=torch.float32)
+        impl = _train_impl(impl)
         _lib.check(ctx.lib.dmnerf_mlp_forward_train(ctx.handle, slot, _lib.ptr(x2), None, None, None, m, 1, _lib.ptr(out),
-                                                    _lib.ptr(acts), ctx.stream()), "dmnerf_mlp_forward_train")
-        fctx.model, fctx.m, fctx.acts, fctx.params = model, m, acts, params
+                                                    _lib.ptr(acts), impl, ctx.stream()), "dmnerf_mlp_forward_train")
+        fctx.model, fctx.m, fctx.acts, fctx.params, fctx.feats_missing = model, m, acts, params, impl != _lib.IMPL_SIMT
         return out.reshape(*x.shape[:-1], out.shape[-1])
 
     @staticmethod
@@ -56,7 +65,7 @@ class MLPFunction(torch.autograd.Function):
         slot = ctx.slot_for(fctx.model)
         ctx.bind(slot, fctx.model)
         d_out = _f32(g_out.reshape(fctx.m, -1))
-        grads = _mlp_backward(ctx, slot, fctx.acts, d_out, fctx.m, fctx.params)
+        grads = _mlp_backward(ctx, slot, fctx.acts, d_out, fctx.m, fctx.params, fctx.feats_missing)
         return (None, None, None) + tuple(grads)
 
 
@@ -98,10 +107,11 @@ class RenderFunction(torch.autograd.Function):
     """dm_nerf() (networks/render.py:31-96) for training: forward + backward through both networks."""
 
     @staticmethod
-    def forward(fctx, model_c, model_f, rays_o, rays_d, z_in, z_stride, t_rand, u, n_importance, n_c, *params):
+    def forward(fctx, model_c, model_f, rays_o, rays_d, z_in, z_stride, t_rand, u, n_importance, n_c, impl, *params):
         dev = rays_o.device
         ctx = get_context(dev)
         lib = ctx.lib
+        impl = _train_impl(impl)
         ins_num = ctx.bind(0, model_c)
         if ctx.bind(1, model_f) != ins_num:
             raise RuntimeError("coarse and fine networks disagree on ins_num")
@@ -123,7 +133,7 @@ class RenderFunction(torch.autograd.Function):
             raw = e(n, ns, Cc)
             acts = e(max(n * ns * apf, 1))
             _lib.check(lib.dmnerf_mlp_forward_train(ctx.handle, net, None, _lib.ptr(rays_o), _lib.ptr(rays_d), _lib.ptr(o[zkey]),
-                                                    n * ns, ns, _lib.ptr(raw), _lib.ptr(acts), st), "dmnerf_mlp_forward_train")
+                                                    n * ns, ns, _lib.ptr(raw), _lib.ptr(acts), impl, st), "dmnerf_mlp_forward_train")
             rgb, w, depth, acc, ins = e(n, 3), e(n, ns), e(n), e(n), e(n, ins_num)
             _lib.check(lib.dmnerf_composite(_lib.ptr(raw), _lib.ptr(o[zkey]), _lib.ptr(rays_d), n, ns, Cc, 0, _lib.ptr(rgb),
                                             _lib.ptr(w), _lib.ptr(depth), _lib.ptr(ins), _lib.ptr(acc), st), "dmnerf_composite")
@@ -133,6 +143,7 @@ class RenderFunction(torch.autograd.Function):
         fctx.models = (model_c, model_f)
         fctx.n, fctx.S, fctx.F, fctx.C, fctx.n_c = n, S, F, Cc, n_c
         fctx.acts = saved
+        fctx.feats_missing = impl != _lib.IMPL_SIMT
         fctx.params = params
         fctx.save_for_backward(rays_d, o["z_vals_coarse"], o["z_vals_fine"], o["raw_coarse"], o["raw_fine"])
         outs = tuple(o[k] for k in _OUT_KEYS)
@@ -160,13 +171,13 @@ class RenderFunction(torch.autograd.Function):
                                                      _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]), _lib.ptr(keep[3]),
                                                      _lib.ptr(keep[4]), _lib.ptr(d_raw), accumulate, st), "dmnerf_composite_backward")
             params = fctx.params[:fctx.n_c] if net == 0 else fctx.params[fctx.n_c:]
-            all_grads += _mlp_backward(ctx, net, fctx.acts[net], d_raw.reshape(n * ns, Cc), n * ns, params)
+            all_grads += _mlp_backward(ctx, net, fctx.acts[net], d_raw.reshape(n * ns, Cc), n * ns, params, fctx.feats_missing)
         fctx.acts = None
-        return (None,) * 10 + tuple(all_grads)
+        return (None,) * 11 + tuple(all_grads)
 
 
 def render_rays_grad(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb=0.0, N_importance=128,
-                     t_rand=None, u=None):
+                     t_rand=None, u=None, impl=_lib.IMPL_AUTO):
     """Training-mode dm_nerf(): same dict as render.render_rays, differentiable w.r.t. both networks' parameters."""
     dev = rays_o.device
     if dev.type != "cuda":
@@ -187,5 +198,6 @@ def render_rays_grad(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, pe
         t_rand = u = None
     pc, _ = ordered_params(model_coarse)
     pf, _ = ordered_params(model_fine)
-    outs = RenderFunction.apply(model_coarse, model_fine, rays_o, rays_d, z_in, z_stride, t_rand, u, N_importance, len(pc), *pc, *pf)
+    outs = RenderFunction.apply(model_coarse, model_fine, rays_o, rays_d, z_in, z_stride, t_rand, u, N_importance, len(pc),
+                                _train_impl(impl), *pc, *pf)
     return dict(zip(_OUT_KEYS, outs))

@@ -48,6 +48,7 @@ struct dmnerf_ctx {
   UmmaWeights packed[2];          // tensor-core operand images (umma_api.cuh)
   Scratch ws_raw_c, ws_raw_f, ws_z_c, ws_z_f, ws_w_c, ws_w_f;
   Scratch host_in, host_out;      // device staging for the *_host entry point
+  bool train_feats_missing[2] = {false, false};
   bool profiling = false;
   bool last_fused = false;       // the last render call took the single-kernel path
   bool profile_valid = false;
@@ -124,7 +125,7 @@ static int mlp_dispatch(dmnerf_ctx* ctx, int net, const float* x, const float* r
   DMN_CHECK(out != nullptr, "mlp: out is NULL");
   if (impl == DMNERF_IMPL_AUTO) impl = umma_available(ctx->packed[net]) ? DMNERF_IMPL_UMMA : DMNERF_IMPL_SIMT;
   if (impl == DMNERF_IMPL_UMMA)
-    return launch_mlp_umma(ctx->packed[net], ctx->net[net], x, ro, rd, z, m, s, out, st);
+    return launch_mlp_umma(ctx->packed[net], ctx->net[net], x, ro, rd, z, m, s, out, nullptr, st);
   return launch_mlp_simt(ctx->net[net], x, ro, rd, z, m, s, out, nullptr, st);
 }
 
@@ -184,22 +185,27 @@ DMNERF_API int dmnerf_act_floats_per_sample(void) { return ACT_FLOATS_PER_SAMPLE
 DMNERF_API int64_t dmnerf_mlp_backward_scratch_floats(int64_t m) { return (int64_t)mlp_backward_scratch_floats(m); }
 
 DMNERF_API int dmnerf_mlp_forward_train(dmnerf_ctx* ctx, int net, const float* x, const float* rays_o, const float* rays_d,
-                                        const float* z, int64_t m, int s, float* out, float* acts, void* stream) {
+                                        const float* z, int64_t m, int s, float* out, float* acts, int impl, void* stream) {
   DMN_CHECK(ctx != nullptr, "mlp_forward_train: ctx is NULL");
   DMN_CHECK(net == 0 || net == 1, "mlp_forward_train: net must be 0 or 1");
   DMN_CHECK(m >= 0 && s >= 1, "mlp_forward_train: bad sizes");
   if (m == 0) return 0;
   DMN_CHECK(out && acts, "mlp_forward_train: out / acts is NULL");
+  DMN_CHECK(impl >= DMNERF_IMPL_AUTO && impl <= DMNERF_IMPL_UMMA, "mlp_forward_train: unknown impl %d", impl);
+  if (impl == DMNERF_IMPL_AUTO) impl = umma_available(ctx->packed[net]) ? DMNERF_IMPL_UMMA : DMNERF_IMPL_SIMT;
+  ctx->train_feats_missing[net] = (impl == DMNERF_IMPL_UMMA);
+  if (impl == DMNERF_IMPL_UMMA)
+    return launch_mlp_umma(ctx->packed[net], ctx->net[net], x, rays_o, rays_d, z, m, s, out, acts, (cudaStream_t)stream);
   return launch_mlp_simt(ctx->net[net], x, rays_o, rays_d, z, m, s, out, acts, (cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const float* d_out, int64_t m, float* const* grads,
-                                   float* scratch, void* stream) {
+                                   float* scratch, int feats_missing, void* stream) {
   DMN_CHECK(ctx != nullptr, "mlp_backward: ctx is NULL");
   DMN_CHECK(net == 0 || net == 1, "mlp_backward: net must be 0 or 1");
   DMN_CHECK(m >= 0 && grads, "mlp_backward: bad arguments");
   DMN_CHECK(m == 0 || (acts && d_out && scratch), "mlp_backward: NULL buffer");
-  return launch_mlp_backward(ctx->net[net], acts, d_out, m, grads, scratch, (cudaStream_t)stream);
+  return launch_mlp_backward(ctx->net[net], acts, d_out, m, grads, scratch, feats_missing, (cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c,

@@ -251,6 +251,58 @@ static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, i
   return 0;
 }
 
+// C[m, n] = bias[n] + sum_k A[m, k] W[n, k]   (a Linear layer: W row-major [N, K])
+__global__ void __launch_bounds__(256) gemm_nt_bias_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                           const float* __restrict__ bias, float* __restrict__ Cm, int ldc,
+                                                           int64_t M, int N, int K) {
+  __shared__ float As[GK][GT + 1];
+  __shared__ float Ws[GK][GT + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * GT;
+  const int n0 = blockIdx.y * GT;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int idx = tid; idx < GT * GK; idx += 256) {
+      const int r = idx / GK, c = idx % GK;
+      const int64_t mm = m0 + r;
+      As[c][r] = (mm < M && k0 + c < K) ? A[mm * lda + k0 + c] : 0.0f;
+      Ws[c][r] = (n0 + r < N && k0 + c < K) ? W[(size_t)(n0 + r) * ldw + k0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < N) Cm[mm * ldc + n] = acc[i][j] + bias[n];
+    }
+  }
+}
+
+static int gemm_nt_bias(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int64_t M, int N,
+                        int K, cudaStream_t st) {
+  dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT));
+  gemm_nt_bias_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st) {
   const int tiles = ((N + GT - 1) / GT) * ((K + GT - 1) / GT);
   int64_t splits = (4 * 148 + tiles - 1) / tiles;
@@ -276,7 +328,7 @@ size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (2 * 128 + 4 
 
 // grads: 30 device pointers in state_dict order (weight, bias per layer); overwritten with the gradient of this call.
 int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads, float* scratch,
-                        cudaStream_t st) {
+                        int feats_missing, cudaStream_t st) {
   DMN_CHECK(p.bound, "mlp_backward: weights not bound");
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   for (int l = 0; l < N_LAYERS; ++l) {
@@ -296,6 +348,11 @@ int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int
   auto gb = [&](int l) { return grads[2 * l + 1]; };
   int rc = 0;
 #define R(x) do { if ((rc = (x))) return rc; } while (0)
+  if (feats_missing) {
+    // the tensor-core forward folds rgb_feature_linear / ins_feature_linear away: rebuild the two planes from h7
+    R(gemm_nt_bias(ap.h[7], 256, p.w[L_RGB_FEAT], 256, p.b[L_RGB_FEAT], ap.rgb_feat, 256, m, 256, 256, st));
+    R(gemm_nt_bias(ap.h[7], 256, p.w[L_INS_FEAT], 256, p.b[L_INS_FEAT], ap.ins_feat, 256, m, 256, 256, st));
+  }
   const float* d_rgb = d_out;           // [m, 3]       lda = C
   const float* d_sig = d_out + 3;       // [m, 1]
   const float* d_ins = d_out + 4;       // [m, ins1]

@@ -46,7 +46,8 @@ __host__ __device__ inline int layer_in(int l) {
 }
 
 // Activations saved by the training forward of one network (planes of row-major [M, width] matrices, in this order):
-//   emb [M,90] | H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128]
+//   H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128] | emb [M,90]
+// (the 90-wide plane comes last so every other plane starts 16-byte aligned for any M)
 constexpr int ACT_FLOATS_PER_SAMPLE = CH_IN + 8 * W_HID + 2 * W_HID + 2 * (W_HID / 2);   // 2906
 struct ActPlanes {
   float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid;
@@ -54,12 +55,12 @@ struct ActPlanes {
 __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
   ActPlanes a;
   float* p = base;
-  a.emb = p; p += m * CH_IN;
   for (int l = 0; l < 8; ++l) { a.h[l] = p; p += m * W_HID; }
   a.rgb_feat = p; p += m * W_HID;
   a.ins_feat = p; p += m * W_HID;
   a.rgb_hid = p; p += m * (W_HID / 2);
-  a.ins_hid = p;
+  a.ins_hid = p; p += m * (W_HID / 2);
+  a.emb = p;
   return a;
 }
 
@@ -108,8 +109,10 @@ int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, con
 int launch_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all,
                               const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_ins,
                               const float* g_weights, float* d_raw, int accumulate, cudaStream_t st);
+// feats_missing != 0: the forward that filled `acts` did not materialise rgb_feat / ins_feat (tensor-core kernel, folded
+// heads); the backward recomputes those two planes from h7 first.
 int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads,
-                        float* scratch, cudaStream_t st);
+                        float* scratch, int feats_missing, cudaStream_t st);
 size_t mlp_backward_scratch_floats(int64_t m);
 
 }  // namespace dmnerf

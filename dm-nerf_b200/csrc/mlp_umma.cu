@@ -112,6 +112,7 @@ struct KArgs {
   int64_t m;
   int32_t s;                   // samples per ray (rays mode)
   float* out;                  // [M, C]
+  float* acts;                 // training forward (RAW mode): ActPlanes base, or nullptr
   int32_t* status;             // device error word
 };
 
@@ -220,6 +221,12 @@ __device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t t
   for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
   tmem_st_x16(tmem_hi, hi);
   tmem_st_x16(tmem_lo, lo);
+}
+
+// 32 consecutive fp32 values of one row to global memory (training forward keeps the activations, common.cuh ActPlanes).
+__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -398,16 +405,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         validp = rowp < a.m;
       }
       float vals[32];
+      auto save_emb = [&](const float* v, int col0, int cnt) {          // training forward: keep the embedded inputs
+        if constexpr (!FUSED) {
+          if (a.acts && validp) {
+            float* dst = act_planes(a.acts, a.m).emb + rowp * CH_IN + col0;
+            for (int i = 0; i < cnt; ++i) dst[i] = v[i];
+          }
+        }
+      };
       if (!FUSED && a.x) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int e = 32 * q + i;
           vals[i] = (validp && e < CH_POS) ? a.x[rowp * CH_IN + e] : 0.0f;
         }
+        save_emb(vals, 32 * q, q == 0 ? 32 : 31);
         store_split32(vals, e_slab, r, 32 * q, tbase + lane_sel + TC_E + 16 * q);
         if (q == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) vals[i] = (validp && i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + i] : 0.0f;
+          save_emb(vals, CH_POS, CH_DIR);
           store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
         }
       } else {
@@ -452,12 +469,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
+          save_emb(vals, 0, 32);
           store_split32(vals, e_slab, r, 0, tbase + lane_sel + TC_E);
           fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
           if (!validp) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
+          save_emb(vals, CH_POS, CH_DIR);
           store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
         } else {
           fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
@@ -465,6 +484,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
+          save_emb(vals, 32, 31);
           store_split32(vals, e_slab, r, 32, tbase + lane_sel + TC_E + 16);
         }
       }
@@ -473,6 +493,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       tc_fence_before();
       mbar_arrive(&misc->inputs_ready);
     };
+    (void)0;
     // may tile tp be prepared during tile tp-1?  (the first fine tile of a pair needs this tile's importance samples)
     auto early_ok = [&](int64_t tp) { return tp < my_tiles && (!FUSED || (tp & 3) != 1); };
 
@@ -536,6 +557,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 dens_acc = fmaf(f[4 * jj + 1], ww.y, dens_acc);
                 dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
                 dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
+              }
+            }
+            if constexpr (!FUSED) {
+              if (a.acts && valid) {                   // training forward: keep the post-activation values (ActPlanes)
+                const ActPlanes ap = act_planes(a.acts, a.m);
+                float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
+                                      : ((t == 16) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
+                store_row32(dst + q * 64 + h * 32, f);
               }
             }
             store_split32(f, slab, r, h * 32, hi_addr + h * 16);
@@ -896,7 +925,7 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
 }
 
 int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, const float* rays_o, const float* rays_d,
-                    const float* z, int64_t m, int s, float* out, cudaStream_t st) {
+                    const float* z, int64_t m, int s, float* out, float* acts, cudaStream_t st) {
   using namespace uk;
   DMN_CHECK(w.ready && w.extra, "mlp(umma): weights not packed (call dmnerf_set_weights first)");
   DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr && z != nullptr), "mlp(umma): pass either x or rays");
@@ -914,7 +943,7 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   KArgs a;
   memset(&a, 0, sizeof(a));
   a.image = (const uint8_t*)w.image; a.bias = w.bias; a.x = x; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
-  a.m = m; a.s = s; a.out = out; a.status = ex->d_status;
+  a.m = m; a.s = s; a.out = out; a.acts = acts; a.status = ex->d_status;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   mlp_umma_kernel<false><<<grid, N_THREADS, SMEM_BYTES, st>>>(ex->prog, a);
   DMN_LAUNCH_OK();

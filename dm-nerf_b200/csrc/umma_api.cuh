@@ -22,7 +22,7 @@ bool umma_available(const UmmaWeights& w);
 // Synchronises `st` and fails if the kernel raised a protocol error (bounded wait expired).
 int umma_check_status(const UmmaWeights& w, cudaStream_t st);
 int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, const float* rays_o, const float* rays_d,
-                    const float* z, int64_t m, int s, float* out, cudaStream_t st);
+                    const float* z, int64_t m, int s, float* out, float* acts, cudaStream_t st);
 
 // Fused whole-pipeline launch (64 + 128 samples, no raw output): see mlp_umma.cu.
 int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmnerf_render_io* io, int64_t n, int flags,

@@ -130,16 +130,17 @@ DMNERF_API int dmnerf_act_floats_per_sample(void);
 DMNERF_API int64_t dmnerf_mlp_backward_scratch_floats(int64_t m);
 
 /* DM_NeRF.forward with saved activations.  Pass either x [M,90] (rays_* NULL) or rays_o/rays_d [N,3] + z [N,S] (x NULL,
- * m = N*S).  out [M,C]. */
+ * m = N*S).  out [M,C].  impl: DMNERF_IMPL_SIMT = exact fp32; DMNERF_IMPL_UMMA / AUTO = the tensor-core kernel, whose folded heads
+ * do not produce the rgb_feature / ins_feature planes -- pass feats_missing = 1 to dmnerf_mlp_backward in that case. */
 DMNERF_API int dmnerf_mlp_forward_train(dmnerf_ctx* ctx, int net, const float* x, const float* rays_o, const float* rays_d,
-                             const float* z, int64_t m, int s, float* out, float* acts, void* stream);
+                             const float* z, int64_t m, int s, float* out, float* acts, int impl, void* stream);
 
 /* Gradient of a scalar loss w.r.t. the 30 parameters of network `net` given d_out = dL/d(out) [M,C] and the activations
  * saved by dmnerf_mlp_forward_train.  grads: 30 device buffers (state_dict order, parameter shapes), overwritten.
  * Gradient routing follows the reference (networks/dm_nerf.py:95: the instance branch reads h.detach()).
  * scratch: dmnerf_mlp_backward_scratch_floats(m) floats. */
 DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const float* d_out, int64_t m, float* const* grads,
-                        float* scratch, void* stream);
+                        float* scratch, int feats_missing, void* stream);
 
 /* Backward of render_train (networks/render.py:6-28): upstream gradients of rgb_map [N,3], depth_map [N], acc_map [N],
  * ins_map [N, C-5 | C-4] and weights [N,S] (any may be NULL) -> d_raw [N,S,C] (added to d_raw when accumulate != 0).
