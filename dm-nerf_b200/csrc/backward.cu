@@ -243,8 +243,134 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
   }
 }
 
+
+// ================================================================================================ 128x128 register-tiled GEMMs
+// Used for the 256/128-wide layers (row strides multiple of 4 floats, inner dimension multiple of 8); the small generic
+// kernels above keep the odd shapes (3 / 1 / ins_num+1 wide heads, 63- and 27-wide embeddings).
+constexpr int BT = 128;     // output tile BT x BT, 256 threads, 8x8 outputs per thread
+constexpr int BK = 8;       // inner slice
+
+__device__ __forceinline__ void fma_8x8(float (&acc)[8][8], const float* __restrict__ as, const float* __restrict__ bs, int ty, int tx) {
+  const float4 a0 = *reinterpret_cast<const float4*>(as + ty * 8), a1 = *reinterpret_cast<const float4*>(as + ty * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(bs + tx * 8), b1 = *reinterpret_cast<const float4*>(bs + tx * 8 + 4);
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+}
+
+// C[m, k] (= | +=) sum_n A[m, n] B[n, k], optional ReLU mask.  M arbitrary, N % 8 == 0, K % 4 == 0, lda/ldb/ldc % 4 == 0.
+__global__ void __launch_bounds__(256) gemm_nn_big_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                          float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int accumulate,
+                                                          const float* __restrict__ mask) {
+  __shared__ __align__(16) float As[2][BK][BT];
+  __shared__ __align__(16) float Bs[2][BK][BT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BT;
+  const int k0 = blockIdx.y * BT;
+  const int ar = tid >> 1, ac = (tid & 1) * 4;          // A slice: row ar, inner offset ac (float4 along the inner dimension)
+  const int br = tid >> 5, bc = (tid & 31) * 4;         // B slice: inner row br, columns bc..bc+3
+  float acc[8][8] = {};
+  float4 ra, rb;
+  auto load = [&](int n0) {
+    const int64_t m = m0 + ar;
+    ra = (m < M) ? *reinterpret_cast<const float4*>(A + m * lda + n0 + ac) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = (k0 + bc < K) ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + br) * ldb + k0 + bc) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto stash = [&](int buf) {
+    As[buf][ac + 0][ar] = ra.x; As[buf][ac + 1][ar] = ra.y; As[buf][ac + 2][ar] = ra.z; As[buf][ac + 3][ar] = ra.w;
+    *reinterpret_cast<float4*>(&Bs[buf][br][bc]) = rb;
+  };
+  load(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int n0 = 0; n0 < N; n0 += BK) {
+    if (n0 + BK < N) load(n0 + BK);                     // prefetch the next slice into registers
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) fma_8x8(acc, As[buf][kk], Bs[buf][kk], ty, tx);
+    if (n0 + BK < N) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4 += 4) {
+      const int k = k0 + tx * 8 + j4;
+      if (k >= K) continue;
+      float4 v = make_float4(acc[i][j4], acc[i][j4 + 1], acc[i][j4 + 2], acc[i][j4 + 3]);
+      float* cp = Cm + m * ldc + k;
+      if (accumulate) { const float4 o = *reinterpret_cast<const float4*>(cp); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      if (mask) {
+        const float4 mk = *reinterpret_cast<const float4*>(mask + m * ldc + k);
+        if (!(mk.x > 0.f)) v.x = 0.f; if (!(mk.y > 0.f)) v.y = 0.f; if (!(mk.z > 0.f)) v.z = 0.f; if (!(mk.w > 0.f)) v.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(cp) = v;
+    }
+  }
+}
+
+// C[n, k] += sum_{m in split} A[m, n] B[m, k].  N % 4 == 0, K % 4 == 0, lda/ldb % 4 == 0; rows_per_split % 8 == 0.
+__global__ void __launch_bounds__(256) gemm_tn_big_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                          float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int64_t rows_per_split) {
+  __shared__ __align__(16) float As[2][BK][BT];
+  __shared__ __align__(16) float Bs[2][BK][BT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * BT, k0 = blockIdx.y * BT;
+  const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t me = (mb + rows_per_split < M) ? mb + rows_per_split : M;
+  const int lr = tid >> 5, lc = (tid & 31) * 4;         // slice row lr (sample), columns lc..lc+3
+  float acc[8][8] = {};
+  float4 ra, rb;
+  auto load = [&](int64_t m0) {
+    const int64_t m = m0 + lr;
+    const bool ok = m < me;
+    ra = (ok && n0 + lc < N) ? *reinterpret_cast<const float4*>(A + m * lda + n0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = (ok && k0 + lc < K) ? *reinterpret_cast<const float4*>(B + m * ldb + k0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto stash = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lr][lc]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = rb;
+  };
+  load(mb);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t m0 = mb; m0 < me; m0 += BK) {
+    if (m0 + BK < me) load(m0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) fma_8x8(acc, As[buf][kk], Bs[buf][kk], ty, tx);
+    if (m0 + BK < me) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int nn = n0 + ty * 8 + i;
+    if (nn >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + tx * 8 + j;
+      if (k < K) atomicAdd(&Cm[(size_t)nn * ldc + k], acc[i][j]);
+    }
+  }
+}
+
 static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, int accumulate,
                    const float* mask, cudaStream_t st) {
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
+                       (!mask || (uintptr_t)mask % 16 == 0);
+  if (aligned && N % BK == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && N >= 64 && K >= 64) {
+    dim3 grid((unsigned)((M + BT - 1) / BT), (unsigned)((K + BT - 1) / BT));
+    gemm_nn_big_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, mask);
+    DMN_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((K + GT - 1) / GT));
   gemm_nn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, accumulate, mask);
   DMN_LAUNCH_OK();
@@ -304,6 +430,19 @@ static int gemm_nt_bias(const float* A, int lda, const float* W, int ldw, const 
 }
 
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st) {
+  const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+  if (aligned && N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && N >= 64 && K >= 64) {
+    const int tiles_b = ((N + BT - 1) / BT) * ((K + BT - 1) / BT);
+    int64_t splits = (3 * 148 + tiles_b - 1) / tiles_b;
+    int64_t rows = (M + splits - 1) / splits;
+    rows = ((rows + BK - 1) / BK) * BK;
+    if (rows < 512) rows = 512;
+    splits = (M + rows - 1) / rows;
+    dim3 grid((unsigned)((N + BT - 1) / BT), (unsigned)((K + BT - 1) / BT), (unsigned)splits);
+    gemm_tn_big_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rows);
+    DMN_LAUNCH_OK();
+    return 0;
+  }
   const int tiles = ((N + GT - 1) / GT) * ((K + GT - 1) / GT);
   int64_t splits = (4 * 148 + tiles - 1) / tiles;
   int64_t rows = (M + splits - 1) / splits;
