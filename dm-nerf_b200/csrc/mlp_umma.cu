@@ -29,32 +29,36 @@ namespace uk {
 using namespace umma;
 
 constexpr int TILE_M = 128;
-constexpr int NS = 6;                      // weight ring stages
+constexpr int NS = 9;                      // weight ring stages
 constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
 constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
-constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;
 constexpr int N_STEPS = 20;
 constexpr int MAX_CHUNKS = 5;
 constexpr int MAX_STAGES = 160;
 constexpr int EPI_THREADS = 256;
 constexpr int N_THREADS = 128 + EPI_THREADS;
 
-// tensor-memory column map (512 columns x 128 lanes x 32 bit)
+// tensor-memory column map (512 columns x 128 lanes x 32 bit) -- completely used:
+//   two fp32 accumulators [128 x 128] and two activation slots, each holding a [128 x 128] activation block (one K-half of
+//   a 256-wide layer input) as split bf16: 64 columns of hi halves + 64 columns of lo halves (2 bf16 per 32-bit column).
+// Every trunk MMA therefore takes its A operand from tensor memory (no shared-memory read for A); the position / direction
+// embeddings, used by 4 of the 73 K chunks of a tile, live in shared memory instead.
 constexpr uint32_t TC_ACC = 0;             // two accumulators: [0,128) and [128,256)
-constexpr uint32_t TC_SLOT = 256;          // bf16-hi halves of the three slots: 64 columns each
-constexpr uint32_t TC_E = 448;             // bf16-hi of the position embedding (64 K -> 32 columns)
-constexpr uint32_t TC_D = 480;             // bf16-hi of the direction embedding (32 K -> 16 columns)
-constexpr uint32_t TC_D_LO = 496;          // bf16-lo of the direction embedding (kept in TMEM too: frees a 16 KB slab)
+constexpr uint32_t TC_SLOT = 256;          // slot s at 256 + 128 s: hi of chunk c at +32 c, lo of chunk c at +64 + 32 c
+constexpr uint32_t SLOT_COLS = 128, SLOT_LO = 64;
 
 // shared-memory map (offsets from the 1024-aligned base)
-constexpr uint32_t SM_SLOT = 0;
-constexpr uint32_t SM_E = 3 * SLOT_BYTES;
-constexpr uint32_t SM_RING = SM_E + CHUNK_BYTES;
+constexpr uint32_t SM_E_HI = 0;                                 // position embedding, K-major SW128 slabs [128 rows][64 bf16]
+constexpr uint32_t SM_E_LO = SM_E_HI + CHUNK_BYTES;
+constexpr uint32_t SM_D_HI = SM_E_LO + CHUNK_BYTES;             // direction embedding (32 of the 64 K columns used)
+constexpr uint32_t SM_D_LO = SM_D_HI + CHUNK_BYTES;
+constexpr uint32_t SM_RING = SM_D_LO + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
 constexpr uint32_t SM_FUSED = SM_MISC + 2048;                   // per-unit state of the fused render kernel
 constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 
-enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..5 = slot*2 + half
+enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..3 = slot*2 + chunk
 
 struct Step {
   int8_t n_chunks;
@@ -75,7 +79,8 @@ struct Program {
 
 struct Misc {                  // lives at SM_MISC
   uint64_t full[NS], empty[NS];
-  uint64_t acc_full[2], epi_done[2], inputs_ready;
+  uint64_t acc_full[2], epi_done[2][2], inputs_ready;   // epi_done[accumulator][64-column chunk]
+  uint64_t a_free;             // the odd half-step of a layer has finished reading slot 0 (its even half-step may overwrite it)
   uint32_t tmem_base;
   int32_t abort_flag;
   float dens[2][TILE_M];
@@ -116,6 +121,17 @@ struct KArgs {
   int32_t* status;             // device error word
 };
 
+// ------------------------------------------------------------------------------------------------ in-kernel cycle profile
+// Diagnostics build only (-DDMN_KPROF, tools/kprof.py): where do the MMA warp and one epilogue thread spend their cycles.
+#ifdef DMN_KPROF
+__device__ long long g_kprof[160][16];
+#define KP_T0() const long long kp_t0 = clock64()
+#define KP_ADD(i) kp[i] += clock64() - kp_t0
+#else
+#define KP_T0() ((void)0)
+#define KP_ADD(i) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ bounded waits
 // Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
 // On a timeout the abort flag is raised and execution simply continues: every later wait returns at once, the kernel
@@ -143,13 +159,13 @@ struct Ring {
   }
 };
 
-// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi on the TS path, A_lo*W_hi on the SS path) and
-// the W_lo stage (A_hi*W_lo, TS).  Executed by the whole (converged) MMA warp; one elected lane issues.
-// A_LO_TMEM: the bf16-lo half of the A operand also lives in tensor memory (direction embedding), otherwise in shared memory.
-template <int KS, bool A_LO_TMEM = false>
-__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_desc, uint32_t a_tmem,
+// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi and A_lo*W_hi) and the W_lo stage (A_hi*W_lo).
+// Executed by the whole (converged) MMA warp; one elected lane issues.
+// A_SMEM = false: a_hi / a_lo are tensor-memory addresses (activation slots);  true: shared-memory descriptors (embeddings).
+template <int KS, bool A_SMEM>
+__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_hi, uint64_t a_lo,
                                             uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status,
-                                            uint32_t a_lo_tmem = 0) {
+                                            long long* kp) {
   const uint32_t s_hi = ring.slot, p_hi = ring.phase;
   ring.advance();
   const uint32_t s_lo = ring.slot, p_lo = ring.phase;
@@ -157,19 +173,26 @@ __device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t rin
   const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
   const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
   if (elect_one()) {
-    wait_bar(&misc->full[s_hi], p_hi, misc, 204, status);
+    { KP_T0(); wait_bar(&misc->full[s_hi], p_hi, misc, 204, status); KP_ADD(4); }
     tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K
-      mma_ts(d_tmem, a_tmem + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-      if (A_LO_TMEM) mma_ts(d_tmem, a_lo_tmem + k * 8, wh + 2 * k, idesc, 1u);
-      else mma_ss(d_tmem, a_desc + 2 * k, wh + 2 * k, idesc, 1u);
+    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K; +8 TMEM columns likewise
+      if (A_SMEM) {
+        mma_ss(d_tmem, a_hi + 2 * k, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+        mma_ss(d_tmem, a_lo + 2 * k, wh + 2 * k, idesc, 1u);
+      } else {
+        mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+        mma_ts(d_tmem, (uint32_t)a_lo + k * 8, wh + 2 * k, idesc, 1u);
+      }
     }
     mma_commit(&misc->empty[s_hi]);
-    wait_bar(&misc->full[s_lo], p_lo, misc, 205, status);
+    { KP_T0(); wait_bar(&misc->full[s_lo], p_lo, misc, 205, status); KP_ADD(5); }
     tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < KS; ++k) mma_ts(d_tmem, a_tmem + k * 8, wl + 2 * k, idesc, 1u);
+    for (int k = 0; k < KS; ++k) {
+      if (A_SMEM) mma_ss(d_tmem, a_hi + 2 * k, wl + 2 * k, idesc, 1u);
+      else mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wl + 2 * k, idesc, 1u);
+    }
     mma_commit(&misc->empty[s_lo]);
   }
   __syncwarp();
@@ -202,16 +225,17 @@ __device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* 
   }
 }
 
-// 32 fp32 values -> bf16 hi into TMEM (16 columns; the hi half feeds two of the three passes, and a TMEM A operand
-// costs no shared-memory bandwidth), bf16 lo into a K-major SW128 slab row (columns [k0, k0+32)).
-__device__ __forceinline__ void store_split32(const float* vals, uint8_t* slab, int row, int k0, uint32_t tmem_addr) {
+// 32 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+32)).
+__device__ __forceinline__ void store_split32_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-    *reinterpret_cast<uint4*>(slab + sw128_offset(row, k0 + 8 * u)) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-  tmem_st_x16(tmem_addr, hi);
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t o = sw128_offset(row, k0 + 8 * u);
+    *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+    *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+  }
 }
 
 // 32 fp32 values -> bf16 hi and bf16 lo, both into TMEM (16 columns each).
@@ -246,8 +270,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&misc->acc_full[i], 1); mbar_init(&misc->epi_done[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&misc->acc_full[i], 1);
+      mbar_init(&misc->epi_done[i][0], EPI_THREADS);
+      mbar_init(&misc->epi_done[i][1], EPI_THREADS);
+    }
     mbar_init(&misc->inputs_ready, EPI_THREADS);
+    mbar_init(&misc->a_free, 1);
     misc->abort_flag = 0;
     fence_barrier_init();
   }
@@ -283,100 +312,138 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     // =========================================================== MMA issuer (converged warp, one elected lane issues)
     // The per-tile schedule is written out structurally (it mirrors build_program(), which drives the producer, the
     // epilogue and the weight packing): 8 trunk layers x 2 half-steps, two folded hidden heads, two output heads.
+    long long kp[16] = {0};
+    (void)kp;
+    const long long kp_role0 = clock64();
+    (void)kp_role0;
     Ring ring{0, 0};
-    uint32_t seen0 = 0, seen1 = 0, seen_in = 0;
-    const uint32_t slot_base = smem_u32(smem + SM_SLOT), ring_base = smem_u32(smem + SM_RING);
-    const uint64_t e_desc = make_sdesc_sw128(smem_u32(smem + SM_E));
+    uint32_t seen00 = 0, seen01 = 0, seen10 = 0, seen11 = 0, seen_in = 0;
+    const uint32_t ring_base = smem_u32(smem + SM_RING);
+    const uint64_t e_hi = make_sdesc_sw128(smem_u32(smem + SM_E_HI)), e_lo = make_sdesc_sw128(smem_u32(smem + SM_E_LO));
+    const uint64_t d_hi = make_sdesc_sw128(smem_u32(smem + SM_D_HI)), d_lo = make_sdesc_sw128(smem_u32(smem + SM_D_LO));
     const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc16 = make_idesc_bf16(128, 16);
     const uint32_t idesc_ins = make_idesc_bf16(128, prog.step[N_STEPS - 1].n);
-    // epilogue of global step gd finished (its output slot is readable, its accumulator is drained)
-    auto need_epi = [&](uint32_t gd) {
-      uint32_t& seen = (gd & 1) ? seen1 : seen0;
+    // The epilogue of global step gd has finished 64-column chunk c: that K chunk of its output slot is readable and
+    // that part of its accumulator is drained.  (Chunk granularity lets the next layer's MMAs on chunk 0 overlap the
+    // epilogue of chunk 1.)
+    auto need_epi = [&](uint32_t gd, int c) {
+      uint32_t& sn = (gd & 1) ? (c ? seen11 : seen10) : (c ? seen01 : seen00);
       const uint32_t need = gd / 2 + 1;
-      while (seen < need) {
-        wait_bar(&misc->epi_done[gd & 1], seen & 1, misc, 201, a.status);
-        ++seen;
+      while (sn < need) {
+        wait_bar(&misc->epi_done[gd & 1][c], sn & 1, misc, 201, a.status);
+        ++sn;
       }
       tc_fence_after();
     };
+    auto need_drained = [&](uint32_t gd) { need_epi(gd, 0); need_epi(gd, 1); };
+    // K chunk j of activation slot `slot` (both bf16 halves in tensor memory)
     auto slot_chunk = [&](int slot, int j, uint32_t d_tmem, uint32_t idesc, uint32_t& accum) {
-      issue_chunk<4>(misc, ring, ring_base, make_sdesc_sw128(slot_base + (slot * 2 + j) * CHUNK_BYTES),
-                     tbase + TC_SLOT + (slot * 2 + j) * 32, d_tmem, idesc, accum, a.status);
+      const uint32_t hi = tbase + TC_SLOT + slot * SLOT_COLS + j * 32;
+      issue_chunk<4, false>(misc, ring, ring_base, hi, hi + SLOT_LO, d_tmem, idesc, accum, a.status, kp);
     };
     auto finish = [&](uint32_t acc) {
       if (elect_one()) mma_commit(&misc->acc_full[acc]);
       __syncwarp();
     };
+    // Slot 0 has been read by everything issued so far: the epilogue of the preceding even half-step may overwrite it.
+    auto release_slot0 = [&]() {
+      if (elect_one()) mma_commit(&misc->a_free);
+      __syncwarp();
+    };
+    // Slot 0 always holds K-half 0 of the current activation (written by the even half-step of the previous layer),
+    // slot 1 K-half 1 (odd half-step).  The even epilogue of a layer runs while the odd half-step's MMAs are in flight,
+    // so the odd half-step reads slot 0 first and releases it (a_free) before it turns to slot 1.
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const uint32_t g0 = (uint32_t)ti * N_STEPS;
       // ---- layer 0: E -> slots 0, 1
       for (uint32_t h = 0; h < 2; ++h) {
         const uint32_t g = g0 + h;
-        if (g >= 2) need_epi(g - 2);
-        while (seen_in < (uint32_t)ti + 1) {
-          wait_bar(&misc->inputs_ready, seen_in & 1, misc, 202, a.status);
-          ++seen_in;
+        if (g >= 2) { KP_T0(); need_drained(g - 2); KP_ADD(0); }
+        {
+          KP_T0();
+          while (seen_in < (uint32_t)ti + 1) {
+            wait_bar(&misc->inputs_ready, seen_in & 1, misc, 202, a.status);
+            ++seen_in;
+          }
+          KP_ADD(3);
         }
         tc_fence_after();
         uint32_t accum = 0;
-        issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, tbase + TC_ACC + h * 128, idesc128, accum, a.status);
+        issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, tbase + TC_ACC + h * 128, idesc128, accum, a.status, kp);
         finish(h);
       }
-      int sa = 0, sb = 1, sf = 2;                    // slots holding K-halves 0 / 1 of the activation, free slot
       // ---- layers 1..7
       for (int l = 1; l < 8; ++l) {
         for (uint32_t h = 0; h < 2; ++h) {
           const uint32_t g = g0 + 2 * l + h, d_tmem = tbase + TC_ACC + h * 128;
-          need_epi(g - 2);
+          { KP_T0(); need_drained(g - 2); KP_ADD(0); }   // accumulator free (and, for h == 0, K-half 0 of the input complete)
           uint32_t accum = 0;
-          slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
-          if (h == 0) need_epi(g - 1);
-          slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
-          if (l == 5) issue_chunk<4>(misc, ring, ring_base, e_desc, tbase + TC_E, d_tmem, idesc128, accum, a.status);
+          slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
+          if (h == 1) release_slot0();
+          if (h == 0) { KP_T0(); need_epi(g - 1, 0); KP_ADD(1); }
+          slot_chunk(1, 0, d_tmem, idesc128, accum);
+          if (h == 0) { KP_T0(); need_epi(g - 1, 1); KP_ADD(2); }
+          slot_chunk(1, 1, d_tmem, idesc128, accum);
+          if (l == 5) issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, d_tmem, idesc128, accum, a.status, kp);
           finish(h);
         }
-        const int t = sb; sb = sa; sa = sf; sf = t;   // (a, b, f) <- (f, a, b)
       }
       {
-        // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> free slot
+        // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> slot 0
         uint32_t accum = 0, d_tmem = tbase + TC_ACC;
-        need_epi(g0 + 14);
-        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
-        need_epi(g0 + 15);
-        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
-        issue_chunk<2, true>(misc, ring, ring_base, 0, tbase + TC_D, d_tmem, idesc128, accum, a.status, tbase + TC_D_LO);
+        { KP_T0(); need_drained(g0 + 14); KP_ADD(7); }
+        slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
+        { KP_T0(); need_epi(g0 + 15, 0); KP_ADD(7); }
+        slot_chunk(1, 0, d_tmem, idesc128, accum);
+        { KP_T0(); need_epi(g0 + 15, 1); KP_ADD(7); }
+        slot_chunk(1, 1, d_tmem, idesc128, accum);
+        issue_chunk<2, true>(misc, ring, ring_base, d_hi, d_lo, d_tmem, idesc128, accum, a.status, kp);
         finish(0);
-        // ---- folded instance hidden layer (step 17, acc 1): h -> slot of K-half 0
+        // ---- folded instance hidden layer (step 17, acc 1): h -> slot 1
         accum = 0; d_tmem = tbase + TC_ACC + 128;
-        slot_chunk(sa, 0, d_tmem, idesc128, accum); slot_chunk(sa, 1, d_tmem, idesc128, accum);
-        slot_chunk(sb, 0, d_tmem, idesc128, accum); slot_chunk(sb, 1, d_tmem, idesc128, accum);
+        slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
+        release_slot0();
+        slot_chunk(1, 0, d_tmem, idesc128, accum); slot_chunk(1, 1, d_tmem, idesc128, accum);
         finish(1);
-        // ---- rgb head (step 18, acc 0, N=16) on the colour hidden slot
+        // ---- rgb head (step 18, acc 0, N=16) on the colour hidden activation (slot 0)
         accum = 0; d_tmem = tbase + TC_ACC;
-        need_epi(g0 + 16);
-        slot_chunk(sf, 0, d_tmem, idesc16, accum); slot_chunk(sf, 1, d_tmem, idesc16, accum);
+        { KP_T0(); need_epi(g0 + 16, 0); KP_ADD(7); }   // N = 16 only touches accumulator columns of chunk 0
+        slot_chunk(0, 0, d_tmem, idesc16, accum);
+        { KP_T0(); need_epi(g0 + 16, 1); KP_ADD(7); }
+        slot_chunk(0, 1, d_tmem, idesc16, accum);
         finish(0);
-        // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden slot
+        // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden activation (slot 1)
         accum = 0; d_tmem = tbase + TC_ACC + 128;
-        need_epi(g0 + 17);
-        slot_chunk(sa, 0, d_tmem, idesc_ins, accum); slot_chunk(sa, 1, d_tmem, idesc_ins, accum);
+        { KP_T0(); need_drained(g0 + 17); KP_ADD(7); }  // N may cover all 128 accumulator columns
+        slot_chunk(1, 0, d_tmem, idesc_ins, accum); slot_chunk(1, 1, d_tmem, idesc_ins, accum);
         finish(1);
       }
     }
+#ifdef DMN_KPROF
+    kp[6] = clock64() - kp_role0;
+    if (lane == 0) for (int i = 0; i < 8; ++i) g_kprof[blockIdx.x][i] = kp[i];
+#endif
   } else if (warp >= 4) {
     // =========================================================== prologue + epilogue warps
     const int et = tid - 128;                 // 0..255
     const int q = et >> 7;                    // column half handled by this warpgroup
     const int r = et & 127;                   // tile row == TMEM lane
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    uint8_t* e_slab = smem + SM_E;
+    uint8_t *e_hi_slab = smem + SM_E_HI, *e_lo_slab = smem + SM_E_LO, *d_hi_slab = smem + SM_D_HI, *d_lo_slab = smem + SM_D_LO;
     float dens_acc = 0.0f;
     const int n_ins1 = prog.ins_num + 1;
+    long long kp[16] = {0};
+    (void)kp;
+    const long long kp_role0 = clock64();
+    (void)kp_role0;
     // Operands (points, embeddings) of tile `tp`: hi halves into TMEM, lo halves into shared memory, then inputs_ready.
     // Called EARLY -- during the previous tile, right after the last reader of E / D (half-step 16) has completed -- so the
     // next tile's first MMAs never wait for sin/cos; only the first tile of a CTA and the first fine tile of a ray pair
     // (whose depths come out of this tile's importance sampling) are prepared late.
     auto prologue = [&](int64_t tp) {
+#ifdef DMN_KPROF
+      const long long kp_p0 = clock64();
+#endif
       const int jp = FUSED ? (int)(tp & 3) : 0;
       const int64_t itemp = blockIdx.x + (FUSED ? (tp >> 2) : tp) * gridDim.x;
       const int up = FUSED ? (int)((tp >> 2) & 1) : 0;                   // ray-data buffer of that ray pair
@@ -420,12 +487,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           vals[i] = (validp && e < CH_POS) ? a.x[rowp * CH_IN + e] : 0.0f;
         }
         save_emb(vals, 32 * q, q == 0 ? 32 : 31);
-        store_split32(vals, e_slab, r, 32 * q, tbase + lane_sel + TC_E + 16 * q);
+        store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 32 * q);
         if (q == 0) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) vals[i] = (validp && i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + i] : 0.0f;
           save_emb(vals, CH_POS, CH_DIR);
-          store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
+          store_split32_smem(vals, d_hi_slab, d_lo_slab, r, 0);
         }
       } else {
         float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
@@ -463,6 +530,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
           vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
         }
+#ifdef DMN_KPROF
+        const long long kp_p1 = clock64();
+        kp[14] += kp_p1 - kp_p0;
+#endif
         if (q == 0) {
           fill_embedding<0, 32, L_POS>(pt, vals);
           if (!validp) {
@@ -470,14 +541,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
           save_emb(vals, 0, 32);
-          store_split32(vals, e_slab, r, 0, tbase + lane_sel + TC_E);
+          store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 0);
+#ifdef DMN_KPROF
+          kp[15] += clock64() - kp_p1;
+#endif
           fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
           if (!validp) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
           save_emb(vals, CH_POS, CH_DIR);
-          store_split32_tmem(vals, tbase + lane_sel + TC_D, tbase + lane_sel + TC_D_LO);
+          store_split32_smem(vals, d_hi_slab, d_lo_slab, r, 0);
         } else {
           fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
           if (!validp) {
@@ -485,19 +559,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
           }
           save_emb(vals, 32, 31);
-          store_split32(vals, e_slab, r, 32, tbase + lane_sel + TC_E + 16);
+          store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 32);
         }
       }
-      fence_proxy_async_smem();
-      tmem_st_wait();
-      tc_fence_before();
+      fence_proxy_async_smem();          // the embeddings are read by the tensor core through the async proxy
       mbar_arrive(&misc->inputs_ready);
     };
     (void)0;
     // may tile tp be prepared during tile tp-1?  (the first fine tile of a pair needs this tile's importance samples)
     auto early_ok = [&](int64_t tp) { return tp < my_tiles && (!FUSED || (tp & 3) != 1); };
 
-    if (my_tiles > 0) prologue(0);
+    if (my_tiles > 0) { KP_T0(); prologue(0); KP_ADD(10); }
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       // ---- which rows does this tile hold
       const int j = FUSED ? (int)(ti & 3) : 0;                            // fused: 0 = coarse tile, 1..3 = fine tiles
@@ -519,23 +591,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       for (int t = 0; t < N_STEPS; ++t) {
         const Step& st = prog.step[t];
         const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
-        wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status);
+        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
         tc_fence_after();
+#ifdef DMN_KPROF
+        const long long kp_body0 = clock64();
+#endif
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
         const float* bias = bias_base + t * 128;
         if (st.out_slot >= 0) {
-          // hidden half-step: 64 columns per thread -> bias, (ReLU), split, store into the destination slot
+          // hidden half-step: per thread 32 columns of K chunk 0, then 32 columns of K chunk 1 -> bias, (ReLU), split,
+          // store into the destination slot.  Each chunk is published on its own barrier as soon as it is complete.
           const int slot = st.out_slot;
-          uint8_t* slab = smem + SM_SLOT + slot * SLOT_BYTES + q * CHUNK_BYTES;     // this thread's 64 columns = chunk q
-          const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * 64 + q * 32;
           const bool is_l7 = (t == 14 || t == 15);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int c = 0; c < 2; ++c) {
+            const int col = c * 64 + q * 32;                                          // first of this thread's 32 columns
+            const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS + c * 32 + q * 16;
             uint32_t v[32];
-            tmem_ld_x32(acc_addr + q * 64 + h * 32, v);
+            tmem_ld_x32(acc_addr + col, v);
             tmem_ld_wait();
             float f[32];
-            const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + h * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const float4 bb = __ldg(b4 + jj);
@@ -548,8 +624,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.0f);
             }
+            if (c == 0 && (t & 1) == 0 && t >= 2) {
+              // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
+              KP_T0();
+              wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
+              KP_ADD(9);
+              tc_fence_after();
+            }
+            store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
             if (is_l7) {        // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
-              const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + q * 64 + h * 32);
+              const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + col);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 const float4 ww = __ldg(w4 + jj);
@@ -564,21 +648,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 const ActPlanes ap = act_planes(a.acts, a.m);
                 float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
                                       : ((t == 16) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
-                store_row32(dst + q * 64 + h * 32, f);
+                store_row32(dst + col, f);
               }
             }
-            store_split32(f, slab, r, h * 32, hi_addr + h * 16);
+            if (c == 1 && t == 15) {   // publish this thread's partial sum of the density dot product; the rgb-head
+              misc->dens[q][r] = dens_acc;     // epilogue (3 barrier hops later) adds the two halves
+              dens_acc = 0.0f;
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc][c]);
+#ifdef DMN_KPROF
+            kp[12 + c] += clock64() - kp_body0;
+#endif
           }
-          if (t == 15) {         // publish this column-half's partial sum of the density dot product; the rgb-head
-            misc->dens[q][r] = dens_acc;   // epilogue (3 barrier hops later) adds the two halves
-            dens_acc = 0.0f;
-          }
-          fence_proxy_async_smem();
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc]);
           // E / D were last read by half-step 16 (complete: we are past 17's accumulator): prepare the next tile now
-          if (t == 17 && early_ok(ti + 1)) prologue(ti + 1);
+          if (t == 17 && early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
         } else if (t == N_STEPS - 2) {
           // rgb head (N=16: 3 live columns) + density                          (dm_nerf.py:101-102,105)
           uint32_t v[16];
@@ -587,7 +672,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             tmem_ld_wait();
           }
           tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc]);             // accumulator drained: the next tile's first half-step may start
+          mbar_arrive(&misc->epi_done[acc][0]);          // accumulator drained: the next tile's first half-step may start
+          mbar_arrive(&misc->epi_done[acc][1]);
           if (q == 0) {
             const float c0 = __uint_as_float(v[0]) + __ldg(bias + 0), c1 = __uint_as_float(v[1]) + __ldg(bias + 1),
                         c2 = __uint_as_float(v[2]) + __ldg(bias + 2);
@@ -652,7 +738,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               }
             }
             tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc]);
+            mbar_arrive(&misc->epi_done[acc][0]);
+            mbar_arrive(&misc->epi_done[acc][1]);
           } else {
             // instance logits weighted by the (detached) weights: sum_i w_i raw_i[4+k]   (render.py:22-24)
             asm volatile("bar.sync 2, 256;" ::: "memory");     // weights of this tile (fz->w) are complete
@@ -670,7 +757,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               }
             }
             tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc]);
+            mbar_arrive(&misc->epi_done[acc][0]);
+            mbar_arrive(&misc->epi_done[acc][1]);
             asm volatile("bar.sync 2, 256;" ::: "memory");     // all running sums of this tile are in
             // ---- rays that end in this tile: write their maps (render.py:19-26) and clear the sums
             const int done_lo = (j == 0) ? 0 : ((j == 2) ? 0 : ((j == 3) ? 1 : 2));
@@ -714,51 +802,60 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           }
         }
       }
-      if (ti + 1 < my_tiles && !early_ok(ti + 1)) prologue(ti + 1);
+      if (ti + 1 < my_tiles && !early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
     }
+#ifdef DMN_KPROF
+    kp[11] = clock64() - kp_role0;
+    if (et == 0) for (int i = 8; i < 16; ++i) g_kprof[blockIdx.x][i] = kp[i];
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(misc->tmem_base, 512);
 }
 
+#ifdef DMN_KPROF
+}  // namespace uk
+}  // namespace dmnerf
+extern "C" __attribute__((visibility("default"))) int dmnerf_debug_kprof(long long* out, int n_blocks) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, dmnerf::uk::g_kprof, sizeof(long long) * 16 * (size_t)n_blocks);
+}
+namespace dmnerf {
+namespace uk {
+#endif
+
 // ------------------------------------------------------------------------------------------------ host: program
 static void build_program(Program& P, int ins_num) {
   memset(&P, 0, sizeof(P));
   P.ins_num = ins_num;
-  int a_slot = -1, b_slot = -1, f_slot = -1;          // slots holding K-halves 0/1 of the current activation, free slot
+  // Slot 0 always holds K-half 0 of the current activation, slot 1 K-half 1 (see the MMA role of the kernel).
   int a_step = -1, b_step = -1;                        // steps that produced them
   int t = 0;
   auto add_chunk = [&](Step& s, int kind, int dep, int ks) {
     s.chunk[s.n_chunks] = (int8_t)kind; s.dep[s.n_chunks] = (int8_t)dep; s.ksteps[s.n_chunks] = (int8_t)ks; ++s.n_chunks;
   };
   auto add_act = [&](Step& s) {
-    add_chunk(s, a_slot * 2 + 0, a_step, 4); add_chunk(s, a_slot * 2 + 1, a_step, 4);
-    add_chunk(s, b_slot * 2 + 0, b_step, 4); add_chunk(s, b_slot * 2 + 1, b_step, 4);
+    add_chunk(s, 0, a_step, 4); add_chunk(s, 1, a_step, 4);
+    add_chunk(s, 2, b_step, 4); add_chunk(s, 3, b_step, 4);
   };
   for (int l = 0; l < 8; ++l) {
-    int out0, out1;
-    if (l == 0) { out0 = 0; out1 = 1; }
-    else { out0 = f_slot; out1 = a_slot; }
     for (int h = 0; h < 2; ++h) {
       Step& s = P.step[t];
-      s.n = 128; s.relu = 1; s.out_slot = (int8_t)(h == 0 ? out0 : out1);
+      s.n = 128; s.relu = 1; s.out_slot = (int8_t)h;
       if (l == 0) add_chunk(s, CK_E, -1, 4);
       else { add_act(s); if (l == 5) add_chunk(s, CK_E, -1, 4); }
       ++t;
     }
-    const int nf = (l == 0) ? 2 : b_slot;
-    a_slot = out0; b_slot = out1; f_slot = nf;
     a_step = t - 2; b_step = t - 1;
   }
-  // folded colour branch -> free slot; folded instance branch -> slot of K-half 0 (free once both MMAs completed)
-  const int rgb_slot = f_slot, ins_slot = a_slot;
-  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = (int8_t)rgb_slot; add_act(s); add_chunk(s, CK_D, -1, 2); ++t; }
-  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = (int8_t)ins_slot; add_act(s); ++t; }
+  // folded colour branch -> slot 0; folded instance branch -> slot 1
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = 0; add_act(s); add_chunk(s, CK_D, -1, 2); ++t; }
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = 1; add_act(s); ++t; }
   { Step& s = P.step[t]; s.n = 16; s.relu = 0; s.out_slot = -1;
-    add_chunk(s, rgb_slot * 2 + 0, t - 2, 4); add_chunk(s, rgb_slot * 2 + 1, t - 2, 4); ++t; }
+    add_chunk(s, 0, t - 2, 4); add_chunk(s, 1, t - 2, 4); ++t; }
   { Step& s = P.step[t]; s.n = (int16_t)(((ins_num + 1) + 15) / 16 * 16); s.relu = 0; s.out_slot = -1;
-    add_chunk(s, ins_slot * 2 + 0, t - 2, 4); add_chunk(s, ins_slot * 2 + 1, t - 2, 4); ++t; }
+    add_chunk(s, 2, t - 2, 4); add_chunk(s, 3, t - 2, 4); ++t; }
   // stage offsets
   uint32_t off = 0;
   int si = 0;

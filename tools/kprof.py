@@ -1,0 +1,83 @@
+"""In-kernel cycle profile of the tcgen05 MLP / fused render kernel (diagnostics build, -DDMN_KPROF).
+
+  python tools/kprof.py --build     (here: compiles tools/bin/libdmnerf_kprof.so)
+  python tools/kprof.py [--fused]   (on the GPU box)
+
+Prints, for a few CTAs, where the MMA-issuing warp and one epilogue thread spent their cycles.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tools", "bin", "libdmnerf_kprof.so")
+NAMES = ["mma:wait acc drained", "mma:wait epi(g-1) chunk0", "mma:wait epi(g-1) chunk1", "mma:wait inputs", "mma:wait W_hi stage",
+         "mma:wait W_lo stage", "mma:role total", "mma:wait (head steps)", "epi:wait acc_full", "epi:wait a_free",
+         "epi:prologue", "epi:role total", "epi:acc_full->arrive c0 (sum)", "epi:acc_full->arrive c1 (sum)", "pro:loads+points", "pro:E[0:32] sincos+store"]
+
+
+def build():
+    sys.path.insert(0, ROOT)
+    from dmnerf_b200 import build as b
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objs = []
+    for src in b.SOURCES:
+        obj = os.path.join(ROOT, "tools", "bin", "kprof_" + src.replace(".cu", ".o"))
+        subprocess.check_call([b.nvcc()] + b.NVCC_FLAGS + ["-DDMN_KPROF", "-I", os.path.join(ROOT, "include"), "-c",
+                                                           os.path.join(b.CSRC, src), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call([b.nvcc()] + b.NVCC_FLAGS[:2] + ["-shared", "-o", LIB] + objs + ["-lcudart"])
+    print(LIB)
+
+
+def main():
+    if "--build" in sys.argv:
+        return build()
+    os.environ["DMNERF_LIB_PATH"] = LIB
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    from dmnerf_b200 import synth, _lib
+    from dmnerf_b200.engine import get_context
+    from dmnerf_b200.testing import model_from_weights, make_models
+    from dmnerf_b200.autograd import mlp_forward_rays
+    from dmnerf_b200.render import render_rays
+    dev = "cuda"
+    wl = synth.workload("dmsr_study")
+    lib = _lib.load()
+    lib.dmnerf_debug_kprof.restype = C.c_int
+    lib.dmnerf_debug_kprof.argtypes = [C.c_void_p, C.c_int]
+    fused = "--fused" in sys.argv
+    with torch.no_grad():
+        if fused:
+            coarse, fine, _, _ = make_models(201, 202, 13, dev)
+            n = 307200
+            ro, rd = torch.from_numpy(wl["rays_o"][:n]).to(dev), torch.from_numpy(wl["rays_d"][:n]).to(dev)
+            z = torch.linspace(float(wl["near"]), float(wl["far"]), 64, device=dev)
+            for _ in range(2):
+                render_rays(ro, rd, coarse, fine, z, want_raw=False, want_samples=False)
+            tiles = (n // 2) * 4
+        else:
+            net = model_from_weights(synth.make_weights(202, 13), dev).eval()
+            n = 307200 // 4
+            ro, rd = torch.from_numpy(wl["rays_o"][:n]).to(dev), torch.from_numpy(wl["rays_d"][:n]).to(dev)
+            z = (torch.rand(n, 192, device=dev).sort(-1).values * 11 + 4).contiguous()
+            for _ in range(2):
+                mlp_forward_rays(net, ro, rd, z, _lib.IMPL_UMMA)
+            tiles = n * 192 // 128
+        get_context(dev).sync_check()
+    buf = (C.c_longlong * (16 * 148))()
+    rc = lib.dmnerf_debug_kprof(buf, 148)
+    assert rc == 0, rc
+    a = np.frombuffer(buf, dtype=np.int64).reshape(148, 16).astype(np.float64)
+    tpc = tiles / 148.0
+    print("%s: %d tiles, %.1f per CTA; cycles per tile (mean over CTAs | CTA 0 | CTA 147)" % ("fused" if fused else "mlp", tiles, tpc))
+    for i, nm in enumerate(NAMES):
+        if nm == "-":
+            continue
+        print("  %-34s %9.0f | %9.0f | %9.0f" % (nm, a[:, i].mean() / tpc, a[0, i] / tpc, a[147, i] / tpc))
+
+
+if __name__ == "__main__":
+    main()
