@@ -17,6 +17,7 @@
 // Warp roles: warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 prologue (points +
 // positional encoding) and epilogue.  All waits are bounded: a protocol bug raises an error code, never a hang.
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "ray_ops.cuh"
@@ -35,7 +36,8 @@ constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16
 constexpr int N_STEPS = 20;
 constexpr int MAX_CHUNKS = 5;
 constexpr int MAX_STAGES = 160;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TMEM lane quadrants x 4 column groups
+constexpr int CHUNK_THREADS = 256;         // threads that produce one 64-column K chunk of a half-step's output
 constexpr int N_THREADS = 128 + EPI_THREADS;
 
 // tensor-memory column map (512 columns x 128 lanes x 32 bit) -- completely used:
@@ -54,7 +56,7 @@ constexpr uint32_t SM_D_HI = SM_E_LO + CHUNK_BYTES;             // direction emb
 constexpr uint32_t SM_D_LO = SM_D_HI + CHUNK_BYTES;
 constexpr uint32_t SM_RING = SM_D_LO + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
-constexpr uint32_t SM_FUSED = SM_MISC + 2048;                   // per-unit state of the fused render kernel
+constexpr uint32_t SM_FUSED = SM_MISC + 4096;                   // per-unit state of the fused render kernel
 constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 
@@ -83,7 +85,7 @@ struct Misc {                  // lives at SM_MISC
   uint64_t a_free;             // the odd half-step of a layer has finished reading slot 0 (its even half-step may overwrite it)
   uint32_t tmem_base;
   int32_t abort_flag;
-  float dens[2][TILE_M];
+  float dens[4][TILE_M];       // per column group: partial density dot products of the tile's rows
 };
 
 // Shared state of the fused render kernel: one work unit = 2 rays = 1 coarse tile (2 x 64 samples) + 3 fine tiles (2 x 192).
@@ -101,6 +103,8 @@ struct Fused {
   float bins[2][FS], cdf[2][FS], vals[2][FF];
 };
 static_assert(sizeof(Fused) <= 12288, "Fused state does not fit its shared-memory block");
+
+static_assert(sizeof(Misc) <= 4096, "Misc does not fit its shared-memory block");
 
 struct KArgs {
   const uint8_t* image;        // packed bf16 operand image (fused: coarse network)
@@ -200,8 +204,33 @@ __device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t rin
 }
 
 // ------------------------------------------------------------------------------------------------ prologue helpers
-// Element e of the embedding [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)] given precomputed sin/cos.
-template <int E0, int COUNT, int L>
+// sin and cos of one argument with |a| < ~1e5: three-constant Cody-Waite reduction by pi/2 + the single-precision minimax
+// polynomials on [-pi/4, pi/4] (the textbook algorithm behind the library's own fast path, <= 2 ulp), written without the
+// large-argument branch so that the compiler can interleave the independent evaluations of a row (the prologue is a long
+// chain of these; with the library call's branch in between they serialise at ~550 cycles each).
+__device__ __forceinline__ void sincos_cw(float a, float& sn, float& cs) {
+  const float t = fmaf(a, 0.636619772f, 12582912.0f);          // 1.5 * 2^23: the integer n = rint(a * 2/pi) lands in the mantissa
+  const int n = __float_as_int(t);
+  const float j = t - 12582912.0f;
+  float r = fmaf(j, -1.57079601e+00f, a);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float ps = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  const float sr = fmaf(r * r2, ps, r);
+  float pc = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  pc = fmaf(pc, r2, -0.5f);
+  const float cr = fmaf(r2, pc, 1.0f);
+  float s0 = (n & 1) ? cr : sr, c0 = (n & 1) ? sr : cr;
+  sn = (n & 2) ? -s0 : s0;
+  cs = ((n + 1) & 2) ? -c0 : c0;
+}
+
+// Elements [E0, E0 + COUNT) of the embedding [v, sin(2^0 v), cos(2^0 v), ..., sin(2^(L-1) v), cos(2^(L-1) v)].
+// FAST: every argument is known to be small enough for sincos_cw (checked warp-wide by the caller).
+template <int E0, int COUNT, int L, bool FAST>
 __device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* COUNT */) {
   constexpr int F_LO = (E0 <= 3) ? 0 : (E0 - 3) / 6;
   constexpr int F_HI_RAW = (E0 + COUNT - 1 - 3) / 6;
@@ -216,22 +245,26 @@ __device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* 
     const float sc = (float)(1 << f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float sn, cs;
-      sincosf(v[c] * sc, &sn, &cs);
       const int es = 3 + 6 * f + c, ec = es + 3;
-      if (es >= E0 && es < E0 + COUNT) vals[es - E0] = sn;
-      if (ec >= E0 && ec < E0 + COUNT) vals[ec - E0] = cs;
+      const bool use_s = es >= E0 && es < E0 + COUNT, use_c = ec >= E0 && ec < E0 + COUNT;
+      if (use_s || use_c) {
+        float sn, cs;
+        if (FAST) sincos_cw(v[c] * sc, sn, cs);
+        else sincosf(v[c] * sc, &sn, &cs);
+        if (use_s) vals[es - E0] = sn;
+        if (use_c) vals[ec - E0] = cs;
+      }
     }
   }
 }
 
-// 32 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+32)).
-__device__ __forceinline__ void store_split32_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
-  uint32_t hi[16], lo[16];
+// 16 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+16)).
+__device__ __forceinline__ void store_split16_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
+  uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  for (int j = 0; j < 8; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < 2; ++u) {
     const uint32_t o = sw128_offset(row, k0 + 8 * u);
     *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
     *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
@@ -260,7 +293,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
   // is 1024-aligned by construction (checked below); addresses derived from it stay compile-time / uniform.
   extern __shared__ __align__(1024) uint8_t smem[];
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   // RAW: work item = one 128-row tile of a.m samples.  FUSED: work item = ray pair = 4 tiles (1 coarse + 3 fine).
   const int64_t n_items = FUSED ? (a.n_rays + 1) / 2 : (a.m + TILE_M - 1) / TILE_M;
   const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -272,8 +305,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     for (int i = 0; i < NS; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&misc->acc_full[i], 1);
-      mbar_init(&misc->epi_done[i][0], EPI_THREADS);
-      mbar_init(&misc->epi_done[i][1], EPI_THREADS);
+      mbar_init(&misc->epi_done[i][0], CHUNK_THREADS);
+      mbar_init(&misc->epi_done[i][1], CHUNK_THREADS);
     }
     mbar_init(&misc->inputs_ready, EPI_THREADS);
     mbar_init(&misc->a_free, 1);
@@ -421,12 +454,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     }
 #ifdef DMN_KPROF
     kp[6] = clock64() - kp_role0;
-    if (lane == 0) for (int i = 0; i < 8; ++i) g_kprof[blockIdx.x][i] = kp[i];
+    if ((tid & 31) == 0) for (int i = 0; i < 8; ++i) g_kprof[blockIdx.x][i] = kp[i];
 #endif
   } else if (warp >= 4) {
     // =========================================================== prologue + epilogue warps
-    const int et = tid - 128;                 // 0..255
-    const int q = et >> 7;                    // column half handled by this warpgroup
+    // 16 warps = 4 TMEM lane quadrants (warp % 4: rows) x 4 column groups (cg): in a hidden half-step every thread owns
+    // one row and 32 of the 128 output columns; the two column groups of a 64-column K chunk publish it together.
+    const int et = tid - 128;                 // 0..511
+    const int cg = et >> 7;                   // column group
     const int r = et & 127;                   // tile row == TMEM lane
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t *e_hi_slab = smem + SM_E_HI, *e_lo_slab = smem + SM_E_LO, *d_hi_slab = smem + SM_D_HI, *d_lo_slab = smem + SM_D_LO;
@@ -436,10 +471,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     (void)kp;
     const long long kp_role0 = clock64();
     (void)kp_role0;
-    // Operands (points, embeddings) of tile `tp`: hi halves into TMEM, lo halves into shared memory, then inputs_ready.
-    // Called EARLY -- during the previous tile, right after the last reader of E / D (half-step 16) has completed -- so the
-    // next tile's first MMAs never wait for sin/cos; only the first tile of a CTA and the first fine tile of a ray pair
-    // (whose depths come out of this tile's importance sampling) are prepared late.
+    // Operands (points, embeddings) of tile `tp`, split bf16 hi / lo into the shared-memory slabs, then inputs_ready.
+    // Column group cg computes embedding columns [16 cg, 16 cg + 16) of the position; groups 0 and 3 also one half of the
+    // direction embedding.  Called EARLY -- during the previous tile, right after the last reader of E / D (half-step 16)
+    // has completed; only the first tile of a CTA and the first fine tile of a ray pair (whose depths come out of this
+    // tile's importance sampling) are prepared late.
     auto prologue = [&](int64_t tp) {
 #ifdef DMN_KPROF
       const long long kp_p0 = clock64();
@@ -460,7 +496,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             rs[6] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
             rs[7] = ok ? 1.0f : 0.0f;
           }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
+          asm volatile("bar.sync 3, 512;" ::: "memory");
           rlp = r >> 6; sip = r & 63;
         } else {
           const int gr = (jp - 1) * TILE_M + r;
@@ -471,28 +507,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         rowp = itemp * TILE_M + r;
         validp = rowp < a.m;
       }
-      float vals[32];
-      auto save_emb = [&](const float* v, int col0, int cnt) {          // training forward: keep the embedded inputs
+      float vals[16];
+      auto zero_if_invalid = [&]() {
+        if (!validp) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vals[i] = 0.0f;
+        }
+      };
+      auto save_emb = [&](int col0) {          // training forward: keep the embedded inputs (ActPlanes.emb)
         if constexpr (!FUSED) {
           if (a.acts && validp) {
             float* dst = act_planes(a.acts, a.m).emb + rowp * CH_IN + col0;
-            for (int i = 0; i < cnt; ++i) dst[i] = v[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < CH_IN && (col0 >= CH_POS || col0 + i < CH_POS)) dst[i] = vals[i];
           }
         }
       };
       if (!FUSED && a.x) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int e = 32 * q + i;
+        for (int i = 0; i < 16; ++i) {
+          const int e = 16 * cg + i;
           vals[i] = (validp && e < CH_POS) ? a.x[rowp * CH_IN + e] : 0.0f;
         }
-        save_emb(vals, 32 * q, q == 0 ? 32 : 31);
-        store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 32 * q);
-        if (q == 0) {
+        save_emb(16 * cg);
+        store_split16_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg);
+        if (cg == 0 || cg == 3) {
+          const int d0 = (cg == 0) ? 0 : 16;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) vals[i] = (validp && i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + i] : 0.0f;
-          save_emb(vals, CH_POS, CH_DIR);
-          store_split32_smem(vals, d_hi_slab, d_lo_slab, r, 0);
+          for (int i = 0; i < 16; ++i) vals[i] = (validp && d0 + i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + d0 + i] : 0.0f;
+          save_emb(CH_POS + d0);
+          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, d0);
         }
       } else {
         float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
@@ -511,7 +556,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 const float upper = (sip == FS - 1) ? zz : __fmul_rn(0.5f, __fadd_rn(zr[sip + 1], zz));
                 zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[ray * FS + sip]));
               }
-              if (q == 0) {
+              if (cg == 0) {
                 fz->zc[rlp][sip] = zz;
                 if (a.zc_out) a.zc_out[ray * FS + sip] = zz;
               }
@@ -534,32 +579,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         const long long kp_p1 = clock64();
         kp[14] += kp_p1 - kp_p0;
 #endif
-        if (q == 0) {
-          fill_embedding<0, 32, L_POS>(pt, vals);
-          if (!validp) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-          }
-          save_emb(vals, 0, 32);
-          store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 0);
+        // |2^9 x| small enough for the branch-free sin/cos in every lane?  (warp-uniform choice; scenes are a few units wide)
+        const float amax = fmaxf(fmaxf(fabsf(pt[0]), fabsf(pt[1])), fabsf(pt[2]));
+        const bool fast = __all_sync(FULL, amax < 64.0f);
+        auto embed_pos = [&](auto fastc) {
+          constexpr bool F = decltype(fastc)::value;
+          if (cg == 0) fill_embedding<0, 16, L_POS, F>(pt, vals);
+          else if (cg == 1) fill_embedding<16, 16, L_POS, F>(pt, vals);
+          else if (cg == 2) fill_embedding<32, 16, L_POS, F>(pt, vals);
+          else fill_embedding<48, 16, L_POS, F>(pt, vals);                  // entries 48..62, entry 63 is the zero pad
+        };
+        if (fast) embed_pos(std::true_type{}); else embed_pos(std::false_type{});
+        zero_if_invalid();
+        save_emb(16 * cg);
+        store_split16_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg);
 #ifdef DMN_KPROF
-          kp[15] += clock64() - kp_p1;
+        kp[15] += clock64() - kp_p1;
 #endif
-          fill_embedding<0, 32, L_DIR>(vd, vals);       // 27 valid entries, the rest stays 0
-          if (!validp) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-          }
-          save_emb(vals, CH_POS, CH_DIR);
-          store_split32_smem(vals, d_hi_slab, d_lo_slab, r, 0);
-        } else {
-          fill_embedding<32, 32, L_POS>(pt, vals);      // entries 32..62, entry 63 is the zero pad
-          if (!validp) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vals[i] = 0.0f;
-          }
-          save_emb(vals, 32, 31);
-          store_split32_smem(vals, e_hi_slab, e_lo_slab, r, 32);
+        if (cg == 0 || cg == 3) {                        // |vd| <= 1: always the branch-free path; 27 valid entries, rest 0
+          if (cg == 0) fill_embedding<0, 16, L_DIR, true>(vd, vals);
+          else fill_embedding<16, 16, L_DIR, true>(vd, vals);
+          zero_if_invalid();
+          save_emb(CH_POS + (cg == 0 ? 0 : 16));
+          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, cg == 0 ? 0 : 16);
         }
       }
       fence_proxy_async_smem();          // the embeddings are read by the tensor core through the async proxy
@@ -598,72 +640,73 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #endif
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
         const float* bias = bias_base + t * 128;
+        const int q = cg;                             // output heads: 64-column half (column groups 0 and 1 only)
         if (st.out_slot >= 0) {
-          // hidden half-step: per thread 32 columns of K chunk 0, then 32 columns of K chunk 1 -> bias, (ReLU), split,
-          // store into the destination slot.  Each chunk is published on its own barrier as soon as it is complete.
+          // hidden half-step: this thread's 32 columns -> bias, (ReLU), split, store into the destination slot; the K
+          // chunk is published on its own barrier as soon as its two column groups are done.
           const int slot = st.out_slot;
-          const bool is_l7 = (t == 14 || t == 15);
+          const int c = cg >> 1;                                                    // K chunk of the output
+          const int col = cg * 32;                                                  // first of this thread's 32 columns
+          const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS + c * 32 + (cg & 1) * 16;
+          uint32_t v[32];
+          tmem_ld_x32(acc_addr + col, v);
+          tmem_ld_wait();
+          float f[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col = c * 64 + q * 32;                                          // first of this thread's 32 columns
-            const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS + c * 32 + q * 16;
-            uint32_t v[32];
-            tmem_ld_x32(acc_addr + col, v);
-            tmem_ld_wait();
-            float f[32];
-            const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bb = __ldg(b4 + jj);
+            f[4 * jj + 0] = __uint_as_float(v[4 * jj + 0]) + bb.x;
+            f[4 * jj + 1] = __uint_as_float(v[4 * jj + 1]) + bb.y;
+            f[4 * jj + 2] = __uint_as_float(v[4 * jj + 2]) + bb.z;
+            f[4 * jj + 3] = __uint_as_float(v[4 * jj + 3]) + bb.w;
+          }
+          if (st.relu) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.0f);
+          }
+          if ((t & 1) == 0 && t >= 2) {
+            // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
+            KP_T0();
+            wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
+            KP_ADD(9);
+            tc_fence_after();
+          }
+          store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
+          if (t == 14 || t == 15) {   // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
+            const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + col);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const float4 bb = __ldg(b4 + jj);
-              f[4 * jj + 0] = __uint_as_float(v[4 * jj + 0]) + bb.x;
-              f[4 * jj + 1] = __uint_as_float(v[4 * jj + 1]) + bb.y;
-              f[4 * jj + 2] = __uint_as_float(v[4 * jj + 2]) + bb.z;
-              f[4 * jj + 3] = __uint_as_float(v[4 * jj + 3]) + bb.w;
+              const float4 ww = __ldg(w4 + jj);
+              dens_acc = fmaf(f[4 * jj + 0], ww.x, dens_acc);
+              dens_acc = fmaf(f[4 * jj + 1], ww.y, dens_acc);
+              dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
+              dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
             }
-            if (st.relu) {
-#pragma unroll
-              for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.0f);
-            }
-            if (c == 0 && (t & 1) == 0 && t >= 2) {
-              // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
-              KP_T0();
-              wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
-              KP_ADD(9);
-              tc_fence_after();
-            }
-            store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
-            if (is_l7) {        // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
-              const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + col);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 ww = __ldg(w4 + jj);
-                dens_acc = fmaf(f[4 * jj + 0], ww.x, dens_acc);
-                dens_acc = fmaf(f[4 * jj + 1], ww.y, dens_acc);
-                dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
-                dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
-              }
-            }
-            if constexpr (!FUSED) {
-              if (a.acts && valid) {                   // training forward: keep the post-activation values (ActPlanes)
-                const ActPlanes ap = act_planes(a.acts, a.m);
-                float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
-                                      : ((t == 16) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
-                store_row32(dst + col, f);
-              }
-            }
-            if (c == 1 && t == 15) {   // publish this thread's partial sum of the density dot product; the rgb-head
-              misc->dens[q][r] = dens_acc;     // epilogue (3 barrier hops later) adds the two halves
+            if (t == 15) {            // publish this thread's partial sum of the dot product; the rgb-head epilogue
+              misc->dens[cg][r] = dens_acc;      // (3 barrier hops later) adds the four column groups in a fixed order
               dens_acc = 0.0f;
             }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc][c]);
-#ifdef DMN_KPROF
-            kp[12 + c] += clock64() - kp_body0;
-#endif
           }
+          if constexpr (!FUSED) {
+            if (a.acts && valid) {                   // training forward: keep the post-activation values (ActPlanes)
+              const ActPlanes ap = act_planes(a.acts, a.m);
+              float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
+                                    : ((t == 16) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
+              store_row32(dst + col, f);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&misc->epi_done[acc][c]);
+#ifdef DMN_KPROF
+          kp[12 + c] += clock64() - kp_body0;
+#endif
           // E / D were last read by half-step 16 (complete: we are past 17's accumulator): prepare the next tile now
           if (t == 17 && early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
+        } else if (cg >= 2) {
+          // the two output heads are drained by column groups 0 and 1 (256 threads, q = 64-column half) alone
+          if (FUSED && j == 0 && t == N_STEPS - 1) asm volatile("bar.sync 3, 512;" ::: "memory");   // fine depths (below)
         } else if (t == N_STEPS - 2) {
           // rgb head (N=16: 3 live columns) + density                          (dm_nerf.py:101-102,105)
           uint32_t v[16];
@@ -677,7 +720,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           if (q == 0) {
             const float c0 = __uint_as_float(v[0]) + __ldg(bias + 0), c1 = __uint_as_float(v[1]) + __ldg(bias + 1),
                         c2 = __uint_as_float(v[2]) + __ldg(bias + 2);
-            const float sigma = misc->dens[0][r] + misc->dens[1][r] + __ldg(bias_base + N_STEPS * 128 + 256);
+            const float sigma = ((misc->dens[0][r] + misc->dens[1][r]) + (misc->dens[2][r] + misc->dens[3][r])) +
+                                __ldg(bias_base + N_STEPS * 128 + 256);
             if constexpr (!FUSED) {
               if (valid) {
                 float* o = a.out + row * C;
@@ -797,7 +841,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
                   for (int k = ln; k < FF; k += 32) a.zf_out[ray * FF + k] = fz->zf[rr][k];
               }
-              asm volatile("bar.sync 2, 256;" ::: "memory");   // fine depths visible to every prologue thread
+              asm volatile("bar.sync 3, 512;" ::: "memory");   // fine depths visible to every prologue thread
             }
           }
         }
