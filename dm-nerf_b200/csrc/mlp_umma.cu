@@ -129,6 +129,8 @@ struct KArgs {
 // Diagnostics build only (-DDMN_KPROF, tools/kprof.py): where do the MMA warp and one epilogue thread spend their cycles.
 #ifdef DMN_KPROF
 __device__ long long g_kprof[160][16];
+__device__ long long g_ktrace[4][64];     // CTA 0, tile KTRACE_TILE: [mma step ready | mma step issued | epi acc_full seen | epi arrived][step]
+#define KTRACE_TILE 100
 #define KP_T0() const long long kp_t0 = clock64()
 #define KP_ADD(i) kp[i] += clock64() - kp_t0
 #else
@@ -334,8 +336,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
         wait_bar(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status);
         if (elect_one()) {
+#ifdef DMN_EXP_NOWEIGHTS     /* timing experiment only: no weight traffic (results are garbage) */
+          (void)image; (void)off; (void)bytes;
+          mbar_arrive(&misc->full[ring.slot]);
+#else
           mbar_arrive_expect_tx(&misc->full[ring.slot], bytes);
           bulk_g2s(smem + SM_RING + ring.slot * STAGE_BYTES, image + off, bytes, &misc->full[ring.slot]);
+#endif
         }
         __syncwarp();
         ring.advance();
@@ -345,6 +352,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     // =========================================================== MMA issuer (converged warp, one elected lane issues)
     // The per-tile schedule is written out structurally (it mirrors build_program(), which drives the producer, the
     // epilogue and the weight packing): 8 trunk layers x 2 half-steps, two folded hidden heads, two output heads.
+#ifdef DMN_KPROF
+    int64_t kt_tile = 0; int kt_step = 0;
+#endif
     long long kp[16] = {0};
     (void)kp;
     const long long kp_role0 = clock64();
@@ -377,6 +387,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     auto finish = [&](uint32_t acc) {
       if (elect_one()) mma_commit(&misc->acc_full[acc]);
       __syncwarp();
+#ifdef DMN_KPROF
+      if (blockIdx.x == 0 && kt_tile >= KTRACE_TILE && kt_tile < KTRACE_TILE + 2 && (tid & 31) == 0)
+        g_ktrace[1][(kt_tile - KTRACE_TILE) * 20 + kt_step] = clock64();
+      ++kt_step;
+#endif
     };
     // Slot 0 has been read by everything issued so far: the epilogue of the preceding even half-step may overwrite it.
     auto release_slot0 = [&]() {
@@ -388,6 +403,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     // so the odd half-step reads slot 0 first and releases it (a_free) before it turns to slot 1.
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const uint32_t g0 = (uint32_t)ti * N_STEPS;
+#ifdef DMN_KPROF
+      kt_tile = ti; kt_step = 0;
+#endif
       // ---- layer 0: E -> slots 0, 1
       for (uint32_t h = 0; h < 2; ++h) {
         const uint32_t g = g0 + h;
@@ -577,7 +595,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         }
 #ifdef DMN_KPROF
         const long long kp_p1 = clock64();
-        kp[14] += kp_p1 - kp_p0;
+        (void)kp_p0;
 #endif
         // |2^9 x| small enough for the branch-free sin/cos in every lane?  (warp-uniform choice; scenes are a few units wide)
         const float amax = fmaxf(fmaxf(fabsf(pt[0]), fabsf(pt[1])), fabsf(pt[2]));
@@ -594,7 +612,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         save_emb(16 * cg);
         store_split16_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg);
 #ifdef DMN_KPROF
-        kp[15] += clock64() - kp_p1;
+        (void)kp_p1;
 #endif
         if (cg == 0 || cg == 3) {                        // |vd| <= 1: always the branch-free path; 27 valid entries, rest 0
           if (cg == 0) fill_embedding<0, 16, L_DIR, true>(vd, vals);
@@ -631,39 +649,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       const float* bias_base = (FUSED && j != 0) ? a.bias_fine : a.bias;
       // ---------------- epilogues of the 20 half-steps
       for (int t = 0; t < N_STEPS; ++t) {
-        const Step& st = prog.step[t];
         const uint32_t g = (uint32_t)ti * N_STEPS + t, acc = g & 1;
-        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
-        tc_fence_after();
-#ifdef DMN_KPROF
-        const long long kp_body0 = clock64();
-#endif
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
         const float* bias = bias_base + t * 128;
         const int q = cg;                             // output heads: 64-column half (column groups 0 and 1 only)
-        if (st.out_slot >= 0) {
-          // hidden half-step: this thread's 32 columns -> bias, (ReLU), split, store into the destination slot; the K
-          // chunk is published on its own barrier as soon as its two column groups are done.
-          const int slot = st.out_slot;
+        if (t < N_STEPS - 2) {
+          // hidden half-step (ReLU layers; even steps fill slot 0, odd steps slot 1): this thread's 32 columns -> bias,
+          // ReLU, split, store into the destination slot; the K chunk is published on its own barrier as soon as its two
+          // column groups are done.  The bias is fetched before the accumulator is waited for (L1 is tiny next to 224 KB of
+          // shared memory: these loads usually come from L2).
+          const int slot = t & 1;
           const int c = cg >> 1;                                                    // K chunk of the output
           const int col = cg * 32;                                                  // first of this thread's 32 columns
           const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS + c * 32 + (cg & 1) * 16;
+          float4 bb[8];
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) bb[jj] = __ldg(b4 + jj);
+          { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+          tc_fence_after();
+#ifdef DMN_KPROF
+          const long long kp_body0 = clock64();
+          if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[2][(ti - KTRACE_TILE) * 20 + t] = kp_body0;
+#endif
           uint32_t v[32];
           tmem_ld_x32(acc_addr + col, v);
           tmem_ld_wait();
+#ifdef DMN_KPROF
+          const long long kp_e1 = clock64();
+          if (t & 1) kp[14] += kp_e1 - kp_body0;
+#endif
           float f[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const float4 bb = __ldg(b4 + jj);
-            f[4 * jj + 0] = __uint_as_float(v[4 * jj + 0]) + bb.x;
-            f[4 * jj + 1] = __uint_as_float(v[4 * jj + 1]) + bb.y;
-            f[4 * jj + 2] = __uint_as_float(v[4 * jj + 2]) + bb.z;
-            f[4 * jj + 3] = __uint_as_float(v[4 * jj + 3]) + bb.w;
-          }
-          if (st.relu) {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.0f);
+            f[4 * jj + 0] = fmaxf(__uint_as_float(v[4 * jj + 0]) + bb[jj].x, 0.0f);
+            f[4 * jj + 1] = fmaxf(__uint_as_float(v[4 * jj + 1]) + bb[jj].y, 0.0f);
+            f[4 * jj + 2] = fmaxf(__uint_as_float(v[4 * jj + 2]) + bb[jj].z, 0.0f);
+            f[4 * jj + 3] = fmaxf(__uint_as_float(v[4 * jj + 3]) + bb[jj].w, 0.0f);
           }
           if ((t & 1) == 0 && t >= 2) {
             // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
@@ -672,7 +694,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             KP_ADD(9);
             tc_fence_after();
           }
+#ifdef DMN_KPROF
+          const long long kp_e2 = clock64();
+          if (t & 1) kp[15] += kp_e2 - kp_e1;
+#endif
           store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
+#ifdef DMN_KPROF
+          const long long kp_e3 = clock64();
+          if (t & 1) kp[13] += kp_e3 - kp_e2;
+#endif
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&misc->epi_done[acc][c]);
+#ifdef DMN_KPROF
+          kp[12] += clock64() - kp_e3;
+          if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[3][(ti - KTRACE_TILE) * 20 + t] = clock64();
+#endif
+          // ---- off the critical path (the MMA warp is already running on what was just published)
           if (t == 14 || t == 15) {   // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
             const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + col);
 #pragma unroll
@@ -683,9 +721,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
               dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
             }
-            if (t == 15) {            // publish this thread's partial sum of the dot product; the rgb-head epilogue
-              misc->dens[cg][r] = dens_acc;      // (3 barrier hops later) adds the four column groups in a fixed order
-              dens_acc = 0.0f;
+            if (t == 15) {            // publish this thread's partial sum of the dot product; the rgb-head epilogue adds
+              misc->dens[cg][r] = dens_acc;      // the four column groups in a fixed order (ordered by this thread's later
+              dens_acc = 0.0f;                   // epi_done arrivals of steps 16 / 17 -> MMA -> acc_full of step 18)
             }
           }
           if constexpr (!FUSED) {
@@ -696,15 +734,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               store_row32(dst + col, f);
             }
           }
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc][c]);
-#ifdef DMN_KPROF
-          kp[12 + c] += clock64() - kp_body0;
-#endif
           // E / D were last read by half-step 16 (complete: we are past 17's accumulator): prepare the next tile now
           if (t == 17 && early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
-        } else if (cg >= 2) {
+          continue;
+        }
+        const Step& st = prog.step[t];
+        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+        tc_fence_after();
+        if (cg >= 2) {
+
           // the two output heads are drained by column groups 0 and 1 (256 threads, q = 64-column half) alone
           if (FUSED && j == 0 && t == N_STEPS - 1) asm volatile("bar.sync 3, 512;" ::: "memory");   // fine depths (below)
         } else if (t == N_STEPS - 2) {
@@ -864,6 +902,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 extern "C" __attribute__((visibility("default"))) int dmnerf_debug_kprof(long long* out, int n_blocks) {
   cudaDeviceSynchronize();
   return (int)cudaMemcpyFromSymbol(out, dmnerf::uk::g_kprof, sizeof(long long) * 16 * (size_t)n_blocks);
+}
+extern "C" __attribute__((visibility("default"))) int dmnerf_debug_ktrace(long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, dmnerf::uk::g_ktrace, sizeof(long long) * 4 * 64);
 }
 namespace dmnerf {
 namespace uk {

@@ -14,17 +14,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tools", "bin", "libdmnerf_kprof.so")
 NAMES = ["mma:wait acc drained", "mma:wait epi(g-1) chunk0", "mma:wait epi(g-1) chunk1", "mma:wait inputs", "mma:wait W_hi stage",
          "mma:wait W_lo stage", "mma:role total", "mma:wait (head steps)", "epi:wait acc_full", "epi:wait a_free",
-         "epi:prologue", "epi:role total", "epi:acc_full->arrive c0 (sum)", "epi:acc_full->arrive c1 (sum)", "pro:loads+points", "pro:E[0:32] sincos+store"]
+         "epi:prologue", "epi:role total", "epi(x18): wait::st+fence+arrive", "epi(odd x9): split + st issue", "epi(odd x9): acc_full->ld done", "epi(odd x9): bias/relu"]
 
 
 def build():
+    global LIB
+    extra = [x for x in sys.argv if x.startswith("-D")]
+    if extra:
+        LIB = LIB.replace(".so", "_" + "_".join(x[2:].lower() for x in extra) + ".so")
     sys.path.insert(0, ROOT)
     from dmnerf_b200 import build as b
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     for src in b.SOURCES:
         obj = os.path.join(ROOT, "tools", "bin", "kprof_" + src.replace(".cu", ".o"))
-        subprocess.check_call([b.nvcc()] + b.NVCC_FLAGS + ["-DDMN_KPROF", "-I", os.path.join(ROOT, "include"), "-c",
+        subprocess.check_call([b.nvcc()] + b.NVCC_FLAGS + extra + ["-DDMN_KPROF", "-I", os.path.join(ROOT, "include"), "-c",
                                                            os.path.join(b.CSRC, src), "-o", obj])
         objs.append(obj)
     subprocess.check_call([b.nvcc()] + b.NVCC_FLAGS[:2] + ["-shared", "-o", LIB] + objs + ["-lcudart"])
@@ -34,7 +38,7 @@ def build():
 def main():
     if "--build" in sys.argv:
         return build()
-    os.environ["DMNERF_LIB_PATH"] = LIB
+    os.environ["DMNERF_LIB_PATH"] = os.environ.get("KPROF_LIB", LIB)
     sys.path.insert(0, ROOT)
     import numpy as np
     import torch
@@ -77,6 +81,23 @@ def main():
         if nm == "-":
             continue
         print("  %-34s %9.0f | %9.0f | %9.0f" % (nm, a[:, i].mean() / tpc, a[0, i] / tpc, a[147, i] / tpc))
+    trace(lib)
+
+
+def trace(lib):
+    import numpy as np
+    buf = (C.c_longlong * 256)()
+    lib.dmnerf_debug_ktrace.restype = C.c_int
+    lib.dmnerf_debug_ktrace.argtypes = [C.c_void_p]
+    assert lib.dmnerf_debug_ktrace(buf) == 0
+    a = np.frombuffer(buf, dtype=np.int64).reshape(4, 64)
+    t0 = a[2][0]
+    print("CTA 0, two consecutive tiles: cycles relative to the first acc_full observation")
+    print(" step | mma issued | acc_full seen (delta) | epilogue arrived (body)")
+    prev = t0
+    for i in range(40):
+        print("  %3d | %9d | %9d (%6d) | %9d (%5d)" % (i, a[1][i] - t0, a[2][i] - t0, a[2][i] - prev, a[3][i] - t0, a[3][i] - a[2][i]))
+        prev = a[2][i]
 
 
 if __name__ == "__main__":
