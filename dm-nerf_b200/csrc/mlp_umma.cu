@@ -260,6 +260,16 @@ __device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* 
   }
 }
 
+// 8 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+8): one 16-byte unit each).
+__device__ __forceinline__ void store_split8_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  const uint32_t o = sw128_offset(row, k0);
+  *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // 16 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+16)).
 __device__ __forceinline__ void store_split16_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
   uint32_t hi[8], lo[8];
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     // The per-tile schedule is written out structurally (it mirrors build_program(), which drives the producer, the
     // epilogue and the weight packing): 8 trunk layers x 2 half-steps, two folded hidden heads, two output heads.
 #ifdef DMN_KPROF
-    int64_t kt_tile = 0; int kt_step = 0;
+    int64_t kt_tile = 0; int kt_step = 0; long long kt_ww = 0, kt_we = 0;
 #endif
     long long kp[16] = {0};
     (void)kp;
@@ -388,8 +398,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       if (elect_one()) mma_commit(&misc->acc_full[acc]);
       __syncwarp();
 #ifdef DMN_KPROF
-      if (blockIdx.x == 0 && kt_tile >= KTRACE_TILE && kt_tile < KTRACE_TILE + 2 && (tid & 31) == 0)
+      if (blockIdx.x == 0 && kt_tile >= KTRACE_TILE && kt_tile < KTRACE_TILE + 2 && (tid & 31) == 0) {
         g_ktrace[1][(kt_tile - KTRACE_TILE) * 20 + kt_step] = clock64();
+        const long long ww = kp[4] + kp[5], we = kp[0] + kp[1] + kp[2] + kp[3] + kp[7];
+        g_ktrace[0][(kt_tile - KTRACE_TILE) * 20 + kt_step] = ((ww - kt_ww) << 32) | (we - kt_we);
+        kt_ww = ww; kt_we = we;
+      } else if ((tid & 31) == 0) { kt_ww = kp[4] + kp[5]; kt_we = kp[0] + kp[1] + kp[2] + kp[3] + kp[7]; }
       ++kt_step;
 #endif
     };
@@ -490,14 +504,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     const long long kp_role0 = clock64();
     (void)kp_role0;
     // Operands (points, embeddings) of tile `tp`, split bf16 hi / lo into the shared-memory slabs, then inputs_ready.
-    // Column group cg computes embedding columns [16 cg, 16 cg + 16) of the position; groups 0 and 3 also one half of the
-    // direction embedding.  Called EARLY -- during the previous tile, right after the last reader of E / D (half-step 16)
-    // has completed; only the first tile of a CTA and the first fine tile of a ray pair (whose depths come out of this
-    // tile's importance sampling) are prepared late.
-    auto prologue = [&](int64_t tp) {
-#ifdef DMN_KPROF
-      const long long kp_p0 = clock64();
-#endif
+    // The work comes in parts so that it can be spread over the idle time of several epilogues of the PREVIOUS tile:
+    //   PRO_E0 / PRO_E1: position-embedding columns [16 cg, 16 cg + 8) / [16 cg + 8, 16 cg + 16) of this thread's row
+    //                    (the E slabs are free once half-step 11, the skip layer, has completed)
+    //   PRO_D:           direction embedding, 16 columns each by column groups 2 and 3 (free after half-step 16)
+    //   PRO_DONE:        make the slabs visible to the tensor core and arrive on inputs_ready
+    // Only the first tile of a CTA and the first fine tile of a ray pair (whose depths come out of the coarse tile's
+    // importance sampling) are prepared in one piece (PRO_ALL) at the tile boundary.
+    constexpr int PRO_E0 = 1, PRO_E1 = 2, PRO_D = 4, PRO_DONE = 8, PRO_ALL = 15;
+    auto prologue = [&](int64_t tp, const int parts) {
       const int jp = FUSED ? (int)(tp & 3) : 0;
       const int64_t itemp = blockIdx.x + (FUSED ? (tp >> 2) : tp) * gridDim.x;
       const int up = FUSED ? (int)((tp >> 2) & 1) : 0;                   // ray-data buffer of that ray pair
@@ -506,15 +521,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       bool validp;
       if constexpr (FUSED) {
         if (jp == 0) {
-          if (et < 2) {
-            const int64_t ray = itemp * 2 + et;
-            const bool ok = ray < a.n_rays;
-            float* rs = fz->ray[up][et];
-            for (int c = 0; c < 3; ++c) { rs[c] = ok ? a.rays_o[ray * 3 + c] : 0.0f; rs[3 + c] = ok ? a.rays_d[ray * 3 + c] : 0.0f; }
-            rs[6] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
-            rs[7] = ok ? 1.0f : 0.0f;
+          if (parts & PRO_E0) {                                           // first part: fetch the pair's rays
+            if (et < 2) {
+              const int64_t ray = itemp * 2 + et;
+              const bool ok = ray < a.n_rays;
+              float* rs = fz->ray[up][et];
+              for (int c = 0; c < 3; ++c) { rs[c] = ok ? a.rays_o[ray * 3 + c] : 0.0f; rs[3 + c] = ok ? a.rays_d[ray * 3 + c] : 0.0f; }
+              rs[6] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
+              rs[7] = ok ? 1.0f : 0.0f;
+            }
+            asm volatile("bar.sync 3, 512;" ::: "memory");
           }
-          asm volatile("bar.sync 3, 512;" ::: "memory");
           rlp = r >> 6; sip = r & 63;
         } else {
           const int gr = (jp - 1) * TILE_M + r;
@@ -525,39 +542,40 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         rowp = itemp * TILE_M + r;
         validp = rowp < a.m;
       }
+      const bool do_d = (parts & PRO_D) && cg >= 2;
+      const int d_col0 = (cg == 2) ? 0 : 16;
       float vals[16];
-      auto zero_if_invalid = [&]() {
-        if (!validp) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) vals[i] = 0.0f;
-        }
-      };
-      auto save_emb = [&](int col0) {          // training forward: keep the embedded inputs (ActPlanes.emb)
+      auto save_emb = [&](int col0, auto cntc) {          // training forward: keep the embedded inputs (ActPlanes.emb)
+        constexpr int CNT = decltype(cntc)::value;
         if constexpr (!FUSED) {
           if (a.acts && validp) {
             float* dst = act_planes(a.acts, a.m).emb + rowp * CH_IN + col0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < CNT; ++i)
               if (col0 + i < CH_IN && (col0 >= CH_POS || col0 + i < CH_POS)) dst[i] = vals[i];
           }
         }
       };
+      using c8 = std::integral_constant<int, 8>;
+      using c16 = std::integral_constant<int, 16>;
       if (!FUSED && a.x) {
+        // pre-embedded input rows [M, 90]
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int e = 16 * cg + i;
-          vals[i] = (validp && e < CH_POS) ? a.x[rowp * CH_IN + e] : 0.0f;
-        }
-        save_emb(16 * cg);
-        store_split16_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg);
-        if (cg == 0 || cg == 3) {
-          const int d0 = (cg == 0) ? 0 : 16;
+        for (int half = 0; half < 2; ++half) {
+          if (!(parts & (half ? PRO_E1 : PRO_E0))) continue;
+          const int e0 = 16 * cg + 8 * half;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) vals[i] = (validp && d0 + i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + d0 + i] : 0.0f;
-          save_emb(CH_POS + d0);
-          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, d0);
+          for (int i = 0; i < 8; ++i) vals[i] = (validp && e0 + i < CH_POS) ? a.x[rowp * CH_IN + e0 + i] : 0.0f;
+          save_emb(e0, c8{});
+          store_split8_smem(vals, e_hi_slab, e_lo_slab, r, e0);
         }
-      } else {
+        if (do_d) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vals[i] = (validp && d_col0 + i < CH_DIR) ? a.x[rowp * CH_IN + CH_POS + d_col0 + i] : 0.0f;
+          save_emb(CH_POS + d_col0, c16{});
+          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, d_col0);
+        }
+      } else if ((parts & (PRO_E0 | PRO_E1)) || do_d) {
         float pt[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
         if (validp) {
           float o0, o1, o2, d0, d1, d2, nrm, zz;
@@ -574,7 +592,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 const float upper = (sip == FS - 1) ? zz : __fmul_rn(0.5f, __fadd_rn(zr[sip + 1], zz));
                 zz = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.t_rand[ray * FS + sip]));
               }
-              if (cg == 0) {
+              if (cg == 0 && (parts & PRO_E0)) {
                 fz->zc[rlp][sip] = zz;
                 if (a.zc_out) a.zc_out[ray * FS + sip] = zz;
               }
@@ -591,45 +609,50 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
           pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
           pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
-          vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm);   // render.py:37
+          if (do_d) { vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm); }   // render.py:37
         }
-#ifdef DMN_KPROF
-        const long long kp_p1 = clock64();
-        (void)kp_p0;
-#endif
         // |2^9 x| small enough for the branch-free sin/cos in every lane?  (warp-uniform choice; scenes are a few units wide)
         const float amax = fmaxf(fmaxf(fabsf(pt[0]), fabsf(pt[1])), fabsf(pt[2]));
         const bool fast = __all_sync(FULL, amax < 64.0f);
-        auto embed_pos = [&](auto fastc) {
+        auto embed_pos8 = [&](auto fastc, auto halfc) {
           constexpr bool F = decltype(fastc)::value;
-          if (cg == 0) fill_embedding<0, 16, L_POS, F>(pt, vals);
-          else if (cg == 1) fill_embedding<16, 16, L_POS, F>(pt, vals);
-          else if (cg == 2) fill_embedding<32, 16, L_POS, F>(pt, vals);
-          else fill_embedding<48, 16, L_POS, F>(pt, vals);                  // entries 48..62, entry 63 is the zero pad
+          constexpr int H = decltype(halfc)::value;
+          if (cg == 0) fill_embedding<0 + 8 * H, 8, L_POS, F>(pt, vals);
+          else if (cg == 1) fill_embedding<16 + 8 * H, 8, L_POS, F>(pt, vals);
+          else if (cg == 2) fill_embedding<32 + 8 * H, 8, L_POS, F>(pt, vals);
+          else fill_embedding<48 + 8 * H, 8, L_POS, F>(pt, vals);           // entries 48..62, entry 63 is the zero pad
+          if (!validp) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vals[i] = 0.0f;
+          }
+          save_emb(16 * cg + 8 * H, c8{});
+          store_split8_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg + 8 * H);
         };
-        if (fast) embed_pos(std::true_type{}); else embed_pos(std::false_type{});
-        zero_if_invalid();
-        save_emb(16 * cg);
-        store_split16_smem(vals, e_hi_slab, e_lo_slab, r, 16 * cg);
-#ifdef DMN_KPROF
-        (void)kp_p1;
-#endif
-        if (cg == 0 || cg == 3) {                        // |vd| <= 1: always the branch-free path; 27 valid entries, rest 0
-          if (cg == 0) fill_embedding<0, 16, L_DIR, true>(vd, vals);
+        using h0 = std::integral_constant<int, 0>;
+        using h1 = std::integral_constant<int, 1>;
+        if (parts & PRO_E0) { if (fast) embed_pos8(std::true_type{}, h0{}); else embed_pos8(std::false_type{}, h0{}); }
+        if (parts & PRO_E1) { if (fast) embed_pos8(std::true_type{}, h1{}); else embed_pos8(std::false_type{}, h1{}); }
+        if (do_d) {                                      // |vd| <= 1: always the branch-free path; 27 valid entries, rest 0
+          if (cg == 2) fill_embedding<0, 16, L_DIR, true>(vd, vals);
           else fill_embedding<16, 16, L_DIR, true>(vd, vals);
-          zero_if_invalid();
-          save_emb(CH_POS + (cg == 0 ? 0 : 16));
-          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, cg == 0 ? 0 : 16);
+          if (!validp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vals[i] = 0.0f;
+          }
+          save_emb(CH_POS + d_col0, c16{});
+          store_split16_smem(vals, d_hi_slab, d_lo_slab, r, d_col0);
         }
       }
-      fence_proxy_async_smem();          // the embeddings are read by the tensor core through the async proxy
-      mbar_arrive(&misc->inputs_ready);
+      if (parts & PRO_DONE) {
+        fence_proxy_async_smem();          // the embeddings are read by the tensor core through the async proxy
+        mbar_arrive(&misc->inputs_ready);
+      }
     };
     (void)0;
     // may tile tp be prepared during tile tp-1?  (the first fine tile of a pair needs this tile's importance samples)
     auto early_ok = [&](int64_t tp) { return tp < my_tiles && (!FUSED || (tp & 3) != 1); };
 
-    if (my_tiles > 0) { KP_T0(); prologue(0); KP_ADD(10); }
+    if (my_tiles > 0) { KP_T0(); prologue(0, PRO_ALL); KP_ADD(10); }
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       // ---- which rows does this tile hold
       const int j = FUSED ? (int)(ti & 3) : 0;                            // fused: 0 = coarse tile, 1..3 = fine tiles
@@ -734,8 +757,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               store_row32(dst + col, f);
             }
           }
-          // E / D were last read by half-step 16 (complete: we are past 17's accumulator): prepare the next tile now
-          if (t == 17 && early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
+          // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11, D by 16.
+          if ((t == 11 || t == 13 || t == 17) && early_ok(ti + 1)) {
+            KP_T0();
+            prologue(ti + 1, t == 11 ? PRO_E0 : (t == 13 ? PRO_E1 : (PRO_D | PRO_DONE)));
+            KP_ADD(10);
+          }
           continue;
         }
         const Step& st = prog.step[t];
@@ -884,7 +911,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           }
         }
       }
-      if (ti + 1 < my_tiles && !early_ok(ti + 1)) { KP_T0(); prologue(ti + 1); KP_ADD(10); }
+      if (ti + 1 < my_tiles && !early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
     }
 #ifdef DMN_KPROF
     kp[11] = clock64() - kp_role0;

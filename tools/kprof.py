@@ -93,10 +93,11 @@ def trace(lib):
     a = np.frombuffer(buf, dtype=np.int64).reshape(4, 64)
     t0 = a[2][0]
     print("CTA 0, two consecutive tiles: cycles relative to the first acc_full observation")
-    print(" step | mma issued | acc_full seen (delta) | epilogue arrived (body)")
+    print(" step | mma issued (W-stage waits, epilogue waits during the step) | acc_full seen (delta) | epilogue arrived (body)")
     prev = t0
     for i in range(40):
-        print("  %3d | %9d | %9d (%6d) | %9d (%5d)" % (i, a[1][i] - t0, a[2][i] - t0, a[2][i] - prev, a[3][i] - t0, a[3][i] - a[2][i]))
+        print("  %3d | %9d (%5d, %5d) | %9d (%6d) | %9d (%5d)" % (i, a[1][i] - t0, a[0][i] >> 32, a[0][i] & 0xffffffff, a[2][i] - t0, a[2][i] - prev,
+                                                           a[3][i] - t0, a[3][i] - a[2][i]))
         prev = a[2][i]
 
 
