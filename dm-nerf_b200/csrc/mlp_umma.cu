@@ -30,10 +30,17 @@ namespace uk {
 using namespace umma;
 
 constexpr int TILE_M = 128;
-constexpr int NS = 9;                      // weight ring stages
+constexpr int NS = 8;                      // weight ring stages
 constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
 constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
-constexpr int N_STEPS = 20;
+constexpr int N_STEPS = 19;                 // 16 trunk half-steps, instance hidden, colour hidden (+ head on CUDA cores), instance head
+constexpr int T_INS_HID = 16, T_RGB_HID = 17, T_INS_OUT = 18;
+// fp32 side table of a network (KArgs::bias): per-step bias rows, then the small layers evaluated on CUDA cores
+constexpr int B_WD = N_STEPS * 128;        // density_linear weights [256]
+constexpr int B_BD = B_WD + 256;           // density bias (+3 pad)
+constexpr int B_WRGB = B_BD + 4;           // rgb_linear weights [3][128]
+constexpr int B_BRGB = B_WRGB + 3 * 128;   // rgb_linear bias (+1 pad)
+constexpr int B_TOTAL = B_BRGB + 4;
 constexpr int MAX_CHUNKS = 5;
 constexpr int MAX_STAGES = 160;
 constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TMEM lane quadrants x 4 column groups
@@ -56,7 +63,7 @@ constexpr uint32_t SM_D_HI = SM_E_LO + CHUNK_BYTES;             // direction emb
 constexpr uint32_t SM_D_LO = SM_D_HI + CHUNK_BYTES;
 constexpr uint32_t SM_RING = SM_D_LO + CHUNK_BYTES;
 constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
-constexpr uint32_t SM_FUSED = SM_MISC + 4096;                   // per-unit state of the fused render kernel
+constexpr uint32_t SM_FUSED = SM_MISC + 9216;                   // per-unit state of the fused render kernel
 constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
 
@@ -85,7 +92,7 @@ struct Misc {                  // lives at SM_MISC
   uint64_t a_free;             // the odd half-step of a layer has finished reading slot 0 (its even half-step may overwrite it)
   uint32_t tmem_base;
   int32_t abort_flag;
-  float dens[4][TILE_M];       // per column group: partial density dot products of the tile's rows
+  float4 part[4][TILE_M];      // per column group and row: partial dot products of the rgb head (xyz) and of the density (w)
 };
 
 // Shared state of the fused render kernel: one work unit = 2 rays = 1 coarse tile (2 x 64 samples) + 3 fine tiles (2 x 192).
@@ -104,11 +111,11 @@ struct Fused {
 };
 static_assert(sizeof(Fused) <= 12288, "Fused state does not fit its shared-memory block");
 
-static_assert(sizeof(Misc) <= 4096, "Misc does not fit its shared-memory block");
+static_assert(sizeof(Misc) <= 9216, "Misc does not fit its shared-memory block");
 
 struct KArgs {
   const uint8_t* image;        // packed bf16 operand image (fused: coarse network)
-  const float* bias;           // [N_STEPS][128] + wd[256] + bd
+  const float* bias;           // [N_STEPS][128] step biases, then the B_* blocks above
   const uint8_t* image_fine;   // fused: fine network
   const float* bias_fine;
   // fused render inputs / outputs (any output may be NULL)
@@ -415,6 +422,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
     // Slot 0 always holds K-half 0 of the current activation (written by the even half-step of the previous layer),
     // slot 1 K-half 1 (odd half-step).  The even epilogue of a layer runs while the odd half-step's MMAs are in flight,
     // so the odd half-step reads slot 0 first and releases it (a_free) before it turns to slot 1.
+    // Accumulators alternate with the GLOBAL half-step counter g (a tile has an odd number of half-steps).
     for (int64_t ti = 0; ti < my_tiles; ++ti) {
       const uint32_t g0 = (uint32_t)ti * N_STEPS;
 #ifdef DMN_KPROF
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #endif
       // ---- layer 0: E -> slots 0, 1
       for (uint32_t h = 0; h < 2; ++h) {
-        const uint32_t g = g0 + h;
+        const uint32_t g = g0 + h, acc = g & 1;
         if (g >= 2) { KP_T0(); need_drained(g - 2); KP_ADD(0); }
         {
           KP_T0();
@@ -434,13 +442,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         }
         tc_fence_after();
         uint32_t accum = 0;
-        issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, tbase + TC_ACC + h * 128, idesc128, accum, a.status, kp);
-        finish(h);
+        issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, tbase + TC_ACC + acc * 128, idesc128, accum, a.status, kp);
+        finish(acc);
       }
       // ---- layers 1..7
       for (int l = 1; l < 8; ++l) {
         for (uint32_t h = 0; h < 2; ++h) {
-          const uint32_t g = g0 + 2 * l + h, d_tmem = tbase + TC_ACC + h * 128;
+          const uint32_t g = g0 + 2 * l + h, acc = g & 1, d_tmem = tbase + TC_ACC + acc * 128;
           { KP_T0(); need_drained(g - 2); KP_ADD(0); }   // accumulator free (and, for h == 0, K-half 0 of the input complete)
           uint32_t accum = 0;
           slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
@@ -450,38 +458,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           if (h == 0) { KP_T0(); need_epi(g - 1, 1); KP_ADD(2); }
           slot_chunk(1, 1, d_tmem, idesc128, accum);
           if (l == 5) issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, d_tmem, idesc128, accum, a.status, kp);
-          finish(h);
+          finish(acc);
         }
       }
       {
-        // ---- folded colour hidden layer (step 16, acc 0): [h | dir] -> slot 0
-        uint32_t accum = 0, d_tmem = tbase + TC_ACC;
-        { KP_T0(); need_drained(g0 + 14); KP_ADD(7); }
+        // ---- folded instance hidden layer (half-step 16): h -> slot 0 (an even half-step like those of the trunk)
+        uint32_t g = g0 + T_INS_HID, acc = g & 1, d_tmem = tbase + TC_ACC + acc * 128, accum = 0;
+        { KP_T0(); need_drained(g - 2); KP_ADD(7); }
         slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
-        { KP_T0(); need_epi(g0 + 15, 0); KP_ADD(7); }
+        { KP_T0(); need_epi(g - 1, 0); KP_ADD(7); }
         slot_chunk(1, 0, d_tmem, idesc128, accum);
-        { KP_T0(); need_epi(g0 + 15, 1); KP_ADD(7); }
+        { KP_T0(); need_epi(g - 1, 1); KP_ADD(7); }
         slot_chunk(1, 1, d_tmem, idesc128, accum);
-        issue_chunk<2, true>(misc, ring, ring_base, d_hi, d_lo, d_tmem, idesc128, accum, a.status, kp);
-        finish(0);
-        // ---- folded instance hidden layer (step 17, acc 1): h -> slot 1
-        accum = 0; d_tmem = tbase + TC_ACC + 128;
+        finish(acc);
+        // ---- folded colour hidden layer (half-step 17): [h | dir]; its epilogue evaluates the 3-wide rgb head and the
+        //      density on CUDA cores, so nothing is written back to a slot.  Its MMAs hide the epilogue of half-step 16.
+        g = g0 + T_RGB_HID; acc = g & 1; d_tmem = tbase + TC_ACC + acc * 128; accum = 0;
+        { KP_T0(); need_drained(g - 2); KP_ADD(7); }
         slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
         release_slot0();
         slot_chunk(1, 0, d_tmem, idesc128, accum); slot_chunk(1, 1, d_tmem, idesc128, accum);
-        finish(1);
-        // ---- rgb head (step 18, acc 0, N=16) on the colour hidden activation (slot 0)
-        accum = 0; d_tmem = tbase + TC_ACC;
-        { KP_T0(); need_epi(g0 + 16, 0); KP_ADD(7); }   // N = 16 only touches accumulator columns of chunk 0
-        slot_chunk(0, 0, d_tmem, idesc16, accum);
-        { KP_T0(); need_epi(g0 + 16, 1); KP_ADD(7); }
-        slot_chunk(0, 1, d_tmem, idesc16, accum);
-        finish(0);
-        // ---- instance head (step 19, acc 1, N=pad16(ins_num+1)) on the instance hidden activation (slot 1)
-        accum = 0; d_tmem = tbase + TC_ACC + 128;
-        { KP_T0(); need_drained(g0 + 17); KP_ADD(7); }  // N may cover all 128 accumulator columns
-        slot_chunk(1, 0, d_tmem, idesc_ins, accum); slot_chunk(1, 1, d_tmem, idesc_ins, accum);
-        finish(1);
+        issue_chunk<2, true>(misc, ring, ring_base, d_hi, d_lo, d_tmem, idesc128, accum, a.status, kp);
+        finish(acc);
+        // ---- instance head (half-step 18, N = pad16(ins_num+1)) on the instance hidden activation (slot 0)
+        g = g0 + T_INS_OUT; acc = g & 1; d_tmem = tbase + TC_ACC + acc * 128; accum = 0;
+        { KP_T0(); need_drained(g - 2); KP_ADD(7); }    // slot 0 complete, accumulator of half-step 16 drained
+        slot_chunk(0, 0, d_tmem, idesc_ins, accum); slot_chunk(0, 1, d_tmem, idesc_ins, accum);
+        finish(acc);
       }
     }
 #ifdef DMN_KPROF
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
         const float* bias = bias_base + t * 128;
         const int q = cg;                             // output heads: 64-column half (column groups 0 and 1 only)
-        if (t < N_STEPS - 2) {
+        if (t <= T_RGB_HID) {
           // hidden half-step (ReLU layers; even steps fill slot 0, odd steps slot 1): this thread's 32 columns -> bias,
           // ReLU, split, store into the destination slot; the K chunk is published on its own barrier as soon as its two
           // column groups are done.  The bias is fetched before the accumulator is waited for (L1 is tiny next to 224 KB of
@@ -698,10 +701,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           uint32_t v[32];
           tmem_ld_x32(acc_addr + col, v);
           tmem_ld_wait();
-#ifdef DMN_KPROF
-          const long long kp_e1 = clock64();
-          if (t & 1) kp[14] += kp_e1 - kp_body0;
-#endif
+          if (t == T_RGB_HID) {       // nothing goes back to a slot: the accumulator is all the MMA warp waits for
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc][c]);
+          }
           float f[32];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -710,32 +713,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             f[4 * jj + 2] = fmaxf(__uint_as_float(v[4 * jj + 2]) + bb[jj].z, 0.0f);
             f[4 * jj + 3] = fmaxf(__uint_as_float(v[4 * jj + 3]) + bb[jj].w, 0.0f);
           }
-          if ((t & 1) == 0 && t >= 2) {
-            // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
-            KP_T0();
-            wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
-            KP_ADD(9);
-            tc_fence_after();
-          }
-#ifdef DMN_KPROF
-          const long long kp_e2 = clock64();
-          if (t & 1) kp[15] += kp_e2 - kp_e1;
-#endif
-          store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
-#ifdef DMN_KPROF
-          const long long kp_e3 = clock64();
-          if (t & 1) kp[13] += kp_e3 - kp_e2;
-#endif
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc][c]);
-#ifdef DMN_KPROF
-          kp[12] += clock64() - kp_e3;
-          if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[3][(ti - KTRACE_TILE) * 20 + t] = clock64();
-#endif
-          // ---- off the critical path (the MMA warp is already running on what was just published)
-          if (t == 14 || t == 15) {   // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
-            const float4* w4 = reinterpret_cast<const float4*>(bias_base + N_STEPS * 128 + (t - 14) * 128 + col);
+          auto density_partial = [&]() {   // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
+            const float4* w4 = reinterpret_cast<const float4*>(bias_base + B_WD + (t - 14) * 128 + col);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const float4 ww = __ldg(w4 + jj);
@@ -744,49 +723,80 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
               dens_acc = fmaf(f[4 * jj + 3], ww.w, dens_acc);
             }
-            if (t == 15) {            // publish this thread's partial sum of the dot product; the rgb-head epilogue adds
-              misc->dens[cg][r] = dens_acc;      // the four column groups in a fixed order (ordered by this thread's later
-              dens_acc = 0.0f;                   // epi_done arrivals of steps 16 / 17 -> MMA -> acc_full of step 18)
+          };
+          if (t < T_RGB_HID) {
+            if ((t & 1) == 0 && t >= 2) {
+              // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
+              KP_T0();
+              wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
+              KP_ADD(9);
+              tc_fence_after();
             }
+            store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
+            if (t == 15) {            // publish before this half-step's arrive: the arrive orders it ahead of the reader
+              density_partial();      // (epi_done 15 -> MMA warp -> acc_full 17 -> colour-head epilogue)
+              misc->part[cg][r].w = dens_acc;
+              dens_acc = 0.0f;
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc][c]);
+#ifdef DMN_KPROF
+            if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[3][(ti - KTRACE_TILE) * 20 + t] = clock64();
+#endif
+            if (t == 14) density_partial();      // off the critical path
           }
           if constexpr (!FUSED) {
             if (a.acts && valid) {                   // training forward: keep the post-activation values (ActPlanes)
               const ActPlanes ap = act_planes(a.acts, a.m);
               float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
-                                    : ((t == 16) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
+                                    : ((t == T_RGB_HID) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
               store_row32(dst + col, f);
             }
           }
-          // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11, D by 16.
-          if ((t == 11 || t == 13 || t == 17) && early_ok(ti + 1)) {
+          // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11.
+          if ((t == 11 || t == 13) && early_ok(ti + 1)) {
             KP_T0();
-            prologue(ti + 1, t == 11 ? PRO_E0 : (t == 13 ? PRO_E1 : (PRO_D | PRO_DONE)));
+            prologue(ti + 1, t == 11 ? PRO_E0 : PRO_E1);
             KP_ADD(10);
           }
-          continue;
-        }
-        const Step& st = prog.step[t];
-        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
-        tc_fence_after();
-        if (cg >= 2) {
-
-          // the two output heads are drained by column groups 0 and 1 (256 threads, q = 64-column half) alone
-          if (FUSED && j == 0 && t == N_STEPS - 1) asm volatile("bar.sync 3, 512;" ::: "memory");   // fine depths (below)
-        } else if (t == N_STEPS - 2) {
-          // rgb head (N=16: 3 live columns) + density                          (dm_nerf.py:101-102,105)
-          uint32_t v[16];
-          if (q == 0) {
-            tmem_ld_x16(acc_addr, v);
-            tmem_ld_wait();
+          if (t < T_RGB_HID) continue;
+          // ---------------- colour hidden layer: the 3-wide rgb head on CUDA cores (fp32), 32 columns per thread
+          {
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+            const float4* w0 = reinterpret_cast<const float4*>(bias_base + B_WRGB + col);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float4 wa = __ldg(w0 + jj), wb = __ldg(w0 + 32 + jj), wc = __ldg(w0 + 64 + jj);
+              p0 = fmaf(f[4 * jj + 0], wa.x, p0); p0 = fmaf(f[4 * jj + 1], wa.y, p0); p0 = fmaf(f[4 * jj + 2], wa.z, p0); p0 = fmaf(f[4 * jj + 3], wa.w, p0);
+              p1 = fmaf(f[4 * jj + 0], wb.x, p1); p1 = fmaf(f[4 * jj + 1], wb.y, p1); p1 = fmaf(f[4 * jj + 2], wb.z, p1); p1 = fmaf(f[4 * jj + 3], wb.w, p1);
+              p2 = fmaf(f[4 * jj + 0], wc.x, p2); p2 = fmaf(f[4 * jj + 1], wc.y, p2); p2 = fmaf(f[4 * jj + 2], wc.z, p2); p2 = fmaf(f[4 * jj + 3], wc.w, p2);
+            }
+            float4* dstp = &misc->part[cg][r];
+            dstp->x = p0; dstp->y = p1; dstp->z = p2;
           }
-          tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc][0]);          // accumulator drained: the next tile's first half-step may start
-          mbar_arrive(&misc->epi_done[acc][1]);
-          if (q == 0) {
-            const float c0 = __uint_as_float(v[0]) + __ldg(bias + 0), c1 = __uint_as_float(v[1]) + __ldg(bias + 1),
-                        c2 = __uint_as_float(v[2]) + __ldg(bias + 2);
-            const float sigma = ((misc->dens[0][r] + misc->dens[1][r]) + (misc->dens[2][r] + misc->dens[3][r])) +
-                                __ldg(bias_base + N_STEPS * 128 + 256);
+          // D was last read by this half-step: finish the next tile's operands (column groups 2 and 3 embed the direction).
+          // After a coarse tile of the fused kernel the next tile's depths do not exist yet: everybody waits for column
+          // group 0 to composite this tile and draw the importance samples, then prepares the first fine tile in one piece
+          // (the instance head of this tile is drained afterwards, off the critical path).
+          const bool late_next = FUSED && j == 0 && ti + 1 < my_tiles;
+          if (cg != 0) {
+            asm volatile("bar.arrive 4, 512;" ::: "memory");
+            if (early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_D | PRO_DONE); KP_ADD(10); }
+            if (FUSED && j == 0) asm volatile("bar.sync 3, 512;" ::: "memory");     // fine depths are in shared memory
+            if (late_next) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
+            continue;
+          }
+          if (early_ok(ti + 1)) prologue(ti + 1, PRO_DONE);
+          asm volatile("bar.sync 4, 512;" ::: "memory");
+          if (cg == 0) {
+            // rgb_linear (dm_nerf.py:102,105) and density_linear (dm_nerf.py:101): add the four column groups' partial
+            // dot products in a fixed order
+            const float4 s0 = misc->part[0][r], s1 = misc->part[1][r], s2 = misc->part[2][r], s3 = misc->part[3][r];
+            const float c0 = ((s0.x + s1.x) + (s2.x + s3.x)) + __ldg(bias_base + B_BRGB + 0);
+            const float c1 = ((s0.y + s1.y) + (s2.y + s3.y)) + __ldg(bias_base + B_BRGB + 1);
+            const float c2 = ((s0.z + s1.z) + (s2.z + s3.z)) + __ldg(bias_base + B_BRGB + 2);
+            const float sigma = ((s0.w + s1.w) + (s2.w + s3.w)) + __ldg(bias_base + B_BD);
             if constexpr (!FUSED) {
               if (valid) {
                 float* o = a.out + row * C;
@@ -832,6 +842,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               }
             }
           }
+          if constexpr (FUSED) {
+            if (j == 0) {
+              // ---- hierarchical sampling (render.py:66-70) by this column group: 64 threads per ray, results stay in
+              //      shared memory.  (Barrier 1 = the 128 threads of column group 0.)
+              const int rr = r >> 6, t64 = r & 63;
+              fz->vals[rr][t64] = fz->zc[rr][t64];
+              if (t64 < FS - 1) fz->bins[rr][t64] = __fmul_rn(0.5f, __fadd_rn(fz->zc[rr][t64 + 1], fz->zc[rr][t64]));
+              asm volatile("bar.sync 1, 128;" ::: "memory");          // bins and this tile's weights fz->w are complete
+              const int64_t ray = item * 2 + rr;
+              const float* wr = fz->w + rr * FS;
+              const float* uu = (a.u && fz->ray[u_cur][rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
+              if (t64 < 32) ray_build_cdf([&](int k) { return wr[k + 1]; }, FS - 1, fz->cdf[rr], t64);
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              for (int sidx = t64; sidx < FI; sidx += 64)
+                fz->vals[rr][FS + sidx] = ray_sample_at(fz->bins[rr], fz->cdf[rr], FS - 1, uu ? uu[sidx] : linspace01(sidx, FI));
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              // both runs ascending (always, for the deterministic linspace)?  One vote for the pair keeps the barrier simple.
+              const bool mine = (uu == nullptr) && ray_sorted_part(fz->vals[rr] + FS, FI, t64, 64) && ray_sorted_part(fz->vals[rr], FS, t64, 64);
+              int all_sorted;
+              asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.and.pred q, 1, 128, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                           : "=r"(all_sorted) : "r"((int)mine) : "memory");
+              if (all_sorted) ray_merge_part(fz->vals[rr], FS, fz->vals[rr] + FS, FI, fz->zf[rr], t64, 64);
+              else ray_rank_part(fz->vals[rr], FF, fz->zf[rr], t64, 64);
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
+                for (int k = t64; k < FF; k += 64) a.zf_out[ray * FF + k] = fz->zf[rr][k];
+              asm volatile("bar.sync 3, 512;" ::: "memory");          // fine depths visible to every prologue thread
+              if (late_next) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
+            }
+          }
+          continue;
+        }
+        const Step& st = prog.step[t];
+        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+        tc_fence_after();
+        if (cg >= 2) {
+          // the instance head is drained by column groups 0 and 1 (256 threads, q = 64-column half) alone
         } else {
           // instance head (N = pad16(ins_num+1))                                 (dm_nerf.py:103,105)
           if constexpr (!FUSED) {
@@ -888,30 +935,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 else if (et - 5 < n_out) { if (o_ins) o_ins[ray * n_out + (et - 5)] = sigmoidf_acc(vsum); }
               }
             }
-            if (j == 0) {
-              // ---- hierarchical sampling (render.py:66-70): one warp per ray, results stay in shared memory
-              if (et < 64) {
-                const int rr = et >> 5, ln = et & 31;
-                for (int k = ln; k < FS; k += 32) fz->vals[rr][k] = fz->zc[rr][k];
-                __syncwarp();
-                for (int k = ln; k < FS - 1; k += 32) fz->bins[rr][k] = __fmul_rn(0.5f, __fadd_rn(fz->zc[rr][k + 1], fz->zc[rr][k]));
-                __syncwarp();
-                const int64_t ray = item * 2 + rr;
-                const float* wr = fz->w + rr * FS;
-                const float* uu = (a.u && fz->ray[u_cur][rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
-                ray_sample_pdf(fz->bins[rr], [&](int k) { return wr[k + 1]; }, FS - 1, FI, uu, fz->cdf[rr], fz->vals[rr] + FS, ln);
-                if (!uu && ray_is_sorted(fz->vals[rr] + FS, FI, ln) && ray_is_sorted(fz->vals[rr], FS, ln))
-                  ray_merge_sorted(fz->vals[rr], FS, fz->vals[rr] + FS, FI, fz->zf[rr], ln);
-                else ray_rank_sort(fz->vals[rr], FF, fz->zf[rr], ln);
-                if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
-                  for (int k = ln; k < FF; k += 32) a.zf_out[ray * FF + k] = fz->zf[rr][k];
-              }
-              asm volatile("bar.sync 3, 512;" ::: "memory");   // fine depths visible to every prologue thread
-            }
           }
         }
       }
-      if (ti + 1 < my_tiles && !early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
+      if (ti + 1 < my_tiles && !early_ok(ti + 1) && !(FUSED && j == 0)) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
     }
 #ifdef DMN_KPROF
     kp[11] = clock64() - kp_role0;
@@ -962,13 +989,11 @@ static void build_program(Program& P, int ins_num) {
     }
     a_step = t - 2; b_step = t - 1;
   }
-  // folded colour branch -> slot 0; folded instance branch -> slot 1
-  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = 0; add_act(s); add_chunk(s, CK_D, -1, 2); ++t; }
-  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = 1; add_act(s); ++t; }
-  { Step& s = P.step[t]; s.n = 16; s.relu = 0; s.out_slot = -1;
+  // folded instance branch -> slot 0; folded colour branch (its 3-wide head runs on CUDA cores); instance head on slot 0
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = 0; add_act(s); ++t; }                              // T_INS_HID
+  { Step& s = P.step[t]; s.n = 128; s.relu = 1; s.out_slot = -1; add_act(s); add_chunk(s, CK_D, -1, 2); ++t; }  // T_RGB_HID
+  { Step& s = P.step[t]; s.n = (int16_t)(((ins_num + 1) + 15) / 16 * 16); s.relu = 0; s.out_slot = -1;        // T_INS_OUT
     add_chunk(s, 0, t - 2, 4); add_chunk(s, 1, t - 2, 4); ++t; }
-  { Step& s = P.step[t]; s.n = (int16_t)(((ins_num + 1) + 15) / 16 * 16); s.relu = 0; s.out_slot = -1;
-    add_chunk(s, 2, t - 2, 4); add_chunk(s, 3, t - 2, 4); ++t; }
   // stage offsets
   uint32_t off = 0;
   int si = 0;
@@ -1027,18 +1052,19 @@ __global__ void pack_kernel(const PackStage* __restrict__ stages, int n_entries,
 
 __global__ void bias_kernel(NetParams p, const float* __restrict__ fold_b_rgb, const float* __restrict__ fold_b_ins,
                             float* __restrict__ bias) {
-  // [20][128] step biases, then density weights [256], then density bias
-  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < N_STEPS * 128 + 257; i += blockDim.x * gridDim.x) {
+  // [N_STEPS][128] step biases, then the CUDA-core layers: density weights / bias, rgb_linear weights / bias (B_* offsets)
+  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < B_TOTAL; i += blockDim.x * gridDim.x) {
     float v = 0.0f;
     if (i < 16 * 128) {
       const int t = i / 128, c = i % 128, l = t / 2, h = t % 2;
       v = p.b[l][h * 128 + c];
-    } else if (i < 17 * 128) v = fold_b_rgb[i - 16 * 128];
-    else if (i < 18 * 128) v = fold_b_ins[i - 17 * 128];
-    else if (i < 19 * 128) { const int c = i - 18 * 128; v = c < 3 ? p.b[L_RGB_OUT][c] : 0.0f; }
-    else if (i < 20 * 128) { const int c = i - 19 * 128; v = c < p.ins_num + 1 ? p.b[L_INS_OUT][c] : 0.0f; }
-    else if (i < 20 * 128 + 256) v = p.w[L_DENSITY][i - 20 * 128];
-    else v = p.b[L_DENSITY][0];
+    } else if (i < (T_INS_HID + 1) * 128) v = fold_b_ins[i - T_INS_HID * 128];
+    else if (i < (T_RGB_HID + 1) * 128) v = fold_b_rgb[i - T_RGB_HID * 128];
+    else if (i < (T_INS_OUT + 1) * 128) { const int c = i - T_INS_OUT * 128; v = c < p.ins_num + 1 ? p.b[L_INS_OUT][c] : 0.0f; }
+    else if (i < B_WD + 256) v = p.w[L_DENSITY][i - B_WD];
+    else if (i == B_BD) v = p.b[L_DENSITY][0];
+    else if (i >= B_WRGB && i < B_WRGB + 3 * 128) v = p.w[L_RGB_OUT][i - B_WRGB];
+    else if (i >= B_BRGB && i < B_BRGB + 3) v = p.b[L_RGB_OUT][i - B_BRGB];
     bias[i] = v;
   }
 }
@@ -1081,7 +1107,7 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
     w.ins_num = p.ins_num;
     w.image_bytes = x->prog.stage_off[x->prog.n_stages];
     DMN_CUDA(cudaMalloc(&w.image, w.image_bytes));
-    DMN_CUDA(cudaMalloc((void**)&w.bias, (N_STEPS * 128 + 260) * sizeof(float)));
+    DMN_CUDA(cudaMalloc((void**)&w.bias, B_TOTAL * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_w_rgb, 128 * 283 * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_w_ins, 128 * 256 * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_b, 256 * sizeof(float)));
@@ -1110,13 +1136,11 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
         e.src = p.w[l]; e.ld = layer_in(l); e.n_base = h * 128; e.n_valid = 128;
         if (kind == CK_E) { e.col_base = (l == 0) ? 0 : 256; e.k_valid = 63; }
         else { e.col_base = 64 * c; e.k_valid = 64; }
-      } else if (t == 16) {                           // folded rgb hidden layer: [128][283]
+      } else if (t == T_RGB_HID) {                    // folded rgb hidden layer: [128][283]
         e.src = x->fold_w_rgb; e.ld = 283; e.n_base = 0; e.n_valid = 128;
         if (kind == CK_D) { e.col_base = 256; e.k_valid = 27; } else { e.col_base = 64 * c; e.k_valid = 64; }
-      } else if (t == 17) {                           // folded instance hidden layer: [128][256]
+      } else if (t == T_INS_HID) {                    // folded instance hidden layer: [128][256]
         e.src = x->fold_w_ins; e.ld = 256; e.n_base = 0; e.n_valid = 128; e.col_base = 64 * c; e.k_valid = 64;
-      } else if (t == 18) {                           // rgb_linear [3][128]
-        e.src = p.w[L_RGB_OUT]; e.ld = 128; e.n_base = 0; e.n_valid = 3; e.col_base = 64 * c; e.k_valid = 64;
       } else {                                        // ins_linear [ins_num+1][128]
         e.src = p.w[L_INS_OUT]; e.ld = 128; e.n_base = 0; e.n_valid = p.ins_num + 1; e.col_base = 64 * c; e.k_valid = 64;
       }

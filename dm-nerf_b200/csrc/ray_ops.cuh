@@ -85,9 +85,9 @@ __device__ __forceinline__ float warp_scan_add(float v, int lane) {
 //   bins: [nb] (shared), wts: accessor for nb-1 weights, cdf: shared scratch [nb], out: [ns].
 //   u == nullptr => deterministic linspace.  The cdf is a warp prefix sum (the reference's GPU cumsum is a parallel fp32
 //   scan as well; its CPU cumsum differs from either by ~1e-7, far below the 1e-5 bin-mass threshold of helpers.py:151).
+// Part 1 (one warp): cdf[0..nb) of the nb-1 bin weights.
 template <class WFn>
-__device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int nb, int ns, const float* u, float* cdf,
-                                               float* out, int lane) {
+__device__ __forceinline__ void ray_build_cdf(WFn wts, int nb, float* cdf, int lane) {
   const int nw = nb - 1;
   float part = 0.0f;
   for (int j = lane; j < nw; j += 32) part += __fadd_rn(wts(j), 1e-5f);      // helpers.py:125
@@ -101,39 +101,52 @@ __device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int n
     if (j < nw) cdf[j + 1] = carry + incl;
     carry += __shfl_sync(FULL, incl, 31);
   }
-  __syncwarp();
-  for (int s = lane; s < ns; s += 32) {
-    const float us = u ? u[s] : linspace01(s, ns);
-    // searchsorted(cdf, u, right=True): first index with cdf[idx] > u   (helpers.py:139)
-    int lo = 0, hi = nb;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cdf[mid] > us) hi = mid; else lo = mid + 1;
-    }
-    const int below = max(lo - 1, 0), above = min(lo, nb - 1);
-    const float cb = cdf[below], ca = cdf[above];
-    float denom = __fsub_rn(ca, cb);
-    if (denom < 1e-5f) denom = 1.0f;                                          // helpers.py:151
-    const float t = __fdiv_rn(__fsub_rn(us, cb), denom);
-    const float bb = bins[below], ba = bins[above];
-    out[s] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                  // helpers.py:153
+}
+
+// Part 2 (any thread): the sample for one value of u.
+__device__ __forceinline__ float ray_sample_at(const float* bins, const float* cdf, int nb, float us) {
+  // searchsorted(cdf, u, right=True): first index with cdf[idx] > u   (helpers.py:139)
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] > us) hi = mid; else lo = mid + 1;
   }
+  const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+  const float cb = cdf[below], ca = cdf[above];
+  float denom = __fsub_rn(ca, cb);
+  if (denom < 1e-5f) denom = 1.0f;                                          // helpers.py:151
+  const float t = __fdiv_rn(__fsub_rn(us, cb), denom);
+  const float bb = bins[below], ba = bins[above];
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));                    // helpers.py:153
+}
+
+template <class WFn>
+__device__ __forceinline__ void ray_sample_pdf(const float* bins, WFn wts, int nb, int ns, const float* u, float* cdf,
+                                               float* out, int lane) {
+  ray_build_cdf(wts, nb, cdf, lane);
   __syncwarp();
+  for (int s = lane; s < ns; s += 32) out[s] = ray_sample_at(bins, cdf, nb, u ? u[s] : linspace01(s, ns));
+  __syncwarp();
+}
+
+// Thread `tid` of `nthr` cooperating threads: is its share of v[0..n) (shared) non-decreasing?
+__device__ __forceinline__ bool ray_sorted_part(const float* v, int n, int tid, int nthr) {
+  bool ok = true;
+  for (int i = tid + 1; i < n; i += nthr) ok = ok && (v[i] >= v[i - 1]);
+  return ok;
 }
 
 // Warp-uniform: is v[0..n) (shared) non-decreasing?
 __device__ __forceinline__ bool ray_is_sorted(const float* v, int n, int lane) {
-  bool ok = true;
-  for (int i = lane + 1; i < n; i += 32) ok = ok && (v[i] >= v[i - 1]);
-  return __all_sync(FULL, ok);
+  return __all_sync(FULL, ray_sorted_part(v, n, lane, 32));
 }
 
 // Merge of two ASCENDING runs a[0..na) and b[0..nb) (shared) into out[0..na+nb): each element's output position is its own
 // index plus the number of elements of the other run that precede it (binary search; ties: run a first).  This is
 // sort(cat(a, b)) (networks/render.py:70) when both inputs are sorted -- always true for the coarse depths, and true for
-// the importance samples whenever u is non-decreasing (the deterministic linspace).
-__device__ __forceinline__ void ray_merge_sorted(const float* a, int na, const float* b, int nb, float* out, int lane) {
-  for (int e = lane; e < na + nb; e += 32) {
+// the importance samples whenever u is non-decreasing (the deterministic linspace).  `nthr` threads share the elements.
+__device__ __forceinline__ void ray_merge_part(const float* a, int na, const float* b, int nb, float* out, int tid, int nthr) {
+  for (int e = tid; e < na + nb; e += nthr) {
     const bool from_a = e < na;
     const float v = from_a ? a[e] : b[e - na];
     const float* other = from_a ? b : a;
@@ -145,12 +158,15 @@ __device__ __forceinline__ void ray_merge_sorted(const float* a, int na, const f
     }
     out[(from_a ? e : e - na) + lo] = v;
   }
+}
+__device__ __forceinline__ void ray_merge_sorted(const float* a, int na, const float* b, int nb, float* out, int lane) {
+  ray_merge_part(a, na, b, nb, out, lane, 32);
   __syncwarp();
 }
 
 // Rank sort of vals[0..T) (shared) into out[0..T): ascending, ties by index (networks/render.py:70).
-__device__ __forceinline__ void ray_rank_sort(const float* vals, int T, float* out, int lane) {
-  for (int e = lane; e < T; e += 32) {
+__device__ __forceinline__ void ray_rank_part(const float* vals, int T, float* out, int tid, int nthr) {
+  for (int e = tid; e < T; e += nthr) {
     const float v = vals[e];
     int rank = 0;
     for (int j = 0; j < T; ++j) {
@@ -159,6 +175,9 @@ __device__ __forceinline__ void ray_rank_sort(const float* vals, int T, float* o
     }
     out[rank] = v;
   }
+}
+__device__ __forceinline__ void ray_rank_sort(const float* vals, int T, float* out, int lane) {
+  ray_rank_part(vals, T, out, lane, 32);
   __syncwarp();
 }
 
