@@ -343,8 +343,8 @@ def run_ours(args):
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": peak_src,
                 "note": "algorithmic FLOPs (2*693504 MACs per network evaluation, the reference's layer shapes); the kernel issues 3 bf16 "
-                        "tensor passes (hi/lo operand split for fp32 parity) over 565248 padded+folded MACs per sample, so "
-                        "frac cannot exceed 693504/(3*565248) = 0.409 of the bf16 peak",
+                        "tensor passes (hi/lo operand split for fp32 parity) over 563200 padded+folded MACs per sample, so "
+                        "frac cannot exceed 693504/(3*563200) = 0.410 of the bf16 peak",
                 "stage_ms_per_step": {k: float(v / args.steps) for k, v in
                                       zip(("coarse_z_or_fused_kernel", "coarse_mlp", "coarse_composite", "hier_sample", "fine_mlp",
                                            "fine_composite"), stage_ms)}}

@@ -5,17 +5,25 @@
 // ~2^-16 per product, measured ~1e-5 on outputs, inside the 1e-4 parity budget; single-pass bf16/tf32 is not).
 //
 // Data flow per tile (nothing 256-wide ever leaves the SM):
-//   * activations: three rotating 128-column "slots"; the bf16-hi half of a slot lives in tensor memory (A operand of the
-//     two TS passes: no shared-memory read), the bf16-lo half in shared memory as two K-major SWIZZLE_128B slabs (SS pass).
+//   * activations: two 128-column "slots" in TENSOR MEMORY, each holding one K-half of the current 256-wide activation as
+//     split bf16 (64 columns of hi halves + 64 of lo halves).  Every trunk MMA takes its A operand from tensor memory
+//     (TS form: no shared-memory read for A); with the two fp32 accumulators the 512 TMEM columns are exactly used.
+//     The position / direction embeddings (4 of the 73 K chunks of a tile) are shared-memory operands (SS form).
 //   * every 256-wide layer is executed as two N=128 half-steps with separate TMEM accumulators, so the epilogue of one
-//     half-step (TMEM -> registers -> bias/ReLU/split -> slot) overlaps the tensor work of the next.
+//     half-step (TMEM -> registers -> bias/ReLU/split -> slot) overlaps the tensor work of the next.  The even half-step of a
+//     layer overwrites slot 0 while the odd one still reads it: the odd half-step reads slot 0 first and releases it
+//     (a_free barrier).  Epilogue results are published per 64-column K chunk.
 //   * weights: packed once per weight update (dmnerf_set_weights) into the exact shared-memory image, streamed in
 //     16 KB stages through a ring with 1-D bulk async copies (TMA engine, mbarrier completion) from L2.
 //   * heads: rgb_feature_linear / ins_feature_linear have no activation, so they are folded into the following layer at
-//     pack time (W' = W2 W1, fp64 accumulate); density (N=1) is a CUDA-core dot product inside layer 7's epilogue.
+//     pack time (W' = W2 W1, fp64 accumulate); density (N=1) and the 3-wide rgb head are fp32 CUDA-core dot products inside
+//     the epilogues of layer 7 / the colour hidden layer; the instance head is an N=pad16 MMA.  19 half-steps per tile.
 //
-// Warp roles: warp 0 weight producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 prologue (points +
-// positional encoding) and epilogue.  All waits are bounded: a protocol bug raises an error code, never a hang.
+// Warp roles (640 threads): warp 0 weight producer, warp 1 MMA issuer (converged warp, one elected lane), warp 2 TMEM
+// allocator, warps 4-19 prologue (points + positional encoding, sliced into the idle time of the previous tile's
+// epilogues) and epilogue: 4 TMEM lane quadrants x 4 column groups, i.e. one row and 32 accumulator columns per thread.
+// All waits are bounded: a protocol bug raises an error code, never a hang.
+//
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -779,17 +787,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           // After a coarse tile of the fused kernel the next tile's depths do not exist yet: everybody waits for column
           // group 0 to composite this tile and draw the importance samples, then prepares the first fine tile in one piece
           // (the instance head of this tile is drained afterwards, off the critical path).
-          const bool late_next = FUSED && j == 0 && ti + 1 < my_tiles;
           if (cg != 0) {
             asm volatile("bar.arrive 4, 512;" ::: "memory");
             if (early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_D | PRO_DONE); KP_ADD(10); }
-            if (FUSED && j == 0) asm volatile("bar.sync 3, 512;" ::: "memory");     // fine depths are in shared memory
-            if (late_next) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
-            continue;
-          }
-          if (early_ok(ti + 1)) prologue(ti + 1, PRO_DONE);
-          asm volatile("bar.sync 4, 512;" ::: "memory");
-          if (cg == 0) {
+          } else {
+            if (early_ok(ti + 1)) prologue(ti + 1, PRO_DONE);
+            asm volatile("bar.sync 4, 512;" ::: "memory");
             // rgb_linear (dm_nerf.py:102,105) and density_linear (dm_nerf.py:101): add the four column groups' partial
             // dot products in a fixed order
             const float4 s0 = misc->part[0][r], s1 = misc->part[1][r], s2 = misc->part[2][r], s3 = misc->part[3][r];
@@ -841,7 +844,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 ac[0] = p0; ac[1] = p1; ac[2] = p2; ac[3] = p3; ac[4] = p4;
               }
             }
-          }
           if constexpr (FUSED) {
             if (j == 0) {
               // ---- hierarchical sampling (render.py:66-70) by this column group: 64 threads per ray, results stay in
@@ -868,9 +870,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               asm volatile("bar.sync 1, 128;" ::: "memory");
               if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
                 for (int k = t64; k < FF; k += 64) a.zf_out[ray * FF + k] = fz->zf[rr][k];
-              asm volatile("bar.sync 3, 512;" ::: "memory");          // fine depths visible to every prologue thread
-              if (late_next) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
             }
+          }
+          }
+          if (FUSED && j == 0) {
+            asm volatile("bar.sync 3, 512;" ::: "memory");            // fine depths visible to every prologue thread
+            if (ti + 1 < my_tiles) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
           }
           continue;
         }

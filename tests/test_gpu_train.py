@@ -144,3 +144,62 @@ def test_dropin_training_loop_runs_and_rebinds_updated_weights():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]            # Adam on a fixed batch must make progress => the re-bound weights are live
+
+
+@pytest.mark.parametrize("m", [300, 128 * 5])
+def test_tensor_core_training_forward_saves_the_reference_activations(m):
+    """dmnerf_mlp_forward_train(impl=UMMA, rays mode): the planes kept for the backward -- the embedded inputs produced by the
+    kernel's own branch-free sin/cos (dm_nerf.py:37-38), H0..H7 (dm_nerf.py:84-87) and the two hidden head activations
+    (dm_nerf.py:93,99) -- against the oracle on the same rays; a ragged last tile included."""
+    from dmnerf_b200.engine import get_context
+    wl = synth.workload("dmsr_study")
+    w = synth.make_weights(11, 13)
+    net = model_from_weights(w, DEV)
+    ctx = get_context(torch.device(DEV))
+    lib = ctx.lib
+    S = 4
+    n = (m + S - 1) // S
+    m = n * S
+    sel = np.linspace(0, 307199, n).astype(np.int64)
+    ro, rd = cu(wl["rays_o"][sel]), cu(wl["rays_d"][sel])
+    z = (torch.rand(n, S, generator=torch.Generator().manual_seed(5)).sort(-1).values * 11 + 4).to(DEV).contiguous()
+    assert ctx.bind(0, net) == 13
+    apf = lib.dmnerf_act_floats_per_sample()
+    raw = torch.empty(m, 18, device=DEV)
+    acts = torch.zeros(m * apf, device=DEV)
+    _lib.check(lib.dmnerf_mlp_forward_train(ctx.handle, 0, None, _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(z), m, S, _lib.ptr(raw),
+                                            _lib.ptr(acts), _lib.IMPL_UMMA, ctx.stream()), "dmnerf_mlp_forward_train")
+    ctx.sync_check()
+    acts = acts.cpu().numpy()
+    off = 0
+    planes = {}
+    for name, width in [("h%d" % l, 256) for l in range(8)] + [("rgb_feat", 256), ("ins_feat", 256), ("rgb_hid", 128),
+                                                              ("ins_hid", 128), ("emb", 90)]:
+        planes[name] = acts[off:off + m * width].reshape(m, width)
+        off += m * width
+    # oracle on the CPU
+    p = O.to_torch(w)
+    pts = (torch.from_numpy(wl["rays_o"][sel])[:, None, :] + torch.from_numpy(wl["rays_d"][sel])[:, None, :] * z.cpu()[..., None])
+    vd = torch.from_numpy(wl["rays_d"][sel])
+    vd = (vd / vd.norm(dim=-1, keepdim=True))[:, None, :].expand(n, S, 3)
+    x = torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1).reshape(m, 90)
+    emb = planes["emb"]
+    # |sin|,|cos| <= 1: the periodic terms must agree to ~2 ulp of 1 (arguments reach 2^9 * |x| ~ 5e3)
+    assert np.abs(emb[:, 3:63] - x.numpy()[:, 3:63]).max() <= 1e-6
+    assert np.abs(emb[:, 66:] - x.numpy()[:, 66:]).max() <= 1e-6
+    np.testing.assert_allclose(emb[:, :3], x.numpy()[:, :3], rtol=0, atol=1e-6)
+    h = x[:, :63]
+    for i in range(8):
+        h = torch.relu(torch.nn.functional.linear(h, p["mlps.%d.weight" % i], p["mlps.%d.bias" % i]))
+        assert scale_err(planes["h%d" % i], h.numpy()) <= 1e-4, i
+        if i == 4:
+            h = torch.cat([h, x[:, :63]], -1)
+    rf = torch.nn.functional.linear(h, p["rgb_feature_linear.weight"], p["rgb_feature_linear.bias"])
+    rh = torch.relu(torch.nn.functional.linear(torch.cat([rf, x[:, 63:]], -1), p["rgb_feature_linears.0.weight"],
+                                               p["rgb_feature_linears.0.bias"]))
+    inf = torch.nn.functional.linear(h, p["ins_feature_linear.weight"], p["ins_feature_linear.bias"])
+    ih = torch.relu(torch.nn.functional.linear(inf, p["ins_feature_linears.0.weight"], p["ins_feature_linears.0.bias"]))
+    assert scale_err(planes["rgb_hid"], rh.numpy()) <= 1e-4
+    assert scale_err(planes["ins_hid"], ih.numpy()) <= 1e-4
+    out = O.mlp_forward(p, x).numpy()
+    assert scale_err(raw.cpu().numpy(), out) <= 1e-4
