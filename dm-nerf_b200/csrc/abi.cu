@@ -298,7 +298,7 @@ DMNERF_API int dmnerf_sync_check(dmnerf_ctx* ctx, void* stream) {
     int rc = umma_check_status(ctx->packed[i], (cudaStream_t)stream);
     if (rc) return rc;
   }
-  return 0;
+  return gemm_tc_check_status((cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_profile_enable(dmnerf_ctx* ctx, int enable) {

@@ -8,6 +8,9 @@
 //       db += column sums of dY     -> colsum_kernel
 //     with the reference's gradient routing (dm_nerf.py:95: the instance branch reads h.detach(), so it contributes to
 //     ins_feature_linear and below only).
+#include <cstdlib>
+#include <cstring>
+
 #include "ray_ops.cuh"
 
 namespace dmnerf {
@@ -361,8 +364,20 @@ __global__ void __launch_bounds__(256) gemm_tn_big_kernel(const float* __restric
   }
 }
 
+// DMNERF_BWD_IMPL=simt keeps every backward GEMM on the fp32 CUDA-core kernels (cross-check / A-B timing).
+static bool bwd_use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DMNERF_BWD_IMPL");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, int accumulate,
                    const float* mask, cudaStream_t st) {
+  if (bwd_use_tc() && M >= 512 && gemm_nn_tc_supported(N, K, ldc, C, mask))
+    return launch_gemm_nn_tc(A, lda, B, ldb, C, ldc, M, N, accumulate, mask, nullptr, 0, st);
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0) &&
                        (!mask || (uintptr_t)mask % 16 == 0);
   if (aligned && N % BK == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && N >= 64 && K >= 64) {
@@ -423,13 +438,24 @@ __global__ void __launch_bounds__(256) gemm_nt_bias_kernel(const float* __restri
 
 static int gemm_nt_bias(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int64_t M, int N,
                         int K, cudaStream_t st) {
+  if (bwd_use_tc() && M >= 512 && N == 256 && K == 256 && ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && (uintptr_t)bias % 16 == 0)
+    return launch_gemm_nn_tc(A, lda, W, ldw, C, ldc, M, K, 0, nullptr, bias, 1, st);
   dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT));
   gemm_nt_bias_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
   DMN_LAUNCH_OK();
   return 0;
 }
 
-static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st) {
+static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStream_t st);
+
+// colsum_out != NULL: also colsum_out[n] += sum_m A[m, n] (the bias gradient of the same layer, zero-initialised by the caller).
+static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st,
+                   float* colsum_out = nullptr) {
+  if (bwd_use_tc() && M >= 512 && gemm_tn_tc_supported(N, K)) return launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, colsum_out, M, N, st);
+  if (colsum_out) {
+    int rc = colsum(A, lda, colsum_out, M, N, st);
+    if (rc) return rc;
+  }
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
   if (aligned && N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && N >= 64 && K >= 64) {
     const int tiles_b = ((N + BT - 1) / BT) * ((K + BT - 1) / BT);
@@ -502,15 +528,14 @@ int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int
   R(gemm_nn(d_rgb, C, p.w[L_RGB_OUT], 128, S1, 128, m, 3, 128, 0, ap.rgb_hid, st));       // through ReLU of rgb_hid
   R(gemm_nn(d_ins, C, p.w[L_INS_OUT], 128, S2, 128, m, ins1, 128, 0, ap.ins_hid, st));    // through ReLU of ins_hid
   // ---- hidden head layers (dm_nerf.py:90-99)
-  R(gemm_tn(S1, 128, ap.rgb_feat, 256, gw(L_RGB_HID), 283, m, 128, 256, st));
+  R(gemm_tn(S1, 128, ap.rgb_feat, 256, gw(L_RGB_HID), 283, m, 128, 256, st, gb(L_RGB_HID)));      // + bias gradient
   R(gemm_tn(S1, 128, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));
-  R(colsum(S1, 128, gb(L_RGB_HID), m, 128, st));
-  R(gemm_tn(S2, 128, ap.ins_feat, 256, gw(L_INS_HID), 256, m, 128, 256, st));   R(colsum(S2, 128, gb(L_INS_HID), m, 128, st));
+  R(gemm_tn(S2, 128, ap.ins_feat, 256, gw(L_INS_HID), 256, m, 128, 256, st, gb(L_INS_HID)));      // + bias gradient
   R(gemm_nn(S1, 128, p.w[L_RGB_HID], 283, S3, 256, m, 128, 256, 0, nullptr, st));         // d rgb_feature (no activation)
   R(gemm_nn(S2, 128, p.w[L_INS_HID], 256, S4, 256, m, 128, 256, 0, nullptr, st));         // d ins_feature
   // ---- feature layers on the final trunk activation (dm_nerf.py:89,95-96)
-  R(gemm_tn(S3, 256, ap.h[7], 256, gw(L_RGB_FEAT), 256, m, 256, 256, st));      R(colsum(S3, 256, gb(L_RGB_FEAT), m, 256, st));
-  R(gemm_tn(S4, 256, ap.h[7], 256, gw(L_INS_FEAT), 256, m, 256, 256, st));      R(colsum(S4, 256, gb(L_INS_FEAT), m, 256, st));
+  R(gemm_tn(S3, 256, ap.h[7], 256, gw(L_RGB_FEAT), 256, m, 256, 256, st, gb(L_RGB_FEAT)));
+  R(gemm_tn(S4, 256, ap.h[7], 256, gw(L_INS_FEAT), 256, m, 256, 256, st, gb(L_INS_FEAT)));
   // d h8 = d sigma (x) w_density + d rgb_feat W_rgb_feat   (the instance branch saw h.detach()), then ReLU mask of layer 7
   R(gemm_nn(d_sig, C, p.w[L_DENSITY], 256, G, 256, m, 1, 256, 0, nullptr, st));
   R(gemm_nn(S3, 256, p.w[L_RGB_FEAT], 256, G, 256, m, 256, 256, 1, ap.h[7], st));
@@ -521,11 +546,11 @@ int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int
     const int kin = layer_in(l);
     if (l == 0) {
       R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st));
+      R(colsum(cur, 256, gb(0), m, 256, st));
     } else {
-      R(gemm_tn(cur, 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st));
+      R(gemm_tn(cur, 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));             // dW and db of layer l
       if (l == 5) R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));   // skip input [h, pts]
     }
-    R(colsum(cur, 256, gb(l), m, 256, st));
     if (l > 0) {
       R(gemm_nn(cur, 256, p.w[l], kin, nxt, 256, m, 256, 256, 0, ap.h[l - 1], st));
       float* t = cur; cur = nxt; nxt = t;

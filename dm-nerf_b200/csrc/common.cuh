@@ -115,4 +115,13 @@ int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int
                         float* scratch, int feats_missing, cudaStream_t st);
 size_t mlp_backward_scratch_floats(int64_t m);
 
+// Tensor-core GEMMs of the backward (gemm_umma.cu): split-bf16 three-pass tcgen05 kernels for the wide layer shapes.
+bool gemm_nn_tc_supported(int N, int K, int ldc, const float* C, const float* mask);
+bool gemm_tn_tc_supported(int N, int K);
+int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
+                      const float* mask, const float* bias, int w_kmajor, cudaStream_t st);
+int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N,
+                      cudaStream_t st);
+int gemm_tc_check_status(cudaStream_t st);
+
 }  // namespace dmnerf

@@ -1,0 +1,446 @@
+// tcgen05 (UMMA) GEMM kernels for the training backward of the DM_NeRF network (networks/dm_nerf.py:80-106 differentiated,
+// driven by train_dmsr.py:62-64): the two wide GEMM shapes of every layer,
+//
+//   gemm_nn:  dX[M, 256]  (+)= dY[M, N] * W[N, 256]            (N = 128 or 256; optional ReLU mask from the saved activation)
+//   gemm_tn:  dW[NA, 256]  +=  dY[M, NA]^T * X[M, 256]          (NA = 128 or 256; contraction over the M samples)
+//
+// with the same fp32-grade arithmetic as the forward kernel: every fp32 operand is split into bf16 hi + bf16 lo and each
+// product is issued as three tensor passes  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  into fp32 accumulators in tensor memory.
+//
+// Operands come straight from the row-major fp32 matrices in global memory; the only preparation is the hi/lo split, done by
+// the CUDA cores while the block is written into shared memory.  One loader serves every operand, because the memory image
+// of a [rows][64 columns] block in the SWIZZLE_128B layout is the same whether the tensor core reads it K-major (rows = M or
+// N index, columns = contraction index: dY in gemm_nn) or MN-major (rows = contraction index, columns = M / N index: W in
+// gemm_nn, dY and X in gemm_tn) -- only the descriptor differs: MN-major operands set the a/b "major" bits of the instruction
+// descriptor, their leading byte offset is the stride between 64-column blocks, their stride byte offset the 1024 B between
+// 8-row groups, and a K = 16 step advances the start address by two such groups (validated on hardware by
+// tools/umma_probe.cu, modes 7 / 8 -> profiles/r01_umma_probe.txt).
+//
+// Structure (both kernels): 512 threads, persistent CTAs.  All 16 warps split the stage they fetched into registers one or two
+// stages earlier and store it (2-3 stages of shared memory), issue the global loads of a later stage, the block synchronises,
+// and one elected lane of warp 0 issues the stage's 12 MMAs and commits them to the stage's mbarrier; loads, splits and tensor
+// work of neighbouring stages overlap.  gemm_nn drains its [128 x 256] accumulator after every
+// 128-row tile (bias-free epilogue: optional accumulate, ReLU mask, fp32 store); gemm_tn keeps the whole [NA x 256] gradient
+// in tensor memory for the CTA's share of the samples and adds it to global memory once at the end (fp32 atomics).
+#include <cstring>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace dmnerf {
+namespace tg {
+
+using namespace umma;
+
+constexpr int NT = 512;                    // threads per CTA: 16 warps load + split; one elected lane of warp 0 issues
+constexpr int NOUT = 256;                  // output columns (gemm_nn) / columns of X (gemm_tn)
+
+// SWIZZLE_128B shared-memory descriptor with explicit leading / stride byte offsets.
+__device__ __forceinline__ uint64_t sdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t A_MN = 1u << 15, B_MN = 1u << 16;      // instruction-descriptor bits: operand is MN-major
+
+// One 16-byte unit of a bf16 slab = 8 consecutive fp32 values of one matrix row.  Loads are issued one or two stages ahead
+// of their use (register prefetch): with a single thread of control per stage the DRAM latency would otherwise sit on the
+// critical path of every stage.
+struct Unit { float v[8]; };
+
+// 8 floats of row r (valid below r_end), columns col.. (valid below c_end) of a row-major matrix; zero outside.
+__device__ __forceinline__ void load_unit(Unit& u, const float* __restrict__ src, int64_t ld, int64_t r, int64_t r_end, int col,
+                                          int c_end, bool vec_ok) {
+  if (r < r_end && vec_ok && col + 8 <= c_end) {
+    const float4* p4 = reinterpret_cast<const float4*>(src + r * ld + col);
+    const float4 x = __ldg(p4), y = __ldg(p4 + 1);
+    u.v[0] = x.x; u.v[1] = x.y; u.v[2] = x.z; u.v[3] = x.w; u.v[4] = y.x; u.v[5] = y.y; u.v[6] = y.z; u.v[7] = y.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u.v[i] = (r < r_end && col + i < c_end) ? __ldg(src + r * ld + col + i) : 0.0f;
+  }
+}
+
+// Split the unit into bf16 hi / lo and store it at (row, 16-byte unit cu) of the two swizzled slabs.
+__device__ __forceinline__ void store_unit(const Unit& u, uint8_t* hi, uint8_t* lo, int row, int cu) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_bf16x2(u.v[2 * i], u.v[2 * i + 1], h[i], l[i]);
+  const uint32_t o = sw128_offset(row, cu * 8);
+  *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void fail(int32_t* status, int code) { atomicCAS(status, 0, code); }
+
+// ------------------------------------------------------------------------------------------------ gemm_nn / gemm_nt
+// W_KMAJOR = false:  C[M, 256] (+)= A[M, N] * W[N, 256]                (dX = dY W; W rows are the contraction index)
+// W_KMAJOR = true:   C[M, 256]   =  A[M, N] * W[256, N]^T + bias       (y = x W^T + b: rebuilds the feature planes)
+// N = 64 * NCH.
+constexpr uint32_t NN_A_BYTES = 128 * 128;               // one [128 x 64] slab
+constexpr uint32_t NN_W_BYTES = 256 * 128;               // the W block of a chunk: 4 slabs [64 x 64] or one slab [256 x 64]
+constexpr uint32_t NN_W_SLAB = 64 * 128;
+constexpr uint32_t NN_STAGE = 2 * NN_A_BYTES + 2 * NN_W_BYTES;          // A hi, A lo, W hi, W lo = 96 KB
+constexpr uint32_t NN_SMEM = 2 * NN_STAGE + 1024;
+constexpr int NN_UA = 128 * 8 / NT, NN_UW = 256 * 8 / NT;               // units per thread: 2 of A, 4 of W
+
+template <int NCH, bool W_KMAJOR>
+__global__ void __launch_bounds__(NT, 1) gemm_nn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                           float* __restrict__ C, int ldc, int64_t M, int accumulate,
+                                                           const float* __restrict__ mask, const float* __restrict__ bias, int vec_a,
+                                                           int vec_w, int32_t* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t done[2], acc_done;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tD = tmem_base_s;
+  const uint32_t idesc = make_idesc_bf16(128, NOUT) | (W_KMAJOR ? 0u : B_MN);
+  const int64_t n_tiles = (M + 127) / 128;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_chunks = my_tiles * NCH;
+  // chunk q of this CTA: tile blockIdx.x + (q / NCH) * gridDim.x, contraction columns [64 (q % NCH), +64)
+  Unit ra[NN_UA], rw[NN_UW];
+  auto issue = [&](int64_t q) {
+    const int c = (int)(q % NCH);
+    const int64_t m0 = (blockIdx.x + (q / NCH) * gridDim.x) * 128;
+#pragma unroll
+    for (int i = 0; i < NN_UA; ++i) {
+      const int u = tid + i * NT;
+      load_unit(ra[i], A, lda, m0 + (u >> 3), M, 64 * c + (u & 7) * 8, 64 * NCH, vec_a != 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NN_UW; ++i) {
+      const int u = tid + i * NT;
+      if (W_KMAJOR) load_unit(rw[i], W, ldw, u >> 3, NOUT, 64 * c + (u & 7) * 8, 64 * NCH, vec_w != 0);       // row = output column
+      else load_unit(rw[i], W, ldw, 64 * c + ((u >> 3) & 63), 64 * NCH, 64 * (u >> 9) + (u & 7) * 8, NOUT, vec_w != 0);
+    }
+  };
+  if (n_chunks > 0) issue(0);
+  uint32_t tile_i = 0;
+  for (int64_t q = 0; q < n_chunks; ++q) {
+    const int c = (int)(q % NCH);
+    const uint32_t s = (uint32_t)q & 1;
+    uint8_t* st = smem + s * NN_STAGE;
+    uint8_t *a_hi = st, *a_lo = st + NN_A_BYTES, *w_hi = st + 2 * NN_A_BYTES, *w_lo = w_hi + NN_W_BYTES;
+    if (q >= 2 && !mbar_wait(&done[s], (uint32_t)((q >> 1) - 1) & 1)) fail(status, 601);      // the MMAs that read this stage are done
+#pragma unroll
+    for (int i = 0; i < NN_UA; ++i) {
+      const int u = tid + i * NT;
+      store_unit(ra[i], a_hi, a_lo, u >> 3, u & 7);
+    }
+#pragma unroll
+    for (int i = 0; i < NN_UW; ++i) {
+      const int u = tid + i * NT;
+      if (W_KMAJOR) store_unit(rw[i], w_hi, w_lo, u >> 3, u & 7);
+      else store_unit(rw[i], w_hi + (u >> 9) * NN_W_SLAB, w_lo + (u >> 9) * NN_W_SLAB, (u >> 3) & 63, u & 7);
+    }
+    if (q + 1 < n_chunks) issue(q + 1);                  // in flight while this stage is multiplied
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t da_hi = sdesc(sa_hi + ks * 32, 16, 1024), da_lo = sdesc(sa_lo + ks * 32, 16, 1024);
+          const uint64_t db_hi = W_KMAJOR ? sdesc(sw_hi + ks * 32, 16, 1024) : sdesc(sw_hi + ks * 2048, NN_W_SLAB, 1024);
+          const uint64_t db_lo = W_KMAJOR ? sdesc(sw_lo + ks * 32, 16, 1024) : sdesc(sw_lo + ks * 2048, NN_W_SLAB, 1024);
+          mma_ss(tD, da_hi, db_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+          mma_ss(tD, da_lo, db_hi, idesc, 1u);
+          mma_ss(tD, da_hi, db_lo, idesc, 1u);
+        }
+        mma_commit(&done[s]);
+        if (c == NCH - 1) mma_commit(&acc_done);
+      }
+      __syncwarp();
+    }
+    if (c != NCH - 1) continue;
+    // ---- epilogue of the tile: warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
+    if (!mbar_wait(&acc_done, tile_i & 1)) fail(status, 602);
+    ++tile_i;
+    tc_fence_after();
+    {
+      const int64_t m = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
+      const int col0 = (warp >> 2) * 64;
+      const uint32_t taddr = tD + ((uint32_t)((warp & 3) * 32) << 16) + col0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (m < M) {
+          float* crow = C + m * ldc + col0 + c0;
+          const float* mrow = mask ? mask + m * ldc + col0 + c0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c0 + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (mrow) {
+              const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
+              if (!(mk.x > 0.0f)) o.x = 0.0f;
+              if (!(mk.y > 0.0f)) o.y = 0.0f;
+              if (!(mk.z > 0.0f)) o.z = 0.0f;
+              if (!(mk.w > 0.0f)) o.w = 0.0f;
+            }
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                    // the accumulator is drained before the next tile overwrites it
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tD, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ gemm_tn
+// C[NA, 256] += A[mb:me, NA]^T * B[mb:me, 256] for this CTA's rows; 32 samples per stage, 3 stages in flight, loads issued two
+// stages ahead.  colsum != NULL: colsum[n] += sum over the rows of A[:, n] (the bias gradient, from the registers that
+// already hold A).
+constexpr uint32_t TN_SLAB = 32 * 128;                   // one [32 x 64] slab
+constexpr int TN_STAGES = 3;
+
+template <int NA>
+__global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                           float* __restrict__ C, int ldc, float* __restrict__ colsum, int64_t M,
+                                                           int64_t rows_per_cta, int vec_a, int vec_b, int32_t* status) {
+  constexpr int SA = NA / 64, SB = NOUT / 64;            // slabs per operand
+  constexpr uint32_t STAGE = 2 * (SA + SB) * TN_SLAB;   // hi + lo
+  constexpr int NH = NA / 128;                           // accumulators of 128 gradient rows
+  constexpr int UPT = (SA + SB) * 256 / NT;              // units per thread per stage (4 or 3); unit U = tid + i * NT
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t done[TN_STAGES], acc_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float csum_s[NA];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < TN_STAGES; ++i) mbar_init(&done[i], 1);
+    mbar_init(&acc_done, 1);
+    fence_barrier_init();
+  }
+  if (tid < NA) csum_s[tid] = 0.0f;
+  if (warp == 0) tmem_alloc(&tmem_base_s, NH * 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tD = tmem_base_s;
+  const uint32_t idesc = make_idesc_bf16(128, NOUT) | A_MN | B_MN;
+  const int64_t mb = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t me = (mb + rows_per_cta < M) ? mb + rows_per_cta : M;
+  const int64_t n_chunks = (me > mb) ? (me - mb + 31) / 32 : 0;
+  float csum[UPT][8];
+#pragma unroll
+  for (int i = 0; i < UPT; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[i][j] = 0.0f;
+  auto issue = [&](Unit (&r)[UPT], int64_t q) {
+    const int64_t m0 = mb + q * 32;
+#pragma unroll
+    for (int i = 0; i < UPT; ++i) {
+      const int U = tid + i * NT, slab = U >> 8, u = U & 255;
+      if (slab < SA) load_unit(r[i], A, lda, m0 + (u >> 3), me, 64 * slab + (u & 7) * 8, NA, vec_a != 0);
+      else load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, NOUT, vec_b != 0);
+    }
+  };
+  auto stage = [&](Unit (&r)[UPT], int64_t q) {            // store chunk q from registers, prefetch chunk q + 2, multiply
+    const uint32_t s = (uint32_t)(q % TN_STAGES);
+    uint8_t* st = smem + s * STAGE;
+    uint8_t *a_hi = st, *a_lo = st + SA * TN_SLAB, *b_hi = st + 2 * SA * TN_SLAB, *b_lo = b_hi + SB * TN_SLAB;
+    if (q >= TN_STAGES && !mbar_wait(&done[s], (uint32_t)(q / TN_STAGES - 1) & 1)) fail(status, 611);
+#pragma unroll
+    for (int i = 0; i < UPT; ++i) {
+      const int U = tid + i * NT, slab = U >> 8, u = U & 255;
+      if (slab < SA) {
+        store_unit(r[i], a_hi + slab * TN_SLAB, a_lo + slab * TN_SLAB, u >> 3, u & 7);
+        if (colsum) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) csum[i][j] += r[i].v[j];
+        }
+      } else {
+        store_unit(r[i], b_hi + (slab - SA) * TN_SLAB, b_lo + (slab - SA) * TN_SLAB, u >> 3, u & 7);
+      }
+    }
+    if (q + 2 < n_chunks) issue(r, q + 2);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da_hi = sdesc(sa_hi + h * 2 * TN_SLAB + ks * 2048, TN_SLAB, 1024);
+            const uint64_t da_lo = sdesc(sa_lo + h * 2 * TN_SLAB + ks * 2048, TN_SLAB, 1024);
+            const uint64_t db_hi = sdesc(sb_hi + ks * 2048, TN_SLAB, 1024), db_lo = sdesc(sb_lo + ks * 2048, TN_SLAB, 1024);
+            const uint32_t d = tD + h * 256;
+            mma_ss(d, da_hi, db_hi, idesc, (q == 0 && ks == 0) ? 0u : 1u);
+            mma_ss(d, da_lo, db_hi, idesc, 1u);
+            mma_ss(d, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        mma_commit(&done[s]);
+      }
+      __syncwarp();
+    }
+  };
+  Unit r0[UPT], r1[UPT];
+  if (n_chunks > 0) issue(r0, 0);
+  if (n_chunks > 1) issue(r1, 1);
+  for (int64_t q = 0; q < n_chunks; q += 2) {
+    stage(r0, q);
+    if (q + 1 < n_chunks) stage(r1, q + 1);
+  }
+  if (n_chunks > 0) {
+    if (warp == 0) {
+      if (elect_one()) mma_commit(&acc_done);
+      __syncwarp();
+    }
+    if (colsum) {       // bias gradient: per-thread partial sums -> shared memory -> one global atomic per column and CTA
+#pragma unroll
+      for (int i = 0; i < UPT; ++i) {
+        const int U = tid + i * NT, slab = U >> 8, u = U & 255;
+        if (slab < SA) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(&csum_s[64 * slab + (u & 7) * 8 + j], csum[i][j]);
+        }
+      }
+      __syncthreads();
+      if (tid < NA) atomicAdd(colsum + tid, csum_s[tid]);
+    }
+    if (!mbar_wait(&acc_done, 0)) fail(status, 612);
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const int n = h * 128 + (warp & 3) * 32 + lane;                     // gradient row
+      const int col0 = (warp >> 2) * 64;
+      const uint32_t taddr = tD + h * 256 + ((uint32_t)((warp & 3) * 32) << 16) + col0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_wait();
+        float* crow = C + (int64_t)n * ldc + col0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(crow + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tD, NH * 256);
+}
+
+static int32_t* g_status = nullptr;       // device error word shared by the GEMM launches of this process
+
+static int ensure_status() {
+  if (!g_status) {
+    DMN_CUDA(cudaMalloc((void**)&g_status, sizeof(int32_t)));
+    DMN_CUDA(cudaMemset(g_status, 0, sizeof(int32_t)));
+  }
+  return 0;
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+static bool vec4_ok(const void* p, int ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
+
+}  // namespace tg
+
+// Shapes the tensor-core kernels are specialised for (everything else stays on the fp32 CUDA-core kernels of backward.cu).
+bool gemm_nn_tc_supported(int N, int K, int ldc, const float* C, const float* mask) {
+  return (N == 128 || N == 256) && K == 256 && ldc % 4 == 0 && ((uintptr_t)C % 16 == 0) && (!mask || (uintptr_t)mask % 16 == 0);
+}
+bool gemm_tn_tc_supported(int N, int K) { return (N == 128 || N == 256) && K == 256; }
+
+// w_kmajor == 0: C[M,256] (+)= A[M,N] W[N,256] (mask optional);  w_kmajor != 0: C[M,256] = A[M,N] W[256,N]^T + bias.
+int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
+                      const float* mask, const float* bias, int w_kmajor, cudaStream_t st) {
+  using namespace tg;
+  if (M <= 0) return 0;
+  if (ensure_status()) return 1;
+  static bool attr = false;
+  if (!attr) {
+    DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
+    attr = true;
+  }
+  DMN_CHECK(!w_kmajor || N == 256, "gemm_nt(tc): contraction width %d not supported", N);
+  DMN_CHECK(!bias || (uintptr_t)bias % 16 == 0, "gemm(tc): bias must be 16-byte aligned");
+  const int64_t tiles = (M + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  const int va = vec4_ok(A, lda), vw = vec4_ok(W, ldw);
+  if (w_kmajor) gemm_nn_tc_kernel<4, true><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
+  else if (N == 128) gemm_nn_tc_kernel<2, false><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
+  else gemm_nn_tc_kernel<4, false><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N,
+                      cudaStream_t st) {
+  using namespace tg;
+  if (M <= 0) return 0;
+  if (ensure_status()) return 1;
+  constexpr uint32_t SMEM128 = TN_STAGES * 2 * (2 + 4) * TN_SLAB + 1024, SMEM256 = TN_STAGES * 2 * (4 + 4) * TN_SLAB + 1024;
+  static bool attr = false;
+  if (!attr) {
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM128));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM256));
+    attr = true;
+  }
+  int64_t rows = (M + sm_count() - 1) / sm_count();
+  rows = ((rows + 31) / 32) * 32;
+  const unsigned grid = (unsigned)((M + rows - 1) / rows);
+  const int va = vec4_ok(A, lda), vb = vec4_ok(B, ldb);
+  if (N == 128) gemm_tn_tc_kernel<128><<<grid, NT, SMEM128, st>>>(A, lda, B, ldb, C, ldc, colsum, M, rows, va, vb, g_status);
+  else gemm_tn_tc_kernel<256><<<grid, NT, SMEM256, st>>>(A, lda, B, ldb, C, ldc, colsum, M, rows, va, vb, g_status);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+// Asynchronous failure word of the GEMM kernels (0 = fine); checked by dmnerf_sync_check.
+int gemm_tc_check_status(cudaStream_t st) {
+  if (!tg::g_status) return 0;
+  int32_t h = 0;
+  DMN_CUDA(cudaMemcpyAsync(&h, tg::g_status, sizeof(h), cudaMemcpyDeviceToHost, st));
+  DMN_CUDA(cudaStreamSynchronize(st));
+  DMN_CHECK(h == 0, "tensor-core backward GEMM: barrier protocol failure (code %d)", h);
+  return 0;
+}
+
+}  // namespace dmnerf

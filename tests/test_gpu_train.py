@@ -203,3 +203,31 @@ def test_tensor_core_training_forward_saves_the_reference_activations(m):
     assert scale_err(planes["ins_hid"], ih.numpy()) <= 1e-4
     out = O.mlp_forward(p, x).numpy()
     assert scale_err(raw.cpu().numpy(), out) <= 1e-4
+
+
+@pytest.mark.parametrize("ins_num", [13, 59])
+def test_mlp_backward_tensor_core_gemms(ins_num):
+    """Batches of >= 512 samples run the layer GEMMs of the backward (dX = dY W, dW = dY^T X) on the tcgen05 split-bf16
+    kernels (gemm_umma.cu); with the exact-fp32 forward the 30 parameter gradients must still agree with torch autograd on the
+    oracle to fp32 noise.  1333 samples: ten full 128-row tiles + a ragged one, 32-sample stages with a ragged tail."""
+    m = 1333
+    w = synth.make_weights(21, ins_num)
+    p = O.to_torch(w)
+    for v in p.values():
+        v.requires_grad_(True)
+    gen = torch.Generator().manual_seed(9)
+    pts = torch.rand(m, 3, generator=gen) * 6 - 3
+    vd = torch.randn(m, 3, generator=gen)
+    vd = vd / vd.norm(dim=-1, keepdim=True)
+    x = torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1)
+    G = torch.randn(m, 4 + ins_num + 1, generator=gen)
+    (O.mlp_forward(p, x) * G).sum().backward()
+    net = model_from_weights(w, DEV).train()
+    y = net(x.to(DEV), impl=_lib.IMPL_SIMT)
+    (y * G.to(DEV)).sum().backward()
+    from dmnerf_b200.engine import get_context
+    get_context(torch.device(DEV)).sync_check()
+    for k, prm in net.named_parameters():
+        ref = p[k].grad.numpy()
+        got = prm.grad.cpu().numpy()
+        assert scale_err(got, ref) <= 2e-4 and rel_l2(got, ref) <= 1e-4, (k, scale_err(got, ref), rel_l2(got, ref))

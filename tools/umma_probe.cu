@@ -36,6 +36,17 @@ struct Params {
   int* status;         // 0 ok, else failure code
 };
 
+// Generic SWIZZLE_128B descriptor with explicit leading / stride byte offsets (MN-major experiments, modes 7 / 8).
+__device__ __forceinline__ uint64_t make_sdesc_generic(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_mma, bar_load;
@@ -63,7 +74,19 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
   // ---- stage A: row = tid
-  {
+  if (p.mode >= 7) {
+    // MN-major operands: shared-memory rows are K indices, 64 consecutive M (or N) elements per 128-byte row, one slab of K
+    // rows per group of 64 M / N elements.
+    for (int k = 0; k < K; ++k) {
+      __nv_bfloat16 h = __float2bfloat16_rn(p.A[(size_t)tid * K + k]);
+      *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)(tid >> 6) * K * 128 + sw128_offset(k, tid & 63)) = h;
+    }
+    for (int n = tid; n < N; n += 128)
+      for (int k = 0; k < K; ++k) {
+        __nv_bfloat16 h = __float2bfloat16_rn(p.B[(size_t)n * K + k]);
+        *reinterpret_cast<__nv_bfloat16*>(sBhi + (size_t)(n >> 6) * K * 128 + sw128_offset(k, n & 63)) = h;
+      }
+  } else {
     const float* arow = p.A + (size_t)tid * K;
     for (int k0 = 0; k0 < K; k0 += 16) {
       uint32_t hi[8], lo[8];
@@ -79,7 +102,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
     }
   }
   // ---- stage B
-  if (p.mode == 3) {
+  if (p.mode >= 7) {
+  } else if (p.mode == 3) {
     if (tid == 0) {
       mbar_arrive_expect_tx(&bar_load, (uint32_t)(KS * N * 128));
       for (int s = 0; s < KS; ++s)
@@ -103,7 +127,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   tc_fence_before();
   __syncthreads();
 
-  const uint32_t idesc = make_idesc_bf16(128, N);
+  const uint32_t idesc = make_idesc_bf16(128, N) | (p.mode >= 7 ? ((1u << 15) | (1u << 16)) : 0u);
   long long t0 = 0, t1 = 0;
   if (warp == 0) {                                   // converged warp, one elected lane issues (uniform-register operands)
     bool ok = true;
@@ -112,7 +136,16 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
     tc_fence_after();
     t0 = clock64();
     if (elect_one()) {
-    if (p.mode == 5 || p.mode == 6) {
+    if (p.mode >= 7) {
+      const uint32_t slab = (uint32_t)K * 128u;                    // bytes between groups of 64 M / N elements
+      for (int rep = 0; rep < p.reps; ++rep)
+        for (int k0 = 0; k0 < K; k0 += 16) {
+          const uint32_t lbo = (p.mode == 7) ? slab : 1024u, sbo = (p.mode == 7) ? 1024u : slab;
+          const uint64_t da = make_sdesc_generic(smem_u32(sA) + (k0 >> 3) * 1024, lbo, sbo);
+          const uint64_t db = make_sdesc_generic(smem_u32(sBhi) + (k0 >> 3) * 1024, lbo, sbo);
+          mma_ss(tD, da, db, idesc, (rep > 0 || k0 > 0) ? 1u : 0u);
+        }
+    } else if (p.mode == 5 || p.mode == 6) {
       // raw tensor-pipe rate: 32 MMAs per iteration, operands fixed, no address arithmetic between issues
       const uint64_t db = make_sdesc_sw128(smem_u32(sBhi));
       const uint64_t da0 = make_sdesc_sw128(smem_u32(sA));
@@ -281,6 +314,11 @@ int main() {
   run_case("time SS N=128 K=256 x64", 0, 128, 256, 64, false);
   run_case("time x3 N=256 K=128 x64", 2, 256, 128, 64, false);
   fails += run_case("prod N=128 K=128 (TS hi, SS lo)", 4, 128, 128, 1, true);
+  fails += run_case("MN-major A,B N=256 K=64  (LBO=slab)", 7, 256, 64, 1, true);
+  fails += run_case("MN-major A,B N=256 K=128 (LBO=slab)", 7, 256, 128, 1, true);
+  fails += run_case("MN-major A,B N=128 K=64  (LBO=slab)", 7, 128, 64, 1, true);
+  run_case("MN-major A,B N=256 K=64  (SBO=slab: expected FAIL)", 8, 256, 64, 1, true);
+  run_case("time MN-major SS N=256 K=128 x64", 7, 256, 128, 64, false);
   run_case("time TS   N=128 K=256 x64", 1, 128, 256, 64, false);
   run_case("time prod N=128 K=128 x64", 4, 128, 128, 64, false);
   run_case("time prod N=256 K=128 x64", 4, 256, 128, 64, false);
