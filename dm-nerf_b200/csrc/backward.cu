@@ -451,7 +451,9 @@ static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStr
 // colsum_out != NULL: also colsum_out[n] += sum_m A[m, n] (the bias gradient of the same layer, zero-initialised by the caller).
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st,
                    float* colsum_out = nullptr) {
-  if (bwd_use_tc() && M >= 512 && gemm_tn_tc_supported(N, K)) return launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, colsum_out, M, N, st);
+  if (bwd_use_tc() && M >= 512 && gemm_tn_tc_supported(N, K)) return launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, colsum_out, M, N, K, 0, st);
+  if (bwd_use_tc() && M >= 512 && !colsum_out && gemm_tn_tc_supported(K, N))      // narrow dY, wide X: compute (X^T dY)^T
+    return launch_gemm_tn_tc(B, ldb, A, lda, C, ldc, nullptr, M, K, N, 1, st);
   if (colsum_out) {
     int rc = colsum(A, lda, colsum_out, M, N, st);
     if (rc) return rc;

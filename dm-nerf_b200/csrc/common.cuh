@@ -120,8 +120,8 @@ bool gemm_nn_tc_supported(int N, int K, int ldc, const float* C, const float* ma
 bool gemm_tn_tc_supported(int N, int K);
 int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
                       const float* mask, const float* bias, int w_kmajor, cudaStream_t st);
-int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N,
-                      cudaStream_t st);
+int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
+                      int transpose, cudaStream_t st);
 int gemm_tc_check_status(cudaStream_t st);
 
 }  // namespace dmnerf

@@ -80,26 +80,48 @@ __device__ __forceinline__ void fail(int32_t* status, int code) { atomicCAS(stat
 // ------------------------------------------------------------------------------------------------ gemm_nn / gemm_nt
 // W_KMAJOR = false:  C[M, 256] (+)= A[M, N] * W[N, 256]                (dX = dY W; W rows are the contraction index)
 // W_KMAJOR = true:   C[M, 256]   =  A[M, N] * W[256, N]^T + bias       (y = x W^T + b: rebuilds the feature planes)
-// N = 64 * NCH.
+// N = 64 * NCH.  The weight matrix is the same for every tile, so it is split ONCE per call into a packed image of ready-made
+// stage blocks (pack_w_kernel) that are streamed into the stages with bulk async copies (TMA engine, mbarrier transaction
+// counts, requested as soon as a stage is free); the 16 loader warps only handle the activation / gradient rows, fetched two
+// stages ahead.
 constexpr uint32_t NN_A_BYTES = 128 * 128;               // one [128 x 64] slab
 constexpr uint32_t NN_W_BYTES = 256 * 128;               // the W block of a chunk: 4 slabs [64 x 64] or one slab [256 x 64]
 constexpr uint32_t NN_W_SLAB = 64 * 128;
 constexpr uint32_t NN_STAGE = 2 * NN_A_BYTES + 2 * NN_W_BYTES;          // A hi, A lo, W hi, W lo = 96 KB
 constexpr uint32_t NN_SMEM = 2 * NN_STAGE + 1024;
-constexpr int NN_UA = 128 * 8 / NT, NN_UW = 256 * 8 / NT;               // units per thread: 2 of A, 4 of W
+constexpr int NN_UA = 128 * 8 / NT;                      // A units per thread and stage: 2
+constexpr int NN_THREADS = NT;
+
+// image[c] = { W_hi block, W_lo block } of contraction chunk c, in the shared-memory layout of a stage.
+template <bool W_KMAJOR>
+__global__ void pack_w_kernel(const float* __restrict__ W, int ldw, int nch, int vec_w, uint8_t* __restrict__ image) {
+  const int c = blockIdx.x;
+  uint8_t* w_hi = image + (size_t)c * 2 * NN_W_BYTES;
+  uint8_t* w_lo = w_hi + NN_W_BYTES;
+  for (int u = threadIdx.x; u < 256 * 8; u += blockDim.x) {
+    Unit r;
+    if (W_KMAJOR) {
+      load_unit(r, W, ldw, u >> 3, NOUT, 64 * c + (u & 7) * 8, 64 * nch, vec_w != 0);                 // row = output column
+      store_unit(r, w_hi, w_lo, u >> 3, u & 7);
+    } else {
+      load_unit(r, W, ldw, 64 * c + ((u >> 3) & 63), 64 * nch, 64 * (u >> 9) + (u & 7) * 8, NOUT, vec_w != 0);
+      store_unit(r, w_hi + (u >> 9) * NN_W_SLAB, w_lo + (u >> 9) * NN_W_SLAB, (u >> 3) & 63, u & 7);
+    }
+  }
+}
 
 template <int NCH, bool W_KMAJOR>
-__global__ void __launch_bounds__(NT, 1) gemm_nn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                           float* __restrict__ C, int ldc, int64_t M, int accumulate,
-                                                           const float* __restrict__ mask, const float* __restrict__ bias, int vec_a,
-                                                           int vec_w, int32_t* status) {
+__global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* __restrict__ A, int lda, const uint8_t* __restrict__ wimage,
+                                                                   float* __restrict__ C, int ldc, int64_t M, int accumulate,
+                                                                   const float* __restrict__ mask, const float* __restrict__ bias,
+                                                                   int vec_a, int32_t* status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t done[2], acc_done;
+  __shared__ uint64_t done[2], wfull[2], acc_done;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&acc_done, 1);
+    mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&wfull[0], 1); mbar_init(&wfull[1], 1); mbar_init(&acc_done, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 256);
@@ -112,105 +134,130 @@ __global__ void __launch_bounds__(NT, 1) gemm_nn_tc_kernel(const float* __restri
   const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t n_chunks = my_tiles * NCH;
   // chunk q of this CTA: tile blockIdx.x + (q / NCH) * gridDim.x, contraction columns [64 (q % NCH), +64)
-  Unit ra[NN_UA], rw[NN_UW];
-  auto issue = [&](int64_t q) {
-    const int c = (int)(q % NCH);
-    const int64_t m0 = (blockIdx.x + (q / NCH) * gridDim.x) * 128;
+
+  {
+    // ===================================================== loaders + weight requests + MMA issuer + epilogue (16 warps)
+    auto issue = [&](Unit (&r)[NN_UA], int64_t q) {
+      const int c = (int)(q % NCH);
+      const int64_t m0 = (blockIdx.x + (q / NCH) * gridDim.x) * 128;
 #pragma unroll
-    for (int i = 0; i < NN_UA; ++i) {
-      const int u = tid + i * NT;
-      load_unit(ra[i], A, lda, m0 + (u >> 3), M, 64 * c + (u & 7) * 8, 64 * NCH, vec_a != 0);
-    }
-#pragma unroll
-    for (int i = 0; i < NN_UW; ++i) {
-      const int u = tid + i * NT;
-      if (W_KMAJOR) load_unit(rw[i], W, ldw, u >> 3, NOUT, 64 * c + (u & 7) * 8, 64 * NCH, vec_w != 0);       // row = output column
-      else load_unit(rw[i], W, ldw, 64 * c + ((u >> 3) & 63), 64 * NCH, 64 * (u >> 9) + (u & 7) * 8, NOUT, vec_w != 0);
-    }
-  };
-  if (n_chunks > 0) issue(0);
-  uint32_t tile_i = 0;
-  for (int64_t q = 0; q < n_chunks; ++q) {
-    const int c = (int)(q % NCH);
-    const uint32_t s = (uint32_t)q & 1;
-    uint8_t* st = smem + s * NN_STAGE;
-    uint8_t *a_hi = st, *a_lo = st + NN_A_BYTES, *w_hi = st + 2 * NN_A_BYTES, *w_lo = w_hi + NN_W_BYTES;
-    if (q >= 2 && !mbar_wait(&done[s], (uint32_t)((q >> 1) - 1) & 1)) fail(status, 601);      // the MMAs that read this stage are done
-#pragma unroll
-    for (int i = 0; i < NN_UA; ++i) {
-      const int u = tid + i * NT;
-      store_unit(ra[i], a_hi, a_lo, u >> 3, u & 7);
-    }
-#pragma unroll
-    for (int i = 0; i < NN_UW; ++i) {
-      const int u = tid + i * NT;
-      if (W_KMAJOR) store_unit(rw[i], w_hi, w_lo, u >> 3, u & 7);
-      else store_unit(rw[i], w_hi + (u >> 9) * NN_W_SLAB, w_lo + (u >> 9) * NN_W_SLAB, (u >> 3) & 63, u & 7);
-    }
-    if (q + 1 < n_chunks) issue(q + 1);                  // in flight while this stage is multiplied
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 0) {
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t da_hi = sdesc(sa_hi + ks * 32, 16, 1024), da_lo = sdesc(sa_lo + ks * 32, 16, 1024);
-          const uint64_t db_hi = W_KMAJOR ? sdesc(sw_hi + ks * 32, 16, 1024) : sdesc(sw_hi + ks * 2048, NN_W_SLAB, 1024);
-          const uint64_t db_lo = W_KMAJOR ? sdesc(sw_lo + ks * 32, 16, 1024) : sdesc(sw_lo + ks * 2048, NN_W_SLAB, 1024);
-          mma_ss(tD, da_hi, db_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
-          mma_ss(tD, da_lo, db_hi, idesc, 1u);
-          mma_ss(tD, da_hi, db_lo, idesc, 1u);
-        }
-        mma_commit(&done[s]);
-        if (c == NCH - 1) mma_commit(&acc_done);
+      for (int i = 0; i < NN_UA; ++i) {
+        const int u = tid + i * NT;
+        load_unit(r[i], A, lda, m0 + (u >> 3), M, 64 * c + (u & 7) * 8, 64 * NCH, vec_a != 0);
       }
-      __syncwarp();
-    }
-    if (c != NCH - 1) continue;
-    // ---- epilogue of the tile: warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
-    if (!mbar_wait(&acc_done, tile_i & 1)) fail(status, 602);
-    ++tile_i;
-    tc_fence_after();
-    {
-      const int64_t m = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
-      const int col0 = (warp >> 2) * 64;
-      const uint32_t taddr = tD + ((uint32_t)((warp & 3) * 32) << 16) + col0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c0, v);
-        tmem_ld_wait();
-        if (m < M) {
-          float* crow = C + m * ldc + col0 + c0;
-          const float* mrow = mask ? mask + m * ldc + col0 + c0 : nullptr;
+    };
+    uint32_t tile_i = 0;
+    auto stage = [&](Unit (&r)[NN_UA], int64_t q) {
+      const int c = (int)(q % NCH);
+      const uint32_t s = (uint32_t)q & 1;
+      uint8_t* st = smem + s * NN_STAGE;
+      uint8_t *a_hi = st, *a_lo = st + NN_A_BYTES, *w_hi = st + 2 * NN_A_BYTES, *w_lo = w_hi + NN_W_BYTES;
+      // ReLU mask of this thread's 64 output values: fetched at the start of the tile's last chunk, so that the DRAM latency
+      // is hidden behind that chunk instead of sitting (twice) in the epilogue; kept as two 32-bit words.
+      const int64_t m_row = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
+      float4 mk[16];
+      const bool want_mask = (c == NCH - 1) && mask != nullptr && m_row < M;
+      if (want_mask) {
+        const float4* mrow4 = reinterpret_cast<const float4*>(mask + m_row * ldc + (warp >> 2) * 64);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c0 + j));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        for (int j = 0; j < 16; ++j) mk[j] = __ldg(mrow4 + j);
+      }
+      if (q >= 2 && !mbar_wait(&done[s], (uint32_t)((q >> 1) - 1) & 1)) fail(status, 601);      // the MMAs that read this stage are done
+      if (tid == 0) {
+        // this chunk's weights: 64 KB from the packed image (L2); they land while the previous chunk is still being multiplied
+        mbar_arrive_expect_tx(&wfull[s], 2 * NN_W_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bulk_g2s(w_hi + i * 16384, wimage + (size_t)c * 2 * NN_W_BYTES + i * 16384, 16384, &wfull[s]);
+      }
+#pragma unroll
+      for (int i = 0; i < NN_UA; ++i) {
+        const int u = tid + i * NT;
+        store_unit(r[i], a_hi, a_lo, u >> 3, u & 7);
+      }
+      if (q + 2 < n_chunks) issue(r, q + 2);               // in flight while this and the next stage are multiplied
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        if (!mbar_wait(&wfull[s], (uint32_t)(q >> 1) & 1)) fail(status, 604);                   // this stage's weights have landed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da_hi = sdesc(sa_hi + ks * 32, 16, 1024), da_lo = sdesc(sa_lo + ks * 32, 16, 1024);
+            const uint64_t db_hi = W_KMAJOR ? sdesc(sw_hi + ks * 32, 16, 1024) : sdesc(sw_hi + ks * 2048, NN_W_SLAB, 1024);
+            const uint64_t db_lo = W_KMAJOR ? sdesc(sw_lo + ks * 32, 16, 1024) : sdesc(sw_lo + ks * 2048, NN_W_SLAB, 1024);
+            mma_ss(tD, da_hi, db_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+            mma_ss(tD, da_lo, db_hi, idesc, 1u);
+            mma_ss(tD, da_hi, db_lo, idesc, 1u);
+          }
+          mma_commit(&done[s]);
+          if (c == NCH - 1) mma_commit(&acc_done);
+        }
+        __syncwarp();
+      }
+      if (c != NCH - 1) return;
+      // ---- epilogue of the tile: warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
+      uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (want_mask) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t b = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = mk[8 * h2 + j];
+            b |= (x.x > 0.0f ? 1u : 0u) << (4 * j) | (x.y > 0.0f ? 1u : 0u) << (4 * j + 1) | (x.z > 0.0f ? 1u : 0u) << (4 * j + 2) |
+                 (x.w > 0.0f ? 1u : 0u) << (4 * j + 3);
+          }
+          mbits[h2] = b;
+        }
+      }
+      if (!mbar_wait(&acc_done, tile_i & 1)) fail(status, 602);
+      ++tile_i;
+      tc_fence_after();
+      {
+        const int64_t m = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
+        const int col0 = (warp >> 2) * 64;
+        const uint32_t taddr = tD + ((uint32_t)((warp & 3) * 32) << 16) + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(taddr + c0, v);
+          tmem_ld_wait();
+          if (m < M) {
+            float* crow = C + m * ldc + col0 + c0;
+            const uint32_t mb = mbits[c0 >> 5];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c0 + j));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              if (accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(crow + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              if (!((mb >> j) & 1u)) o.x = 0.0f;
+              if (!((mb >> (j + 1)) & 1u)) o.y = 0.0f;
+              if (!((mb >> (j + 2)) & 1u)) o.z = 0.0f;
+              if (!((mb >> (j + 3)) & 1u)) o.w = 0.0f;
+              *reinterpret_cast<float4*>(crow + j) = o;
             }
-            if (accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + j);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            if (mrow) {
-              const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
-              if (!(mk.x > 0.0f)) o.x = 0.0f;
-              if (!(mk.y > 0.0f)) o.y = 0.0f;
-              if (!(mk.z > 0.0f)) o.z = 0.0f;
-              if (!(mk.w > 0.0f)) o.w = 0.0f;
-            }
-            *reinterpret_cast<float4*>(crow + j) = o;
           }
         }
       }
+      tc_fence_before();
+      __syncthreads();                    // the accumulator is drained before the next tile overwrites it
+      tc_fence_after();
+    };
+    Unit r0[NN_UA], r1[NN_UA];
+    if (n_chunks > 0) issue(r0, 0);
+    if (n_chunks > 1) issue(r1, 1);
+    for (int64_t q = 0; q < n_chunks; q += 2) {
+      stage(r0, q);
+      if (q + 1 < n_chunks) stage(r1, q + 1);
     }
-    tc_fence_before();
-    __syncthreads();                    // the accumulator is drained before the next tile overwrites it
-    tc_fence_after();
   }
   tc_fence_before();
   __syncthreads();
@@ -218,20 +265,23 @@ __global__ void __launch_bounds__(NT, 1) gemm_nn_tc_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ gemm_tn
-// C[NA, 256] += A[mb:me, NA]^T * B[mb:me, 256] for this CTA's rows; 32 samples per stage, 3 stages in flight, loads issued two
-// stages ahead.  colsum != NULL: colsum[n] += sum over the rows of A[:, n] (the bias gradient, from the registers that
-// already hold A).
+// P[NA, NB] = A[mb:me, 0:NA]^T * B[mb:me, 0:nb] for this CTA's rows (NB = 256, or 64 with nb <= 64 valid columns); 32 samples
+// per stage, 3 stages in flight, loads issued two stages ahead.  Every CTA writes its partial product to its own slice of a
+// scratch buffer; reduce_partials_kernel adds the slices into the gradient (fp32 atomics from 148 CTAs onto the same 64 K
+// addresses were the slowest part of the first version).  colsum != NULL: colsum[n] += sum over the rows of A[:, n] (the bias
+// gradient, from the registers that already hold A).
 constexpr uint32_t TN_SLAB = 32 * 128;                   // one [32 x 64] slab
 constexpr int TN_STAGES = 3;
 
-template <int NA>
+template <int NA, int NB>
 __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                           float* __restrict__ C, int ldc, float* __restrict__ colsum, int64_t M,
+                                                           int nb, float* __restrict__ partial, float* __restrict__ colsum, int64_t M,
                                                            int64_t rows_per_cta, int vec_a, int vec_b, int32_t* status) {
-  constexpr int SA = NA / 64, SB = NOUT / 64;            // slabs per operand
+  constexpr int SA = NA / 64, SB = NB / 64;              // slabs per operand
   constexpr uint32_t STAGE = 2 * (SA + SB) * TN_SLAB;   // hi + lo
   constexpr int NH = NA / 128;                           // accumulators of 128 gradient rows
-  constexpr int UPT = (SA + SB) * 256 / NT;              // units per thread per stage (4 or 3); unit U = tid + i * NT
+  constexpr int UPT = ((SA + SB) * 256 + NT - 1) / NT;   // units per thread per stage; unit U = tid + i * NT
+  constexpr int ACC_COLS = (NH * NB < 32) ? 32 : NH * NB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t done[TN_STAGES], acc_done;
   __shared__ uint32_t tmem_base_s;
@@ -244,12 +294,12 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
     fence_barrier_init();
   }
   if (tid < NA) csum_s[tid] = 0.0f;
-  if (warp == 0) tmem_alloc(&tmem_base_s, NH * 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, ACC_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tD = tmem_base_s;
-  const uint32_t idesc = make_idesc_bf16(128, NOUT) | A_MN | B_MN;
+  const uint32_t idesc = make_idesc_bf16(128, NB) | A_MN | B_MN;
   const int64_t mb = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t me = (mb + rows_per_cta < M) ? mb + rows_per_cta : M;
   const int64_t n_chunks = (me > mb) ? (me - mb + 31) / 32 : 0;
@@ -264,7 +314,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
     for (int i = 0; i < UPT; ++i) {
       const int U = tid + i * NT, slab = U >> 8, u = U & 255;
       if (slab < SA) load_unit(r[i], A, lda, m0 + (u >> 3), me, 64 * slab + (u & 7) * 8, NA, vec_a != 0);
-      else load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, NOUT, vec_b != 0);
+      else if (slab < SA + SB) load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb, vec_b != 0);
     }
   };
   auto stage = [&](Unit (&r)[UPT], int64_t q) {            // store chunk q from registers, prefetch chunk q + 2, multiply
@@ -281,7 +331,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
 #pragma unroll
           for (int j = 0; j < 8; ++j) csum[i][j] += r[i].v[j];
         }
-      } else {
+      } else if (slab < SA + SB) {
         store_unit(r[i], b_hi + (slab - SA) * TN_SLAB, b_lo + (slab - SA) * TN_SLAB, u >> 3, u & 7);
       }
     }
@@ -299,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
             const uint64_t da_hi = sdesc(sa_hi + h * 2 * TN_SLAB + ks * 2048, TN_SLAB, 1024);
             const uint64_t da_lo = sdesc(sa_lo + h * 2 * TN_SLAB + ks * 2048, TN_SLAB, 1024);
             const uint64_t db_hi = sdesc(sb_hi + ks * 2048, TN_SLAB, 1024), db_lo = sdesc(sb_lo + ks * 2048, TN_SLAB, 1024);
-            const uint32_t d = tD + h * 256;
+            const uint32_t d = tD + h * NB;
             mma_ss(d, da_hi, db_hi, idesc, (q == 0 && ks == 0) ? 0u : 1u);
             mma_ss(d, da_lo, db_hi, idesc, 1u);
             mma_ss(d, da_hi, db_lo, idesc, 1u);
@@ -317,6 +367,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
     stage(r0, q);
     if (q + 1 < n_chunks) stage(r1, q + 1);
   }
+  float* mine = partial + (size_t)blockIdx.x * NA * NB;
   if (n_chunks > 0) {
     if (warp == 0) {
       if (elect_one()) mma_commit(&acc_done);
@@ -336,25 +387,41 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
     }
     if (!mbar_wait(&acc_done, 0)) fail(status, 612);
     tc_fence_after();
+    // warp w -> accumulator rows (w & 3) * 32 + lane, 32-column groups (w >> 2), (w >> 2) + 4, ...
 #pragma unroll 1
     for (int h = 0; h < NH; ++h) {
       const int n = h * 128 + (warp & 3) * 32 + lane;                     // gradient row
-      const int col0 = (warp >> 2) * 64;
-      const uint32_t taddr = tD + h * 256 + ((uint32_t)((warp & 3) * 32) << 16) + col0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int c0 = (warp >> 2) * 32; c0 < NB; c0 += 128) {
         uint32_t v[32];
-        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_x32(tD + h * NB + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
         tmem_ld_wait();
-        float* crow = C + (int64_t)n * ldc + col0 + c0;
+        float4* dst = reinterpret_cast<float4*>(mine + (size_t)n * NB + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(crow + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
     }
+  } else {
+    for (int i = tid; i < NA * NB; i += NT) mine[i] = 0.0f;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tD, NH * 256);
+  if (warp == 0) tmem_dealloc(tD, ACC_COLS);
+}
+
+// C[n, k] += sum_cta partial[cta][n][k]  (k < kb valid columns of the NB-wide partials);  transpose: C[k, n] instead
+// (the product was computed with the roles of the two operands exchanged).
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int NA, int NB, int kb, float* __restrict__ C,
+                                       int ldc, int transpose) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NA * NB) return;
+  const int n = idx / NB, k = idx % NB;
+  if (k >= kb) return;
+  float s = 0.0f;
+  for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * NA * NB + idx];
+  if (transpose) C[(size_t)k * ldc + n] += s;
+  else C[(size_t)n * ldc + k] += s;
 }
 
 static int32_t* g_status = nullptr;       // device error word shared by the GEMM launches of this process
@@ -384,7 +451,7 @@ static bool vec4_ok(const void* p, int ld) { return ((uintptr_t)p % 16 == 0) && 
 bool gemm_nn_tc_supported(int N, int K, int ldc, const float* C, const float* mask) {
   return (N == 128 || N == 256) && K == 256 && ldc % 4 == 0 && ((uintptr_t)C % 16 == 0) && (!mask || (uintptr_t)mask % 16 == 0);
 }
-bool gemm_tn_tc_supported(int N, int K) { return (N == 128 || N == 256) && K == 256; }
+bool gemm_tn_tc_supported(int N, int K) { return (N == 128 || N == 256) && (K == 256 || (K >= 1 && K <= 64)); }
 
 // w_kmajor == 0: C[M,256] (+)= A[M,N] W[N,256] (mask optional);  w_kmajor != 0: C[M,256] = A[M,N] W[256,N]^T + bias.
 int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
@@ -392,8 +459,10 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
   using namespace tg;
   if (M <= 0) return 0;
   if (ensure_status()) return 1;
+  static uint8_t* wimage = nullptr;                  // packed weights of the GEMM in flight (launches are stream-ordered)
   static bool attr = false;
   if (!attr) {
+    DMN_CUDA(cudaMalloc((void**)&wimage, 4 * 2 * NN_W_BYTES));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
@@ -403,32 +472,52 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
   DMN_CHECK(!bias || (uintptr_t)bias % 16 == 0, "gemm(tc): bias must be 16-byte aligned");
   const int64_t tiles = (M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  const int va = vec4_ok(A, lda), vw = vec4_ok(W, ldw);
-  if (w_kmajor) gemm_nn_tc_kernel<4, true><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
-  else if (N == 128) gemm_nn_tc_kernel<2, false><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
-  else gemm_nn_tc_kernel<4, false><<<grid, NT, NN_SMEM, st>>>(A, lda, W, ldw, C, ldc, M, accumulate, mask, bias, va, vw, g_status);
+  const int va = vec4_ok(A, lda), vw = vec4_ok(W, ldw), nch = N / 64;
+  if (w_kmajor) pack_w_kernel<true><<<nch, 512, 0, st>>>(W, ldw, nch, vw, wimage);
+  else pack_w_kernel<false><<<nch, 512, 0, st>>>(W, ldw, nch, vw, wimage);
+  DMN_LAUNCH_OK();
+  if (w_kmajor) gemm_nn_tc_kernel<4, true><<<grid, NN_THREADS, NN_SMEM, st>>>(A, lda, wimage, C, ldc, M, accumulate, mask, bias, va, g_status);
+  else if (N == 128) gemm_nn_tc_kernel<2, false><<<grid, NN_THREADS, NN_SMEM, st>>>(A, lda, wimage, C, ldc, M, accumulate, mask, bias, va, g_status);
+  else gemm_nn_tc_kernel<4, false><<<grid, NN_THREADS, NN_SMEM, st>>>(A, lda, wimage, C, ldc, M, accumulate, mask, bias, va, g_status);
   DMN_LAUNCH_OK();
   return 0;
 }
 
-int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N,
-                      cudaStream_t st) {
+// C[N, K] += A[M, N]^T B[M, K]  (N = 128 or 256 and K = 256, or K <= 64);  transpose != 0: the caller passes the WIDE matrix as A
+// and the narrow one (K <= 64 columns) as B and wants C[K, N] += B^T A.
+int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
+                      int transpose, cudaStream_t st) {
   using namespace tg;
   if (M <= 0) return 0;
   if (ensure_status()) return 1;
-  constexpr uint32_t SMEM128 = TN_STAGES * 2 * (2 + 4) * TN_SLAB + 1024, SMEM256 = TN_STAGES * 2 * (4 + 4) * TN_SLAB + 1024;
-  static bool attr = false;
-  if (!attr) {
-    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM128));
-    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM256));
-    attr = true;
-  }
+  static float* scratch = nullptr;                   // per-CTA partial products: up to 148 x [256 x 256] fp32
+  static size_t scratch_ctas = 0;
+  const int NB = (K > 64) ? 256 : 64;
+  DMN_CHECK((N == 128 || N == 256) && K >= 1 && K <= 256 && (NB == 64 || K == 256), "gemm_tn(tc): shape %d x %d not supported", N, K);
   int64_t rows = (M + sm_count() - 1) / sm_count();
   rows = ((rows + 31) / 32) * 32;
   const unsigned grid = (unsigned)((M + rows - 1) / rows);
+  if (!scratch || scratch_ctas < grid) {
+    if (scratch) DMN_CUDA(cudaFree(scratch));
+    scratch_ctas = grid > 148 ? grid : 148;
+    DMN_CUDA(cudaMalloc((void**)&scratch, scratch_ctas * 256 * 256 * sizeof(float)));
+  }
+  static bool attr = false;
+  auto smem_of = [](int na, int nbk) { return (uint32_t)(TN_STAGES * 2 * (na / 64 + nbk / 64) * TN_SLAB + 1024); };
+  if (!attr) {
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 256)));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 256)));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 64)));
+    DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 64)));
+    attr = true;
+  }
   const int va = vec4_ok(A, lda), vb = vec4_ok(B, ldb);
-  if (N == 128) gemm_tn_tc_kernel<128><<<grid, NT, SMEM128, st>>>(A, lda, B, ldb, C, ldc, colsum, M, rows, va, vb, g_status);
-  else gemm_tn_tc_kernel<256><<<grid, NT, SMEM256, st>>>(A, lda, B, ldb, C, ldc, colsum, M, rows, va, vb, g_status);
+  if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
+  else if (N == 256 && NB == 256) gemm_tn_tc_kernel<256, 256><<<grid, NT, smem_of(256, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
+  else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
+  else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
+  DMN_LAUNCH_OK();
+  reduce_partials_kernel<<<(N * NB + 255) / 256, 256, 0, st>>>(scratch, (int)grid, N, NB, K, C, ldc, transpose);
   DMN_LAUNCH_OK();
   return 0;
 }
