@@ -306,7 +306,7 @@ def run_ours(args):
         tms = 1e3 * (time.perf_counter() - t0) / 5
         train = {"rays_per_step": 1024, "ms_per_step": tms, "rays_per_s": 1024 / (tms * 1e-3),
                  "what": "dm_nerf(perturb=1) forward (tcgen05 kernel, activations saved from the epilogue) + backward (composite "
-                         "reverse scan, fp32 CUDA-core GEMM kernels) + Adam step; wall clock"}
+                         "reverse scan, split-bf16 tcgen05 GEMM kernels for dX / dW) + Adam step; wall clock"}
         nc.eval(); nf.eval()
 
     total_rays = n_rays * world * args.steps
