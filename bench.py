@@ -307,6 +307,32 @@ def run_ours(args):
         train = {"rays_per_step": 1024, "ms_per_step": tms, "rays_per_s": 1024 / (tms * 1e-3),
                  "what": "dm_nerf(perturb=1) forward (tcgen05 kernel, activations saved from the epilogue) + backward (composite "
                          "reverse scan, split-bf16 tcgen05 GEMM kernels for dX / dW) + Adam step; wall clock"}
+        # the emptiness penalizer on the fine network's per-sample outputs (forward + backward), HBM-streaming
+        try:
+            from dmnerf_b200.penalizer import ins_penalizer
+            pargs = types.SimpleNamespace(tolerance=0.05, deta_w=0.05)
+            praw = torch.randn(1024, N_COARSE + N_IMPORTANCE, 4 + ins_num + 1, device=dev, requires_grad=True)
+            pz = (torch.rand(1024, N_COARSE + N_IMPORTANCE, device=dev).sort(-1).values * 11 + 4)
+            pdep = pz[:, 100].clone()
+            for _ in range(3):
+                praw.grad = None
+                ins_penalizer(praw, pz, pdep, rays[1], pargs).sum().backward()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(20):
+                praw.grad = None
+                ins_penalizer(praw, pz, pdep, rays[1], pargs).sum().backward()
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            pus = 1e3 * ev0.elapsed_time(ev1) / 20
+            k1 = ins_num + 1
+            pbytes = 1024 * (N_COARSE + N_IMPORTANCE) * (4 * (2 * k1 + k1) + 3 * 4)
+            train["penalizer"] = {"us_per_fwd_bwd": pus, "algorithmic_GBps": pbytes / (pus * 1e-6) / 1e9,
+                                  "what": "ins_penalizer on raw_fine [1024,192,%d]: count + loss kernels, gradient kernel (+ torch "
+                                          "zero-fill of d_raw); algorithmic bytes = raw logits read twice + gradient written once + "
+                                          "z_vals three times" % (4 + k1)}
+        except Exception as exc:                       # informational block: never fail the bench line because of it
+            train["penalizer"] = {"error": str(exc)}
         nc.eval(); nf.eval()
 
     total_rays = n_rays * world * args.steps

@@ -217,6 +217,25 @@ DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const
                                    accumulate, (cudaStream_t)stream);
 }
 
+DMNERF_API int64_t dmnerf_penalizer_state_bytes(void) { return (int64_t)penalizer_state_bytes(); }
+
+DMNERF_API int dmnerf_penalizer_forward(const float* raw, const float* z_vals, const float* depth, const float* rays_d, int64_t n,
+                                        int s, int c, float tolerance, float deta_w, void* state, float* loss, void* stream) {
+  DMN_CHECK(n >= 0, "penalizer_forward: negative ray count");
+  DMN_CHECK(state && loss && (n == 0 || (raw && z_vals && depth && rays_d)), "penalizer_forward: NULL buffer");
+  DMN_CHECK(deta_w > 0.0f, "penalizer_forward: deta_w must be positive");
+  return launch_penalizer_forward(raw, z_vals, depth, rays_d, n, s, c, tolerance, deta_w, state, loss, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_penalizer_backward(const float* raw, const float* z_vals, const float* depth, const float* rays_d, int64_t n,
+                                         int s, int c, float tolerance, float deta_w, const void* state, const float* g_loss,
+                                         float* d_raw, int accumulate, void* stream) {
+  DMN_CHECK(n >= 0, "penalizer_backward: negative ray count");
+  DMN_CHECK(state && g_loss && (n == 0 || (raw && z_vals && depth && rays_d && d_raw)), "penalizer_backward: NULL buffer");
+  return launch_penalizer_backward(raw, z_vals, depth, rays_d, n, s, c, tolerance, deta_w, state, g_loss, d_raw, accumulate,
+                                   (cudaStream_t)stream);
+}
+
 DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n, int S, int NI, int flags, int impl,
                           void* stream) {
   DMN_CHECK(ctx && io, "render_forward: NULL ctx/io");

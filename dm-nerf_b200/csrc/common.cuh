@@ -124,4 +124,12 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
                       int transpose, cudaStream_t st);
 int gemm_tc_check_status(cudaStream_t st);
 
+// Emptiness regulariser (penalizer.cu)
+int launch_penalizer_forward(const float* raw, const float* z, const float* depth, const float* rays_d, int64_t n, int s, int c,
+                             float tol, float w, void* state, float* loss, cudaStream_t st);
+int launch_penalizer_backward(const float* raw, const float* z, const float* depth, const float* rays_d, int64_t n, int s, int c,
+                              float tol, float w, const void* state, const float* g_loss, float* d_raw, int accumulate,
+                              cudaStream_t st);
+size_t penalizer_state_bytes();
+
 }  // namespace dmnerf

@@ -149,6 +149,18 @@ DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const
                               int keep_all_ins, const float* g_rgb, const float* g_depth, const float* g_acc,
                               const float* g_ins, const float* g_weights, float* d_raw, int accumulate, void* stream);
 
+/* "Emptiness" regulariser on the per-sample object logits: emptiness_penalizer / ins_penalizer, networks/penalizer.py:5-62
+ * (train_dmsr.py:53-60).  raw [N,S,C], z_vals [N,S], depth [N] (the rendered depth map, treated as a constant),
+ * rays_d [N,3] -> loss[1] (device).  `state` is caller-provided device scratch of dmnerf_penalizer_state_bytes() bytes that
+ * carries the mask populations from the forward to the backward call.  Backward: d_raw[..., 4:] (+)= g_loss[0] * dL/draw
+ * (g_loss is a DEVICE scalar; channels 0..3 of d_raw are not touched). */
+DMNERF_API int64_t dmnerf_penalizer_state_bytes(void);
+DMNERF_API int dmnerf_penalizer_forward(const float* raw, const float* z_vals, const float* depth, const float* rays_d, int64_t n,
+                                        int s, int c, float tolerance, float deta_w, void* state, float* loss, void* stream);
+DMNERF_API int dmnerf_penalizer_backward(const float* raw, const float* z_vals, const float* depth, const float* rays_d, int64_t n,
+                                         int s, int c, float tolerance, float deta_w, const void* state, const float* g_loss,
+                                         float* d_raw, int accumulate, void* stream);
+
 /* dm_nerf(), networks/render.py:31-96, whole per-ray pipeline on device buffers. */
 DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io, int64_t n_rays, int n_coarse,
                           int n_importance, int flags, int impl, void* stream);

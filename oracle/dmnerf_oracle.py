@@ -14,6 +14,7 @@ those committed fixtures wherever the tests run.
 Every function cites the reference lines it restates.  Weights are passed as a plain dict keyed by
 the reference state_dict names (networks/dm_nerf.py:65-78).
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -166,3 +167,45 @@ def train_loss(out, target_rgb):
     out of scope)."""
     return (((out["rgb_coarse"] - target_rgb) ** 2).mean() + ((out["rgb_fine"] - target_rgb) ** 2).mean()
             + out["ins_coarse"].mean() + out["ins_fine"].mean())
+
+
+def emptiness_penalizer(raw, z_vals, depths, rays_d, tolerance, deta_w):
+    """"Emptiness" regulariser on the per-sample object logits, reference networks/penalizer.py:5-55.
+    raw [N,S,4+K], z_vals [N,S], depths [N,1] (already detached, penalizer.py:59), rays_d [N,3] -> loss tensor of shape [1].
+    In front of the surface (more than `tolerance` before the rendered depth) every sample should be "no object" (last class),
+    weighted by 1 - gaussian(distance to the surface); inside the +-tolerance shell the last class is pushed to 0, weighted by
+    the gaussian.  Both terms are masked means (penalizer.py:41-42, 52)."""
+    sigma_h = torch.Tensor([0.4])                                                   # :10
+    sigma_w = torch.Tensor([deta_w])
+    two_pi_root = torch.sqrt(torch.Tensor([2 * np.pi]))
+
+    def gaussian(delta):                                                            # :7-8
+        return torch.exp(-(delta ** 2) / (2 * (sigma_w ** 2))) / (sigma_h * two_pi_root) + 1e-8
+
+    norm = torch.norm(rays_d[..., None, :], dim=-1)                                 # :13   [N,1]
+    front = (depths - tolerance) * norm                                             # :14,16
+    back = (depths + tolerance) * norm                                              # :15,17
+    surface = depths * norm                                                         # :18
+    pos = z_vals * norm                                                             # :19
+    g = gaussian(surface - pos)                                                     # :22-23
+    air = 1 - g                                                                     # :24
+    m_before = (pos < front).type(torch.float32)                                    # :27
+    m_after = (pos > back).type(torch.float32)                                      # :28
+    m_middle = 1 - (m_after + m_before)                                             # :29
+    pred = torch.sigmoid(raw[..., 4:])                                              # :32-33
+    gt = torch.zeros_like(pred)
+    gt[..., -1] = 1                                                                 # :37-38
+    l_before = -gt * torch.log(pred + 1e-8) - (1 - gt) * torch.log(1 - pred + 1e-8)  # :39
+    l_before = l_before * (air * m_before)[..., None]                               # :40-41
+    l_before = torch.sum(l_before) / (pred.shape[-1] * torch.maximum(torch.sum(m_before), torch.tensor([1e-8])))   # :42-43
+    last = pred[..., -1]                                                            # :46
+    gt_mid = torch.zeros_like(last)
+    l_mid = -gt_mid * torch.log(last + 1e-8) - (1 - gt_mid) * torch.log(1 - last + 1e-8)   # :48-49
+    l_mid = l_mid * (g * m_middle)                                                  # :50-51
+    l_mid = torch.sum(l_mid) / torch.maximum(torch.sum(m_middle), torch.tensor([1e-8]))    # :52
+    return l_before + l_mid                                                         # :53
+
+
+def ins_penalizer(raw, z_vals, depth, rays_d, tolerance, deta_w):
+    """networks/penalizer.py:58-62 (args.tolerance / args.deta_w passed explicitly)."""
+    return emptiness_penalizer(raw, z_vals, depth[..., None].detach(), rays_d, tolerance, deta_w)

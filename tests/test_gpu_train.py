@@ -231,3 +231,28 @@ def test_mlp_backward_tensor_core_gemms(ins_num):
         ref = p[k].grad.numpy()
         got = prm.grad.cpu().numpy()
         assert scale_err(got, ref) <= 2e-4 and rel_l2(got, ref) <= 1e-4, (k, scale_err(got, ref), rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_emptiness_penalizer_matches_reference(golden_dir, tag):
+    """networks/penalizer.py (train_dmsr.py:53-60): loss and its gradient w.r.t. raw against the reference's own values
+    (tests/golden/penalizer.npz, generated by oracle/make_golden_penalizer.py); rays whose depth lies before / behind every
+    sample are included."""
+    from dmnerf_b200.penalizer import ins_penalizer
+    g = load(golden_dir, "penalizer.npz")
+    args = types.SimpleNamespace(tolerance=float(g["tolerance"]), deta_w=float(g["deta_w"]))
+    raw = cu(g["raw_" + tag]).requires_grad_(True)
+    before = _lib.launch_count()
+    loss = ins_penalizer(raw, cu(g["z_" + tag]), cu(g["depth_" + tag]), cu(g["rays_d_" + tag]), args)
+    assert loss.shape == (1,)
+    assert _lib.launch_count() == before + 2
+    ref = float(g["loss_" + tag][0])
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref)
+    (loss.sum() * 3.0).backward()
+    got, want = raw.grad.cpu().numpy(), 3.0 * g["grad_" + tag]
+    assert np.abs(got[..., :4]).max() == 0.0
+    assert scale_err(got, want) <= 1e-5 and rel_l2(got, want) <= 1e-5, (scale_err(got, want), rel_l2(got, want))
+    # empty batch
+    z0 = torch.zeros(0, 64, device=DEV)
+    l0 = ins_penalizer(torch.zeros(0, 64, 18, device=DEV), z0, torch.zeros(0, device=DEV), torch.zeros(0, 3, device=DEV), args)
+    assert float(l0) == 0.0

@@ -116,3 +116,15 @@ def test_fp64_twin_noise_floor(golden_dir):
     y64 = O.mlp_forward(O.to_torch(w, torch.float64), torch.from_numpy(g["x"]).double())
     rel = float((y32.double() - y64).norm() / y64.norm())
     assert rel < 5e-6
+
+
+def test_penalizer(golden_dir):
+    """Oracle emptiness penalizer (networks/penalizer.py:5-62) against the reference's loss and raw-gradient."""
+    g = load(golden_dir, "penalizer.npz")
+    for tag in ("a", "b"):
+        raw = torch.from_numpy(g["raw_" + tag]).clone().requires_grad_(True)
+        loss = O.ins_penalizer(raw, torch.from_numpy(g["z_" + tag]), torch.from_numpy(g["depth_" + tag]),
+                               torch.from_numpy(g["rays_d_" + tag]), float(g["tolerance"]), float(g["deta_w"]))
+        loss.sum().backward()
+        close(loss, g["loss_" + tag])
+        close(raw.grad, g["grad_" + tag], atol=1e-9)
