@@ -1,5 +1,6 @@
 // extern "C" boundary of libdmnerf_b200.so: context, weight binding, stage entry points and the
 // whole-pipeline render call.  See include/dmnerf_b200.h for the contract of every symbol.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -48,6 +49,7 @@ struct dmnerf_ctx {
   UmmaWeights packed[2];          // tensor-core operand images (umma_api.cuh)
   Scratch ws_raw_c, ws_raw_f, ws_z_c, ws_z_f, ws_w_c, ws_w_f;
   Scratch host_in, host_out;      // device staging for the *_host entry point
+  Scratch frame_rays;             // rays of the frame being rendered by dmnerf_render_frame_host
   bool train_feats_missing[2] = {false, false};
   bool profiling = false;
   bool last_fused = false;       // the last render call took the single-kernel path
@@ -84,7 +86,7 @@ DMNERF_API int dmnerf_ctx_destroy(dmnerf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (int i = 0; i < 2; ++i) umma_weights_free(ctx->packed[i]);
   Scratch* all[] = {&ctx->ws_raw_c, &ctx->ws_raw_f, &ctx->ws_z_c, &ctx->ws_z_f, &ctx->ws_w_c, &ctx->ws_w_f,
-                    &ctx->host_in, &ctx->host_out};
+                    &ctx->host_in, &ctx->host_out, &ctx->frame_rays};
   for (Scratch* s : all) s->release();
   for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
   delete ctx;
@@ -340,12 +342,17 @@ DMNERF_API int dmnerf_profile_read(dmnerf_ctx* ctx, float* ms_out, int n_out) {
   return 0;
 }
 
-DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* h, int64_t n, int S, int NI, int flags,
-                               int impl, void* stream) {
+}  // extern "C"
+
+// Host-buffer render: `h` holds HOST pointers for the outputs (and for the inputs unless dev_rays_o / dev_rays_d are given:
+// rays that are already resident on the device, e.g. generated there from the camera).
+static int render_host_impl(dmnerf_ctx* ctx, const dmnerf_render_io* h, const float* dev_rays_o, const float* dev_rays_d, int64_t n,
+                            int S, int NI, int flags, int impl, void* stream) {
   DMN_CHECK(ctx && h, "render_forward_host: NULL ctx/io");
   DMN_CHECK(n >= 0, "render_forward_host: negative ray count");
   if (n == 0) return 0;
-  DMN_CHECK(h->rays_o && h->rays_d && h->z_coarse, "render_forward_host: rays_o / rays_d / z_coarse is NULL");
+  const bool dev_rays = dev_rays_o != nullptr && dev_rays_d != nullptr;
+  DMN_CHECK((dev_rays || (h->rays_o && h->rays_d)) && h->z_coarse, "render_forward_host: rays_o / rays_d / z_coarse is NULL");
   DMN_CHECK(ctx->net[0].bound && ctx->net[1].bound, "render_forward_host: bind both networks first");
   cudaStream_t st = (cudaStream_t)stream;
   DMN_CUDA(cudaSetDevice(ctx->device));
@@ -355,14 +362,18 @@ DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_i
   const size_t zin = (h->z_row_stride == 0) ? (size_t)S : (size_t)n * h->z_row_stride;
 
   // ---- inputs: one device arena
-  size_t in_floats = (size_t)n * 6 + zin + (perturb ? (size_t)n * (S + NI) : 0);
+  size_t in_floats = (dev_rays ? 0 : (size_t)n * 6) + zin + (perturb ? (size_t)n * (S + NI) : 0);
   if (ctx->host_in.reserve(in_floats * 4)) return 2;
   float* d = (float*)ctx->host_in.ptr;
   dmnerf_render_io io;
   memset(&io, 0, sizeof(io));
   float* p = d;
-  DMN_CUDA(cudaMemcpyAsync(p, h->rays_o, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_o = p; p += n * 3;
-  DMN_CUDA(cudaMemcpyAsync(p, h->rays_d, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_d = p; p += n * 3;
+  if (dev_rays) {
+    io.rays_o = dev_rays_o; io.rays_d = dev_rays_d;
+  } else {
+    DMN_CUDA(cudaMemcpyAsync(p, h->rays_o, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_o = p; p += n * 3;
+    DMN_CUDA(cudaMemcpyAsync(p, h->rays_d, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_d = p; p += n * 3;
+  }
   DMN_CUDA(cudaMemcpyAsync(p, h->z_coarse, zin * 4, cudaMemcpyHostToDevice, st)); io.z_coarse = p; p += zin;
   io.z_row_stride = h->z_row_stride;
   if (perturb) {
@@ -393,6 +404,42 @@ DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_i
     if (h->*(o.hp))
       DMN_CUDA(cudaMemcpyAsync(h->*(o.hp), io.*(o.dp), (size_t)n * o.per_ray * 4, cudaMemcpyDeviceToHost, st));
   return dmnerf_sync_check(ctx, stream);
+}
+
+extern "C" {
+
+DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* h, int64_t n, int S, int NI, int flags,
+                               int impl, void* stream) {
+  return render_host_impl(ctx, h, nullptr, nullptr, n, S, NI, flags, impl, stream);
+}
+
+DMNERF_API int dmnerf_render_frame_host(dmnerf_ctx* ctx, const float* K_host, const float* c2w_host, int H, int W, float near_z,
+                                        float far_z, int64_t ray_begin, int64_t ray_count, int n_coarse, int n_importance,
+                                        int flags, int impl, const dmnerf_render_io* out_host, void* stream) {
+  DMN_CHECK(ctx && K_host && c2w_host && out_host, "render_frame_host: NULL argument");
+  DMN_CHECK(H > 0 && W > 0 && n_coarse >= 3 && n_coarse <= 4096, "render_frame_host: bad sizes H=%d W=%d S=%d", H, W, n_coarse);
+  DMN_CHECK(ray_begin >= 0 && ray_count >= 0 && ray_begin + ray_count <= (int64_t)H * W,
+            "render_frame_host: pixel range [%lld, +%lld) outside the %dx%d frame", (long long)ray_begin, (long long)ray_count, H, W);
+  DMN_CHECK(!(flags & DMNERF_FLAG_PERTURB), "render_frame_host: the frame driver is the deterministic test-time path");
+  if (ray_count == 0) return 0;
+  DMN_CUDA(cudaSetDevice(ctx->device));
+  // rays of the whole frame on the device (helpers.py:50-61; tester.py:59-61), the range asked for is rendered
+  if (ctx->frame_rays.reserve((size_t)H * W * 6 * sizeof(float))) return 2;
+  float* ro = (float*)ctx->frame_rays.ptr;
+  float* rd = ro + (size_t)H * W * 3;
+  int rc = dmnerf_get_rays(K_host, c2w_host, H, W, ro, rd, stream);
+  if (rc) return rc;
+  // z_val_sample (helpers.py:114-119): near + linspace(0, 1, S) * (far - near), torch.linspace's symmetric fp32 evaluation
+  std::vector<float> z((size_t)n_coarse);
+  const float step = 1.0f / (float)(n_coarse - 1), span = far_z - near_z;
+  for (int i = 0; i < n_coarse; ++i) {
+    const float t = (i < n_coarse / 2) ? step * (float)i : fmaf(-step, (float)(n_coarse - 1 - i), 1.0f);
+    z[i] = near_z + t * span;
+  }
+  dmnerf_render_io h = *out_host;
+  h.rays_o = nullptr; h.rays_d = nullptr; h.t_rand = nullptr; h.u = nullptr;
+  h.z_coarse = z.data(); h.z_row_stride = 0;
+  return render_host_impl(ctx, &h, ro + ray_begin * 3, rd + ray_begin * 3, ray_count, n_coarse, n_importance, flags, impl, stream);
 }
 
 }  // extern "C"

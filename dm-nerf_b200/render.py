@@ -1,5 +1,7 @@
 """Drop-in for reference networks/render.py: `dm_nerf` (:31-96, the north_star's render_rays) and
 `render_train` (:6-28, raw2outputs), running on the fused B200 kernels through the C ABI."""
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -170,3 +172,34 @@ def dm_nerf(rays, position_embedder, view_embedder, model_coarse, model_fine, z_
 
 # north_star aliases (SURVEY.md name-mapping table)
 raw2outputs = render_train
+
+
+def render_frame(H, W, K, c2w, near, far, model_coarse, model_fine, N_samples=64, N_importance=128, pixel_range=None,
+                 keep_all_ins=False, impl=_lib.IMPL_AUTO, device="cuda"):
+    """One camera of the reference's test-time loop (render_test, networks/tester.py:55-76) through the frame entry point of
+    the C ABI: rays are generated on the device from K / c2w (get_rays_k), the coarse depth row from near / far
+    (z_val_sample), the pixels are rendered by the fused kernel and the maps come back as HOST tensors:
+    rgb [H,W,3], ins [H,W,ins_num], depth [H,W], acc [H,W] (or [n, ...] rows when a pixel_range = (begin, count) is given --
+    the per-rank slice of a sharded frame)."""
+    dev = torch.device(device)
+    ctx = get_context(dev)
+    ins_num = ctx.bind(0, model_coarse)
+    if ctx.bind(1, model_fine) != ins_num:
+        raise RuntimeError("render_frame: coarse and fine networks disagree on ins_num")
+    begin, count = (0, H * W) if pixel_range is None else (int(pixel_range[0]), int(pixel_range[1]))
+    n_ins = ins_num + 1 if keep_all_ins else ins_num
+    pin = dev.type == "cuda"
+    out = {"rgb": torch.empty(count, 3, pin_memory=pin), "ins": torch.empty(count, n_ins, pin_memory=pin),
+           "depth": torch.empty(count, pin_memory=pin), "acc": torch.empty(count, pin_memory=pin)}
+    io = _lib.RenderIO(rgb_fine=out["rgb"].data_ptr(), ins_fine=out["ins"].data_ptr(), depth_fine=out["depth"].data_ptr(),
+                       acc_fine=out["acc"].data_ptr())
+    Kf = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1)[:9]])
+    c2 = torch.as_tensor(c2w, dtype=torch.float32).reshape(-1, 4)[:3].reshape(-1)
+    Cf = (C.c_float * 12)(*[float(v) for v in c2])
+    flags = _lib.FLAG_KEEP_INS if keep_all_ins else 0
+    _lib.check(ctx.lib.dmnerf_render_frame_host(ctx.handle, Kf, Cf, H, W, float(near), float(far), begin, count, N_samples,
+                                                N_importance, flags, impl, C.byref(io), ctx.stream()), "dmnerf_render_frame_host")
+    if pixel_range is None:
+        out = {"rgb": out["rgb"].reshape(H, W, 3), "ins": out["ins"].reshape(H, W, n_ins), "depth": out["depth"].reshape(H, W),
+               "acc": out["acc"].reshape(H, W)}
+    return out

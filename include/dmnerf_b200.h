@@ -149,6 +149,15 @@ DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const
                               int keep_all_ins, const float* g_rgb, const float* g_depth, const float* g_acc,
                               const float* g_ins, const float* g_weights, float* d_raw, int accumulate, void* stream);
 
+/* Frame driver: the test-time loop of render_test (networks/tester.py:55-76) for one camera, without the ray upload: rays
+ * are generated on the device from K / c2w (get_rays_k, helpers.py:50-61), the shared coarse depth row from near / far
+ * (z_val_sample, helpers.py:114-119), and pixels [ray_begin, ray_begin + ray_count) of the H x W frame (pixel-major, the
+ * reference's reshape(-1, 3)) are rendered by dm_nerf(); every non-NULL OUTPUT field of `out_host` (host memory, ray_count
+ * rows) is filled; its input fields are ignored.  Deterministic path only (perturb = 0).  Synchronises the stream. */
+DMNERF_API int dmnerf_render_frame_host(dmnerf_ctx* ctx, const float* K_host, const float* c2w_host, int H, int W, float near_z,
+                                        float far_z, int64_t ray_begin, int64_t ray_count, int n_coarse, int n_importance,
+                                        int flags, int impl, const dmnerf_render_io* out_host, void* stream);
+
 /* "Emptiness" regulariser on the per-sample object logits: emptiness_penalizer / ins_penalizer, networks/penalizer.py:5-62
  * (train_dmsr.py:53-60).  raw [N,S,C], z_vals [N,S], depth [N] (the rendered depth map, treated as a constant),
  * rays_d [N,3] -> loss[1] (device).  `state` is caller-provided device scratch of dmnerf_penalizer_state_bytes() bytes that

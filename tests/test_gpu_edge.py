@@ -109,3 +109,34 @@ def test_non_contiguous_and_batched_inputs():
     s = sample_pdf(bins, torch.rand(2, 3, 62, device=DEV), 16, det=True)
     assert s.shape == (2, 3, 16) and bool((s[..., 1:] >= s[..., :-1] - 1e-6).all())
     assert isinstance(get_embedder(0, -1)[0], torch.nn.Identity)
+
+
+def test_render_frame_driver_matches_explicit_rays():
+    """dmnerf_render_frame_host (render_test's per-camera loop, tester.py:55-76): rays generated on the device from K / c2w,
+    coarse depths from near / far -- identical (bitwise: same kernels, same inputs) to get_rays_k + z_val_sample + dm_nerf on
+    explicit rays; a pixel range renders the matching slice."""
+    import types
+    from dmnerf_b200 import synth
+    from dmnerf_b200.testing import make_models
+    from dmnerf_b200.render import render_frame, dm_nerf
+    from dmnerf_b200.helpers import get_rays_k, z_val_sample
+    from dmnerf_b200.embedder import get_embedder
+    wl = synth.workload("dmsr_study")
+    nc, nf, _, _ = make_models(3, 4, 13, "cuda")
+    H, W = 12, 20
+    K = np.array(wl["K"], dtype=np.float32).copy()
+    K[0, 2], K[1, 2] = W / 2, H / 2
+    c2w = torch.from_numpy(np.asarray(wl["c2w"], dtype=np.float32))
+    near, far = float(wl["near"]), float(wl["far"])
+    with torch.no_grad():
+        fr = render_frame(H, W, K, c2w, near, far, nc, nf)
+        ro, rd = get_rays_k(H, W, K, c2w.cuda())
+        rays = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)
+        args = types.SimpleNamespace(perturb=0.0, N_importance=128, is_train=False, N_ins=None)
+        ref = dm_nerf(rays, get_embedder(10)[0], get_embedder(4)[0], nc, nf, z_val_sample(H * W, near, far, 64, device="cuda"), args)
+        part = render_frame(H, W, K, c2w, near, far, nc, nf, pixel_range=(37, 101))
+    assert fr["rgb"].shape == (H, W, 3) and fr["ins"].shape == (H, W, 13) and fr["depth"].shape == (H, W)
+    assert torch.equal(fr["rgb"].reshape(-1, 3), ref["rgb_fine"].cpu())
+    assert torch.equal(fr["ins"].reshape(-1, 13), ref["ins_fine"].cpu())
+    assert torch.equal(fr["depth"].reshape(-1), ref["depth_fine"].cpu())
+    assert torch.equal(part["rgb"], ref["rgb_fine"].cpu()[37:138]) and torch.equal(part["acc"], fr["acc"].reshape(-1)[37:138])
