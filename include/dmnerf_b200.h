@@ -158,6 +158,15 @@ DMNERF_API int dmnerf_render_frame_host(dmnerf_ctx* ctx, const float* K_host, co
                                         float far_z, int64_t ray_begin, int64_t ray_count, int n_coarse, int n_importance,
                                         int flags, int impl, const dmnerf_render_io* out_host, void* stream);
 
+/* exchanger, networks/manipulator.py:18-83: per-sample swap of network outputs between the original rays and up to 8
+ * transformed ("target") ray sets of an object edit.  ori_raw [N,S,C] is edited IN PLACE; tar_raws / tar_accs are HOST arrays
+ * of n_moves DEVICE pointers ([N,S,C] / [N,C-4]); ori_acc [N,C-4] and tar_accs are the rendered instance maps with every
+ * channel kept (manipulator_render); move_labels is a HOST array.  Outputs: int64 per-sample labels of the original and of the
+ * last target after the occlusion fixes. */
+DMNERF_API int dmnerf_exchanger(float* ori_raw, const float* const* tar_raws, const float* ori_acc, const float* const* tar_accs,
+                                const int* move_labels, int n_moves, int64_t n, int s, int c, int64_t* ori_label,
+                                int64_t* tar_label, void* stream);
+
 /* "Emptiness" regulariser on the per-sample object logits: emptiness_penalizer / ins_penalizer, networks/penalizer.py:5-62
  * (train_dmsr.py:53-60).  raw [N,S,C], z_vals [N,S], depth [N] (the rendered depth map, treated as a constant),
  * rays_d [N,3] -> loss[1] (device).  `state` is caller-provided device scratch of dmnerf_penalizer_state_bytes() bytes that

@@ -209,3 +209,96 @@ def emptiness_penalizer(raw, z_vals, depths, rays_d, tolerance, deta_w):
 def ins_penalizer(raw, z_vals, depth, rays_d, tolerance, deta_w):
     """networks/penalizer.py:58-62 (args.tolerance / args.deta_w passed explicitly)."""
     return emptiness_penalizer(raw, z_vals, depth[..., None].detach(), rays_d, tolerance, deta_w)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Object manipulation at render time (SURVEY.md section 8, row f3): reference networks/manipulator.py:18-205.
+# ------------------------------------------------------------------------------------------------------------------
+def manipulator_nerf(p, rays, z_vals=None, n_samples=None, near=None, far=None):
+    """One network evaluated along the rays at given (or freshly spaced) depths, manipulator.py:108-134.
+    Note the depth formula near*(1-t) + far*t (:119), which differs from z_val_sample's in the last bits."""
+    rays_o, rays_d = rays
+    viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)                      # :110-112
+    n_rays = rays_d.shape[0]
+    if z_vals is None:
+        near_, far_ = near * torch.ones(size=(n_rays, 1)), far * torch.ones(size=(n_rays, 1))
+        t_vals = torch.linspace(0., 1., steps=n_samples)
+        z_vals = (near_ * (1. - t_vals) + far_ * t_vals).expand([n_rays, n_samples])   # :117-120
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]          # :122
+    x = torch.cat([embed(pts.reshape(-1, 3), 10), embed(viewdirs[:, None].expand(pts.shape).reshape(-1, 3), 4)], -1)
+    raw = mlp_forward(p, x)                                                          # :131
+    return raw.reshape(list(pts.shape[:-1]) + [raw.shape[-1]]), z_vals
+
+
+def manipulator_render(raw, z_vals, rays_d):
+    """manipulator.py:86-105: the composite without the detach and with every instance channel kept."""
+    rgb, weights, depth, ins, _ = composite(raw, z_vals, rays_d, keep_all_ins=True)
+    return rgb, weights, depth, ins
+
+
+def exchanger(ori_raw, tar_raws, ori_raw_pred, tar_raw_preds, move_labels):
+    """Per-sample swap of network outputs between the original and the transformed rays, manipulator.py:18-83.
+    Returns (edited ori_raw, tar_raws, per-sample label of the original, per-sample label of the last target)."""
+    ori_raw = ori_raw.clone()
+    ori_label = torch.argmax(torch.sigmoid(ori_raw[..., 4:]), dim=-1)                 # :19-21
+    ori_acc = torch.argmax(torch.sigmoid(ori_raw_pred[..., :-1]), dim=-1)             # :23-25 (last = "empty" class dropped)
+    ori_acc = ori_acc[:, None].expand_as(ori_label)                                   # :26
+    tar_label = None
+    for idx, mv in enumerate(move_labels):
+        tar_raw = tar_raws[idx]
+        ori_label = torch.where((ori_label == mv) & (ori_acc != mv), ori_acc, ori_label)     # :33-36 occluder in front
+        fillings = (ori_acc == mv) & (ori_label != mv)                                # :40-42
+        tar_label = torch.argmax(torch.sigmoid(tar_raw[..., 4:]), dim=-1)             # :45-47
+        tar_acc = torch.argmax(torch.sigmoid(tar_raw_preds[idx][..., :-1]), dim=-1)[:, None].expand_as(tar_label)   # :50-53
+        tar_label = torch.where((tar_label == mv) & (tar_acc != mv), tar_acc, tar_label)     # :57-60
+        code = (tar_label == mv).long() + 2 * (ori_label == mv).long()                # :64-69: 0 none, 1 target only, 2 original only, 3 both
+        take = (code == 1) | (code == 3)                                              # :71-75  exchange
+        wipe = code == 2                                                              #         eliminate
+        ori_raw = torch.where(fillings[..., None], tar_raw, ori_raw)                  # :78
+        ori_raw = torch.where(take[..., None], tar_raw, ori_raw)                      # :81
+        ori_raw = torch.where(wipe[..., None], ori_raw * 0, ori_raw)                  # :82
+    return ori_raw, tar_raws, ori_label, tar_label
+
+
+def manipulator(p_coarse, p_fine, ori_rays, f_tar_rays, n_samples, n_importance, near, far, target_labels, us=None):
+    """Whole edit-time pipeline for one chunk of rays, manipulator.py:137-205.  The reference calls sample_pdf without
+    det=True, i.e. with torch.rand draws (helpers.py:135), in the order: original rays, each target, original again (step 2).
+    `us` (a list of [N, n_importance] tensors consumed in that order) replaces the draws; None draws from torch's global
+    generator exactly like the reference."""
+    us = list(us) if us is not None else None
+
+    def draw(bins, w):
+        return sample_pdf(bins, w, n_importance, u=(us.pop(0) if us is not None else None))
+
+    def fine_pass(rays, coarse_raw, coarse_z):
+        _, w, _, _ = manipulator_render(coarse_raw, coarse_z, rays[1])
+        mid = .5 * (coarse_z[..., 1:] + coarse_z[..., :-1])
+        z_s = draw(mid, w[..., 1:-1])                                                 # :147-148 (random u)
+        z_full, _ = torch.sort(torch.cat([coarse_z, z_s], -1), -1)
+        raw_full, _ = manipulator_nerf(p_fine, rays, z_vals=z_full)
+        _, _, _, ins_acc = manipulator_render(raw_full, z_full, rays[1])
+        return z_s, ins_acc
+
+    ori_raw, ori_z = manipulator_nerf(p_coarse, ori_rays, None, n_samples, near, far)   # :140-141
+    _, ori_ins_acc = fine_pass(ori_rays, ori_raw, ori_z)                              # :144-152
+    tar_raws, tar_zs, tar_samples, tar_accs = [], [], [], []
+    tar_rgb = None
+    for tar_rays in f_tar_rays:                                                       # :155-176
+        t_raw, t_z = manipulator_nerf(p_coarse, tar_rays, None, n_samples, near, far)
+        tar_rgb, _, _, _ = manipulator_render(t_raw, t_z, tar_rays[1])
+        z_s, acc = fine_pass(tar_rays, t_raw, t_z)
+        tar_raws.append(t_raw); tar_zs.append(t_z); tar_samples.append(z_s); tar_accs.append(acc)
+    ori_raw, _, _, _ = exchanger(ori_raw, tar_raws, ori_ins_acc, tar_accs, target_labels)    # :179
+    _, ori_w, _, _ = manipulator_render(ori_raw, ori_z, ori_rays[1])                 # :183
+    mid = .5 * (ori_z[..., 1:] + ori_z[..., :-1])
+    ori_samples = draw(mid, ori_w[..., 1:-1])                                         # :186-187
+    all_tar = torch.cat(tar_samples, -1)                                              # :190
+    ori_z2, _ = torch.sort(torch.cat([ori_z, ori_samples, all_tar], -1), -1)          # :191
+    ori_raw2 = None
+    for idx, tar_rays in enumerate(f_tar_rays):                                       # :192-199
+        ori_raw2, _ = manipulator_nerf(p_fine, ori_rays, z_vals=ori_z2)
+        t_z2, _ = torch.sort(torch.cat([tar_zs[idx], ori_samples, all_tar], -1), -1)
+        tar_raws[idx], _ = manipulator_nerf(p_fine, tar_rays, z_vals=t_z2)
+    ori_raw2, _, _, _ = exchanger(ori_raw2, tar_raws, ori_ins_acc, tar_accs, target_labels)   # :201
+    final_rgb, _, _, final_ins = manipulator_render(ori_raw2, ori_z2, ori_rays[1])    # :203
+    return final_rgb, final_ins, tar_rgb, tar_accs[-1]

@@ -81,6 +81,7 @@ def test_dropin_networks_package_exposes_reference_names():
             "from networks.dm_nerf import get_embedder, DM_NeRF, Embedder;"
             "from networks.helpers import get_rays_k, z_val_sample, sample_pdf;"
             "from networks.penalizer import ins_penalizer, emptiness_penalizer;"
+            "from networks.manipulator import exchanger, manipulator_render, manipulator_nerf, manipulator;"
             "e, d = get_embedder(10); assert d == 63; assert get_embedder(4)[1] == 27;"
             "import torch.nn as nn; assert isinstance(get_embedder(0, -1)[0], nn.Identity);"
             "print('ok')")

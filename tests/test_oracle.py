@@ -128,3 +128,24 @@ def test_penalizer(golden_dir):
         loss.sum().backward()
         close(loss, g["loss_" + tag])
         close(raw.grad, g["grad_" + tag], atol=1e-9)
+
+
+def test_manipulator(golden_dir):
+    """Oracle edit pipeline (networks/manipulator.py:18-205) against the reference run stored in manipulator.npz."""
+    g = load(golden_dir, "manipulator.npz")
+    ins_num = int(g["ins_num"])
+    wc, wf = synth.make_weights(int(g["seed_c"]), ins_num), synth.make_weights(int(g["seed_f"]), ins_num)
+    wc["ins_linear.weight"], wc["ins_linear.bias"] = g["ins_w_c"], g["ins_b_c"]
+    wf["ins_linear.weight"], wf["ins_linear.bias"] = g["ins_w_f"], g["ins_b_f"]
+    t = torch.from_numpy
+    labels = [int(v) for v in g["labels"]]
+    with torch.no_grad():
+        out = O.exchanger(t(g["ex_ori_raw"]), [t(x) for x in g["ex_tar_raws"]], t(g["ex_acc_o"]), [t(x) for x in g["ex_acc_t"]], labels)
+        assert torch.equal(out[0], t(g["ex_out_raw"])) and torch.equal(out[2], t(g["ex_out_label"]))
+        assert torch.equal(out[3], t(g["ex_out_tar_label"]))
+        res = O.manipulator(O.to_torch(wc), O.to_torch(wf), t(g["ori"]), [t(x) for x in g["f_tar"]], int(g["n_samples"]),
+                            int(g["n_importance"]), float(g["near"]), float(g["far"]), labels, us=[t(u) for u in g["us"]])
+    close(res[2], g["tar_rgb"], rtol=1e-4, atol=1e-5)
+    # discrete decisions inside: bulk agreement (bit-exact on the generating machine)
+    for got, key in ((res[0], "final_rgb"), (res[1], "final_ins"), (res[3], "tar_ins_accum")):
+        assert (np.abs(got.numpy() - g[key]).max(-1) <= 1e-3).mean() >= 0.9, key
