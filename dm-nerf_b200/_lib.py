@@ -65,6 +65,7 @@ PROTOTYPES = {
     "dmnerf_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float,
                                           C.c_float, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RenderIO),
                                           C.c_void_p]),
+    "dmnerf_mlp_forward_points": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, _f32p, C.c_int, C.c_void_p]),
     "dmnerf_exchanger": (C.c_int, [_f32p, C.POINTER(C.c_void_p), _f32p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int64,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dmnerf_penalizer_state_bytes": (C.c_int64, []),

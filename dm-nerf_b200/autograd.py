@@ -48,3 +48,19 @@ def mlp_forward_rays(model, rays_o, rays_d, z, impl=_lib.IMPL_AUTO):
                                                _lib.ptr(rays_d.contiguous().float()), _lib.ptr(z.contiguous().float()),
                                                n, s, _lib.ptr(out), impl, ctx.stream()), "dmnerf_mlp_forward_rays")
     return out
+
+
+def mlp_forward_points(model, pts, viewdirs=None, impl=_lib.IMPL_AUTO):
+    """The network at arbitrary points with explicit view directions (zeros by default), embedded inside the kernel: the grid
+    sweep of tools/mesh_generator.py:36-49.  pts [..., 3] -> [..., 4 + ins_num + 1]."""
+    if not pts.is_cuda:
+        raise RuntimeError("mlp_forward_points: expected CUDA tensors (no CPU fallback)")
+    ctx = get_context(pts.device)
+    slot = ctx.slot_for(model)
+    ins_num = ctx.bind(slot, model)
+    p2 = pts.reshape(-1, 3).contiguous().float()
+    v2 = torch.zeros_like(p2) if viewdirs is None else viewdirs.reshape(-1, 3).contiguous().float()
+    out = torch.empty((p2.shape[0], 4 + ins_num + 1), device=pts.device, dtype=torch.float32)
+    _lib.check(ctx.lib.dmnerf_mlp_forward_points(ctx.handle, slot, _lib.ptr(p2), _lib.ptr(v2), p2.shape[0], _lib.ptr(out), impl,
+                                                 ctx.stream()), "dmnerf_mlp_forward_points")
+    return out.reshape(*pts.shape[:-1], out.shape[-1])

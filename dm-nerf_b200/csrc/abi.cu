@@ -143,6 +143,17 @@ DMNERF_API int dmnerf_mlp_forward_rays(dmnerf_ctx* ctx, int net, const float* ra
   return mlp_dispatch(ctx, net, nullptr, rays_o, rays_d, z, n * s, s, out, impl, (cudaStream_t)stream);
 }
 
+DMNERF_API int dmnerf_mlp_forward_points(dmnerf_ctx* ctx, int net, const float* pts, const float* viewdirs, int64_t m, float* out,
+                                         int impl, void* stream) {
+  DMN_CHECK(ctx != nullptr && (net == 0 || net == 1), "mlp_forward_points: bad ctx / net");
+  DMN_CHECK(m >= 0, "mlp_forward_points: negative point count");
+  DMN_CHECK(m == 0 || (pts && viewdirs && out), "mlp_forward_points: NULL buffer");
+  DMN_CHECK(impl != DMNERF_IMPL_SIMT, "mlp_forward_points: the point query runs on the tensor-core kernel only");
+  if (m == 0) return 0;
+  DMN_CHECK(umma_available(ctx->packed[net]), "mlp_forward_points: bind the network with dmnerf_set_weights first");
+  return launch_mlp_umma(ctx->packed[net], ctx->net[net], nullptr, pts, viewdirs, nullptr, m, 1, out, nullptr, (cudaStream_t)stream);
+}
+
 DMNERF_API int dmnerf_composite(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c, int keep_all_ins,
                      float* rgb, float* weights, float* depth, float* ins, float* acc, void* stream) {
   DMN_CHECK(n >= 0, "composite: negative ray count");

@@ -611,15 +611,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               zz = fz->zf[rlp][sip];
             }
           } else {
+            // rays mode: sample s of ray r at depth z.  Points mode (z == NULL, s == 1): rays_o holds the query points and
+            // rays_d the view directions exactly as they go into the embedding (mesh_generator.py:40-44 passes zeros).
             const int64_t ray = rowp / a.s;
-            zz = a.z[rowp];
+            zz = a.z ? a.z[rowp] : 0.0f;
             o0 = a.rays_o[ray * 3]; o1 = a.rays_o[ray * 3 + 1]; o2 = a.rays_o[ray * 3 + 2];
             d0 = a.rays_d[ray * 3]; d1 = a.rays_d[ray * 3 + 1]; d2 = a.rays_d[ray * 3 + 2];
-            nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+            nrm = a.z ? sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2))) : 1.0f;
           }
-          pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
-          pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
-          pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
+          if (FUSED || a.z) {
+            pt[0] = __fadd_rn(o0, __fmul_rn(d0, zz));      // render.py:49
+            pt[1] = __fadd_rn(o1, __fmul_rn(d1, zz));
+            pt[2] = __fadd_rn(o2, __fmul_rn(d2, zz));
+          } else {
+            pt[0] = o0; pt[1] = o1; pt[2] = o2;
+          }
           if (do_d) { vd[0] = __fdiv_rn(d0, nrm); vd[1] = __fdiv_rn(d1, nrm); vd[2] = __fdiv_rn(d2, nrm); }   // render.py:37
         }
         // |2^9 x| small enough for the branch-free sin/cos in every lane?  (warp-uniform choice; scenes are a few units wide)
@@ -1167,7 +1173,8 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
                     const float* z, int64_t m, int s, float* out, float* acts, cudaStream_t st) {
   using namespace uk;
   DMN_CHECK(w.ready && w.extra, "mlp(umma): weights not packed (call dmnerf_set_weights first)");
-  DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr && z != nullptr), "mlp(umma): pass either x or rays");
+  DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr), "mlp(umma): pass either x or rays");
+  DMN_CHECK(x != nullptr || z != nullptr || s == 1, "mlp(umma): points mode (z == NULL) takes one sample per row");
   if (m == 0) return 0;
   UmmaExtra* ex = extra_of(w);
   static bool attr_set = false;

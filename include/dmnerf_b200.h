@@ -158,6 +158,12 @@ DMNERF_API int dmnerf_render_frame_host(dmnerf_ctx* ctx, const float* K_host, co
                                         float far_z, int64_t ray_begin, int64_t ray_count, int n_coarse, int n_importance,
                                         int flags, int impl, const dmnerf_render_io* out_host, void* stream);
 
+/* Point query: the network at m points with explicit view directions, both embedded inside the kernel
+ * (pts [m,3], viewdirs [m,3] used as they are -- no normalisation) -> out [m, 4+ins_num+1].  This is the grid sweep of
+ * tools/mesh_generator.py:36-49 (256^3 points, zero view directions) without the [m,90] embedded tensor in HBM. */
+DMNERF_API int dmnerf_mlp_forward_points(dmnerf_ctx* ctx, int net, const float* pts, const float* viewdirs, int64_t m, float* out,
+                                         int impl, void* stream);
+
 /* exchanger, networks/manipulator.py:18-83: per-sample swap of network outputs between the original rays and up to 8
  * transformed ("target") ray sets of an object edit.  ori_raw [N,S,C] is edited IN PLACE; tar_raws / tar_accs are HOST arrays
  * of n_moves DEVICE pointers ([N,S,C] / [N,C-4]); ori_acc [N,C-4] and tar_accs are the rendered instance maps with every

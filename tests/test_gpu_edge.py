@@ -190,3 +190,24 @@ def test_manipulator_pipeline_matches_reference(golden_dir, impl):
     ok_rgb = (np.abs(rgb.cpu().numpy() - g["final_rgb"]).max(-1) <= 2e-3).mean()
     ok_ins = (np.abs(ins.cpu().numpy() - g["final_ins"]).max(-1) <= 2e-3).mean()
     assert ok_rgb >= 0.85 and ok_ins >= 0.85, (ok_rgb, ok_ins)
+
+
+def test_point_query_matches_embedded_forward():
+    """dmnerf_mlp_forward_points (grid sweep of tools/mesh_generator.py:36-49: zero view directions, points embedded in the
+    kernel) against the oracle network on the embedded points; a ragged tile included."""
+    from dmnerf_b200.autograd import mlp_forward_points
+    from dmnerf_b200.testing import model_from_weights, scale_err
+    from oracle import dmnerf_oracle as O
+    w = synth.make_weights(41, 13)
+    net = model_from_weights(w, "cuda").eval()
+    gen = torch.Generator().manual_seed(2)
+    pts = (torch.rand(1000, 3, generator=gen) * 8 - 4)
+    with torch.no_grad():
+        got = mlp_forward_points(net, pts.cuda()).cpu().numpy()
+        x = torch.cat([O.embed(pts, 10), O.embed(torch.zeros_like(pts), 4)], -1)
+        ref = O.mlp_forward(O.to_torch(w), x).numpy()
+        vd = torch.randn(1000, 3, generator=gen) * 0.5
+        got2 = mlp_forward_points(net, pts.cuda().reshape(10, 100, 3), vd.cuda().reshape(10, 100, 3)).cpu().numpy().reshape(1000, -1)
+        ref2 = O.mlp_forward(O.to_torch(w), torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1)).numpy()
+    assert got.shape == (1000, 18)
+    assert scale_err(got, ref) <= 1e-4 and scale_err(got2, ref2) <= 1e-4, (scale_err(got, ref), scale_err(got2, ref2))
