@@ -19,9 +19,10 @@
 // Structure (both kernels): 512 threads, persistent CTAs.  All 16 warps split the stage they fetched into registers one or two
 // stages earlier and store it (2-3 stages of shared memory), issue the global loads of a later stage, the block synchronises,
 // and one elected lane of warp 0 issues the stage's 12 MMAs and commits them to the stage's mbarrier; loads, splits and tensor
-// work of neighbouring stages overlap.  gemm_nn drains its [128 x 256] accumulator after every
-// 128-row tile (bias-free epilogue: optional accumulate, ReLU mask, fp32 store); gemm_tn keeps the whole [NA x 256] gradient
-// in tensor memory for the CTA's share of the samples and adds it to global memory once at the end (fp32 atomics).
+// work of neighbouring stages overlap.  gemm_nn alternates between two [128 x 256] accumulators and drains a tile one stage
+// late, while the next tile's first chunk is multiplied (epilogue: optional bias / accumulate, ReLU mask, fp32 store);
+// gemm_tn keeps the whole [NA x NB] gradient in tensor memory for the CTA's share of the samples, writes it once to its slice
+// of a scratch buffer, and a small kernel adds the slices.
 #include <cstring>
 
 #include "common.cuh"
@@ -116,15 +117,16 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
                                                                    const float* __restrict__ mask, const float* __restrict__ bias,
                                                                    int vec_a, int32_t* status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t done[2], wfull[2], acc_done;
+  __shared__ uint64_t done[2], wfull[2], acc_done[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&wfull[0], 1); mbar_init(&wfull[1], 1); mbar_init(&acc_done, 1);
+    mbar_init(&done[0], 1); mbar_init(&done[1], 1); mbar_init(&wfull[0], 1); mbar_init(&wfull[1], 1);
+    mbar_init(&acc_done[0], 1); mbar_init(&acc_done[1], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -146,22 +148,72 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
         load_unit(r[i], A, lda, m0 + (u >> 3), M, 64 * c + (u & 7) * 8, 64 * NCH, vec_a != 0);
       }
     };
-    uint32_t tile_i = 0;
+    // ReLU mask of this thread's 64 output values of local tile `ti` (two 128-byte lines of the saved activation): requested
+    // into L2 at the top of a stage (no registers held while the stage runs) and read in the epilogue one chunk later.
+    auto tile_row = [&](int64_t ti) { return (blockIdx.x + ti * gridDim.x) * 128 + (warp & 3) * 32 + lane; };
+    auto prefetch_mask = [&](int64_t ti) {
+      const int64_t m_row = tile_row(ti);
+      if (mask == nullptr || m_row >= M) return;
+      const float* p0 = mask + m_row * ldc + (warp >> 2) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 32));
+    };
+    // Epilogue of local tile ti (accumulator ti & 1): warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
+    auto epilogue = [&](int64_t ti) {
+      if (!mbar_wait(&acc_done[ti & 1], (uint32_t)(ti >> 1) & 1)) fail(status, 602);
+      tc_fence_after();
+      const int64_t m = tile_row(ti);
+      const int col0 = (warp >> 2) * 64;
+      const uint32_t taddr = tD + (uint32_t)(ti & 1) * 256 + ((uint32_t)((warp & 3) * 32) << 16) + col0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (m < M) {
+          float* crow = C + m * ldc + col0 + c0;
+          uint32_t mb = 0xFFFFFFFFu;
+          if (mask) {
+            const float4* mrow4 = reinterpret_cast<const float4*>(mask + m * ldc + col0 + c0);
+            mb = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = __ldg(mrow4 + j);
+              mb |= (x.x > 0.0f ? 1u : 0u) << (4 * j) | (x.y > 0.0f ? 1u : 0u) << (4 * j + 1) | (x.z > 0.0f ? 1u : 0u) << (4 * j + 2) |
+                    (x.w > 0.0f ? 1u : 0u) << (4 * j + 3);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c0 + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (!((mb >> j) & 1u)) o.x = 0.0f;
+            if (!((mb >> (j + 1)) & 1u)) o.y = 0.0f;
+            if (!((mb >> (j + 2)) & 1u)) o.z = 0.0f;
+            if (!((mb >> (j + 3)) & 1u)) o.w = 0.0f;
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        }
+      }
+      tc_fence_before();                 // ordered before the block barrier of the stage that reuses this accumulator
+    };
     auto stage = [&](Unit (&r)[NN_UA], int64_t q) {
       const int c = (int)(q % NCH);
+      const int64_t ti = q / NCH;
       const uint32_t s = (uint32_t)q & 1;
       uint8_t* st = smem + s * NN_STAGE;
       uint8_t *a_hi = st, *a_lo = st + NN_A_BYTES, *w_hi = st + 2 * NN_A_BYTES, *w_lo = w_hi + NN_W_BYTES;
-      // ReLU mask of this thread's 64 output values: fetched at the start of the tile's last chunk, so that the DRAM latency
-      // is hidden behind that chunk instead of sitting (twice) in the epilogue; kept as two 32-bit words.
-      const int64_t m_row = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
-      float4 mk[16];
-      const bool want_mask = (c == NCH - 1) && mask != nullptr && m_row < M;
-      if (want_mask) {
-        const float4* mrow4 = reinterpret_cast<const float4*>(mask + m_row * ldc + (warp >> 2) * 64);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mk[j] = __ldg(mrow4 + j);
-      }
+      // the previous tile is drained one stage late -- after this tile's first chunk has been handed to the tensor core
+      // (the two tiles use different accumulators) -- so its epilogue overlaps tensor work instead of stalling it
+      const bool drain_prev = (c == 0) && ti > 0;
+      if (drain_prev) prefetch_mask(ti - 1);
       if (q >= 2 && !mbar_wait(&done[s], (uint32_t)((q >> 1) - 1) & 1)) fail(status, 601);      // the MMAs that read this stage are done
       if (tid == 0) {
         // this chunk's weights: 64 KB from the packed image (L2); they land while the previous chunk is still being multiplied
@@ -182,74 +234,22 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sw_hi = smem_u32(w_hi), sw_lo = smem_u32(w_lo);
+          const uint32_t d = tD + (uint32_t)(ti & 1) * 256;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da_hi = sdesc(sa_hi + ks * 32, 16, 1024), da_lo = sdesc(sa_lo + ks * 32, 16, 1024);
             const uint64_t db_hi = W_KMAJOR ? sdesc(sw_hi + ks * 32, 16, 1024) : sdesc(sw_hi + ks * 2048, NN_W_SLAB, 1024);
             const uint64_t db_lo = W_KMAJOR ? sdesc(sw_lo + ks * 32, 16, 1024) : sdesc(sw_lo + ks * 2048, NN_W_SLAB, 1024);
-            mma_ss(tD, da_hi, db_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
-            mma_ss(tD, da_lo, db_hi, idesc, 1u);
-            mma_ss(tD, da_hi, db_lo, idesc, 1u);
+            mma_ss(d, da_hi, db_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+            mma_ss(d, da_lo, db_hi, idesc, 1u);
+            mma_ss(d, da_hi, db_lo, idesc, 1u);
           }
           mma_commit(&done[s]);
-          if (c == NCH - 1) mma_commit(&acc_done);
+          if (c == NCH - 1) mma_commit(&acc_done[ti & 1]);
         }
         __syncwarp();
       }
-      if (c != NCH - 1) return;
-      // ---- epilogue of the tile: warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
-      uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (want_mask) {
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t b = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = mk[8 * h2 + j];
-            b |= (x.x > 0.0f ? 1u : 0u) << (4 * j) | (x.y > 0.0f ? 1u : 0u) << (4 * j + 1) | (x.z > 0.0f ? 1u : 0u) << (4 * j + 2) |
-                 (x.w > 0.0f ? 1u : 0u) << (4 * j + 3);
-          }
-          mbits[h2] = b;
-        }
-      }
-      if (!mbar_wait(&acc_done, tile_i & 1)) fail(status, 602);
-      ++tile_i;
-      tc_fence_after();
-      {
-        const int64_t m = (blockIdx.x + (q / NCH) * gridDim.x) * 128 + (warp & 3) * 32 + lane;
-        const int col0 = (warp >> 2) * 64;
-        const uint32_t taddr = tD + ((uint32_t)((warp & 3) * 32) << 16) + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(taddr + c0, v);
-          tmem_ld_wait();
-          if (m < M) {
-            float* crow = C + m * ldc + col0 + c0;
-            const uint32_t mb = mbits[c0 >> 5];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + c0 + j));
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-              }
-              if (accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(crow + j);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              if (!((mb >> j) & 1u)) o.x = 0.0f;
-              if (!((mb >> (j + 1)) & 1u)) o.y = 0.0f;
-              if (!((mb >> (j + 2)) & 1u)) o.z = 0.0f;
-              if (!((mb >> (j + 3)) & 1u)) o.w = 0.0f;
-              *reinterpret_cast<float4*>(crow + j) = o;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncthreads();                    // the accumulator is drained before the next tile overwrites it
-      tc_fence_after();
+      if (drain_prev) epilogue(ti - 1);
     };
     Unit r0[NN_UA], r1[NN_UA];
     if (n_chunks > 0) issue(r0, 0);
@@ -258,10 +258,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
       stage(r0, q);
       if (q + 1 < n_chunks) stage(r1, q + 1);
     }
+    if (my_tiles > 0) epilogue(my_tiles - 1);            // the last tile
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tD, 256);
+  if (warp == 0) tmem_dealloc(tD, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ gemm_tn
