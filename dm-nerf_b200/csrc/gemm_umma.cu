@@ -425,23 +425,31 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_
   else C[(size_t)n * ldc + k] += s;
 }
 
-static int32_t* g_status = nullptr;       // device error word shared by the GEMM launches of this process
+// Scratch of the GEMM launches, one set per CUDA device of the process (launches on a device are stream-ordered, so one packed
+// weight image and one partial-product buffer per device are enough; they live until the process exits).
+struct DevState {
+  int32_t* status = nullptr;          // device error word of the GEMM kernels
+  uint8_t* wimage = nullptr;          // packed weights of the dX GEMM in flight (4 chunks x 64 KB)
+  float* partial = nullptr;           // per-CTA partial products of the dW GEMM
+  size_t partial_ctas = 0;
+  int sms = 0;
+};
+constexpr int MAX_DEVICES = 64;
+static DevState g_dev[MAX_DEVICES];
 
-static int ensure_status() {
-  if (!g_status) {
-    DMN_CUDA(cudaMalloc((void**)&g_status, sizeof(int32_t)));
-    DMN_CUDA(cudaMemset(g_status, 0, sizeof(int32_t)));
+static int dev_state(DevState** out) {
+  int dev = 0;
+  DMN_CUDA(cudaGetDevice(&dev));
+  DMN_CHECK(dev >= 0 && dev < MAX_DEVICES, "gemm(tc): device index %d out of range", dev);
+  DevState& d = g_dev[dev];
+  if (!d.status) {
+    DMN_CUDA(cudaMalloc((void**)&d.status, sizeof(int32_t)));
+    DMN_CUDA(cudaMemset(d.status, 0, sizeof(int32_t)));
+    DMN_CUDA(cudaMalloc((void**)&d.wimage, 4 * 2 * NN_W_BYTES));
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.sms <= 0) d.sms = 148;
   }
+  *out = &d;
   return 0;
-}
-
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  return sms;
 }
 
 static bool vec4_ok(const void* p, int ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
@@ -459,11 +467,12 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
                       const float* mask, const float* bias, int w_kmajor, cudaStream_t st) {
   using namespace tg;
   if (M <= 0) return 0;
-  if (ensure_status()) return 1;
-  static uint8_t* wimage = nullptr;                  // packed weights of the GEMM in flight (launches are stream-ordered)
+  DevState* ds = nullptr;
+  if (dev_state(&ds)) return 1;
+  uint8_t* wimage = ds->wimage;
+  int32_t* g_status = ds->status;
   static bool attr = false;
   if (!attr) {
-    DMN_CUDA(cudaMalloc((void**)&wimage, 4 * 2 * NN_W_BYTES));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
@@ -472,7 +481,7 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
   DMN_CHECK(!w_kmajor || N == 256, "gemm_nt(tc): contraction width %d not supported", N);
   DMN_CHECK(!bias || (uintptr_t)bias % 16 == 0, "gemm(tc): bias must be 16-byte aligned");
   const int64_t tiles = (M + 127) / 128;
-  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  const unsigned grid = (unsigned)(tiles < ds->sms ? tiles : ds->sms);
   const int va = vec4_ok(A, lda), vw = vec4_ok(W, ldw), nch = N / 64;
   if (w_kmajor) pack_w_kernel<true><<<nch, 512, 0, st>>>(W, ldw, nch, vw, wimage);
   else pack_w_kernel<false><<<nch, 512, 0, st>>>(W, ldw, nch, vw, wimage);
@@ -490,19 +499,21 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
                       int transpose, cudaStream_t st) {
   using namespace tg;
   if (M <= 0) return 0;
-  if (ensure_status()) return 1;
-  static float* scratch = nullptr;                   // per-CTA partial products: up to 148 x [256 x 256] fp32
-  static size_t scratch_ctas = 0;
+  DevState* ds = nullptr;
+  if (dev_state(&ds)) return 1;
+  int32_t* g_status = ds->status;
   const int NB = (K > 64) ? 256 : 64;
   DMN_CHECK((N == 128 || N == 256) && K >= 1 && K <= 256 && (NB == 64 || K == 256), "gemm_tn(tc): shape %d x %d not supported", N, K);
-  int64_t rows = (M + sm_count() - 1) / sm_count();
+  int64_t rows = (M + ds->sms - 1) / ds->sms;
   rows = ((rows + 31) / 32) * 32;
   const unsigned grid = (unsigned)((M + rows - 1) / rows);
-  if (!scratch || scratch_ctas < grid) {
-    if (scratch) DMN_CUDA(cudaFree(scratch));
-    scratch_ctas = grid > 148 ? grid : 148;
-    DMN_CUDA(cudaMalloc((void**)&scratch, scratch_ctas * 256 * 256 * sizeof(float)));
+  if (!ds->partial || ds->partial_ctas < grid) {      // up to one [256 x 256] fp32 slice per CTA
+    if (ds->partial) DMN_CUDA(cudaFree(ds->partial));
+    ds->partial = nullptr;
+    ds->partial_ctas = grid > (unsigned)ds->sms ? grid : (unsigned)ds->sms;
+    DMN_CUDA(cudaMalloc((void**)&ds->partial, ds->partial_ctas * 256 * 256 * sizeof(float)));
   }
+  float* scratch = ds->partial;
   static bool attr = false;
   auto smem_of = [](int na, int nbk) { return (uint32_t)(TN_STAGES * 2 * (na / 64 + nbk / 64) * TN_SLAB + 1024); };
   if (!attr) {
@@ -525,9 +536,11 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
 
 // Asynchronous failure word of the GEMM kernels (0 = fine); checked by dmnerf_sync_check.
 int gemm_tc_check_status(cudaStream_t st) {
-  if (!tg::g_status) return 0;
+  int dev = 0;
+  DMN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= tg::MAX_DEVICES || !tg::g_dev[dev].status) return 0;
   int32_t h = 0;
-  DMN_CUDA(cudaMemcpyAsync(&h, tg::g_status, sizeof(h), cudaMemcpyDeviceToHost, st));
+  DMN_CUDA(cudaMemcpyAsync(&h, tg::g_dev[dev].status, sizeof(h), cudaMemcpyDeviceToHost, st));
   DMN_CUDA(cudaStreamSynchronize(st));
   DMN_CHECK(h == 0, "tensor-core backward GEMM: barrier protocol failure (code %d)", h);
   return 0;
