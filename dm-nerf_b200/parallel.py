@@ -61,3 +61,33 @@ def render_frame_sharded(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse
     full = gather_image(out, world, group=group, pad_to=per)                 # [world, per, 5+ins]
     flat = full.reshape(world * per, -1)[:n]
     return unpack_image(flat, ins_num)
+
+
+def render_camera_sharded(H, W, K, c2w, near, far, model_coarse, model_fine, N_samples=64, N_importance=128, frame_fn=None,
+                          group=None, device=None):
+    """One camera of a trajectory (BASELINE config 5; the per-pose loop of render_test, tester.py:55-76) split by pixel range
+    across the ranks: every rank runs the frame driver (rays generated on its own device from K / c2w) on its range and ONE
+    all-gather assembles the image dict {"rgb" [H,W,3], "ins" [H,W,ins_num], "depth" [H,W], "acc" [H,W]} on every rank.
+    `frame_fn(H, W, K, c2w, near, far, mc, mf, N_samples=, N_importance=, pixel_range=)` defaults to render.render_frame."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if frame_fn is None:
+        from .render import render_frame as frame_fn
+    n = H * W
+    lo, hi, per = shard_range(n, world, rank, multiple=128)
+    part = frame_fn(H, W, K, c2w, near, far, model_coarse, model_fine, N_samples=N_samples, N_importance=N_importance,
+                    pixel_range=(lo, hi - lo))
+    out = {"rgb_fine": part["rgb"], "depth_fine": part["depth"], "acc_fine": part["acc"], "ins_fine": part["ins"]}
+    if device is not None:                                  # NCCL gathers device tensors; the frame driver returns host maps
+        out = {k: v.to(device, non_blocking=True) for k, v in out.items()}
+    ins_num = out["ins_fine"].shape[-1]
+    full = gather_image(out, world, group=group, pad_to=per)
+    img = unpack_image(full.reshape(world * per, -1)[:n], ins_num)
+    return {"rgb": img["rgb_fine"].reshape(H, W, 3), "ins": img["ins_fine"].reshape(H, W, ins_num),
+            "depth": img["depth_fine"].reshape(H, W), "acc": img["acc_fine"].reshape(H, W)}
+
+
+def render_trajectory_sharded(poses, H, W, K, near, far, model_coarse, model_fine, **kw):
+    """Generator over a camera trajectory (e.g. the 900 poses of Replica office_2): yields the assembled image dict per pose."""
+    for c2w in poses:
+        yield render_camera_sharded(H, W, K, c2w, near, far, model_coarse, model_fine, **kw)

@@ -41,6 +41,49 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _camera_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dmnerf_b200.parallel import render_trajectory_sharded
+    H, W, ins = 9, 23, 5                                       # 207 pixels: shards of 128 / 79
+
+    def fake_frame(H, W, K, c2w, near, far, mc, mf, N_samples=64, N_importance=128, pixel_range=None):
+        lo, cnt = pixel_range
+        idx = torch.arange(lo, lo + cnt, dtype=torch.float32) + 1000.0 * float(c2w)
+        return {"rgb": torch.stack([idx, idx + 0.25, idx + 0.5], -1), "ins": idx[:, None] * torch.arange(1, ins + 1),
+                "depth": -idx, "acc": idx * 2}
+
+    imgs = list(render_trajectory_sharded([1.0, 2.0], H, W, None, 0.0, 1.0, None, None, frame_fn=fake_frame))
+    if rank == 1:                                              # every rank holds the full image
+        ok = True
+        for pose, img in zip((1.0, 2.0), imgs):
+            idx = torch.arange(H * W, dtype=torch.float32) + 1000.0 * pose
+            ok &= torch.equal(img["rgb"].reshape(-1, 3)[:, 0], idx) and torch.equal(img["depth"].reshape(-1), -idx)
+            ok &= torch.equal(img["ins"].reshape(-1, ins)[:, 2], idx * 3) and torch.equal(img["acc"].reshape(-1), idx * 2)
+            ok &= img["rgb"].shape == (H, W, 3) and img["ins"].shape == (H, W, ins)
+        ret.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_trajectory_render_sharded_by_pixel_range_gloo_world2():
+    """BASELINE config 5 host logic: every pose is split by pixel range over the ranks (frame driver per rank) and assembled
+    with one all-gather; world 2 over gloo with a synthetic frame function."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_camera_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert ok
+
+
 @pytest.mark.timeout(600)
 def test_sharded_render_gloo_world2():
     ctx = mp.get_context("spawn")
