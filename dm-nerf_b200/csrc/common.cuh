@@ -65,6 +65,19 @@ __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
 }
 
 void set_error(const char* fmt, ...);
+
+// Per-device one-time initialisation (kernel attributes are per device): true the first time it is called for the current
+// device with this flag set.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 extern std::atomic<int64_t> g_launches;
 
 #define DMN_CHECK(cond, ...)                   \

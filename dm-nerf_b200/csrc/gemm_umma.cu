@@ -471,12 +471,11 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
   if (dev_state(&ds)) return 1;
   uint8_t* wimage = ds->wimage;
   int32_t* g_status = ds->status;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
     DMN_CUDA(cudaFuncSetAttribute(gemm_nn_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM));
-    attr = true;
   }
   DMN_CHECK(!w_kmajor || N == 256, "gemm_nt(tc): contraction width %d not supported", N);
   DMN_CHECK(!bias || (uintptr_t)bias % 16 == 0, "gemm(tc): bias must be 16-byte aligned");
@@ -514,14 +513,13 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
     DMN_CUDA(cudaMalloc((void**)&ds->partial, ds->partial_ctas * 256 * 256 * sizeof(float)));
   }
   float* scratch = ds->partial;
-  static bool attr = false;
+  static PerDeviceOnce attr_once;
   auto smem_of = [](int na, int nbk) { return (uint32_t)(TN_STAGES * 2 * (na / 64 + nbk / 64) * TN_SLAB + 1024); };
-  if (!attr) {
+  if (attr_once.first()) {
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 256)));
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 256)));
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 64)));
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 64)));
-    attr = true;
   }
   const int va = vec4_ok(A, lda), vb = vec4_ok(B, ldb);
   if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);

@@ -184,11 +184,10 @@ int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, con
   DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr && z != nullptr),
             "mlp: pass either x or (rays_o, rays_d, z)");
   if (m == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DMN_CUDA(cudaFuncSetAttribute(simt::mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)simt::SMEM_BYTES));
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   DMN_CUDA(cudaGetDevice(&dev));

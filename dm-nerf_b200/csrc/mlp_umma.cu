@@ -1022,8 +1022,10 @@ struct PackStage {            // one entry per (step, chunk): produces the W_hi 
 __global__ void fold_kernel(const float* __restrict__ w2, int ld2, const float* __restrict__ w1, const float* __restrict__ b1,
                             const float* __restrict__ b2, int extra_cols, float* __restrict__ wout, float* __restrict__ bout) {
   // wout[n][k] = sum_j w2[n][j] w1[j][k] (k < 256);  wout[n][256 + e] = w2[n][256 + e];  bout[n] = sum_j w2[n][j] b1[j] + b2[n]
+  // grid (128 output rows, 3 column blocks of 128): one output element per thread, so the 256-long fp64 chains of a row run
+  // side by side (this kernel is on the critical path of every training step: the weights change, the fold is redone)
   const int n = blockIdx.x, ldo = 256 + extra_cols;
-  for (int k = threadIdx.x; k < ldo + 1; k += blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < ldo + 1; k += gridDim.y * blockDim.x) {
     if (k < 256) {
       double s = 0.0;
       for (int j = 0; j < 256; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)w1[(size_t)j * 256 + k];
@@ -1128,9 +1130,9 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
   }
   UmmaExtra* x = extra_of(w);
   // fold the activation-free feature layers into the following hidden layers (fp64 accumulate)
-  fold_kernel<<<128, 128, 0, st>>>(p.w[L_RGB_HID], 283, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], p.b[L_RGB_HID], 27, x->fold_w_rgb, x->fold_b);
+  fold_kernel<<<dim3(128, 3), 128, 0, st>>>(p.w[L_RGB_HID], 283, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], p.b[L_RGB_HID], 27, x->fold_w_rgb, x->fold_b);
   DMN_LAUNCH_OK();
-  fold_kernel<<<128, 128, 0, st>>>(p.w[L_INS_HID], 256, p.w[L_INS_FEAT], p.b[L_INS_FEAT], p.b[L_INS_HID], 0, x->fold_w_ins, x->fold_b + 128);
+  fold_kernel<<<dim3(128, 3), 128, 0, st>>>(p.w[L_INS_HID], 256, p.w[L_INS_FEAT], p.b[L_INS_FEAT], p.b[L_INS_HID], 0, x->fold_w_ins, x->fold_b + 128);
   DMN_LAUNCH_OK();
   // one PackStage per (step, chunk)
   std::vector<PackStage> ent;
@@ -1177,10 +1179,9 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   DMN_CHECK(x != nullptr || z != nullptr || s == 1, "mlp(umma): points mode (z == NULL) takes one sample per row");
   if (m == 0) return 0;
   UmmaExtra* ex = extra_of(w);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   DMN_CUDA(cudaGetDevice(&dev));
@@ -1205,10 +1206,9 @@ int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmner
   DMN_CHECK(wc.ins_num == wf.ins_num, "render(umma): coarse/fine ins_num differ");
   if (n == 0) return 0;
   UmmaExtra* ex = extra_of(wc);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DMN_CUDA(cudaFuncSetAttribute(mlp_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   DMN_CUDA(cudaGetDevice(&dev));
