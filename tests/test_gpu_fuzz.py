@@ -1,0 +1,85 @@
+"""GPU: randomised differential tests (hypothesis) of the per-ray stage kernels against the oracle at ragged sizes -- ray counts
+that are not multiples of a warp or a tile, sample counts from 3 to a few hundred, degenerate weights -- and of the domain's
+size-independent properties (sum of weights <= 1, merged depths sorted and within range, deterministic sampling
+monotone, instance map in (0,1))."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+pytestmark = pytest.mark.gpu
+
+from dmnerf_b200.testing import max_rel_err, frac_bad
+from oracle import dmnerf_oracle as O
+
+DEV = "cuda"
+COMMON = dict(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+
+
+def _cu(t):
+    return t.to(DEV).contiguous()
+
+
+@settings(**COMMON)
+@given(n=st.integers(1, 70), s=st.integers(3, 260), k=st.integers(2, 40), seed=st.integers(0, 2 ** 20), keep=st.booleans())
+def test_composite_fuzz(n, s, k, seed, keep):
+    from dmnerf_b200.render import composite
+    gen = torch.Generator().manual_seed(seed)
+    raw = torch.randn(n, s, 4 + k, generator=gen) * 2
+    raw[..., 3] = raw[..., 3] * 3 - 1                                       # plenty of negative (clamped) and large densities
+    z = (torch.rand(n, s, generator=gen).sort(-1).values * 9 + 1)
+    rd = torch.randn(n, 3, generator=gen) * 1.5
+    ref = O.composite(raw, z, rd, keep_all_ins=keep)
+    with torch.no_grad():
+        got = composite(_cu(raw), _cu(z), _cu(rd), keep_all_ins=keep)
+    rgb, w, depth, ins, acc = [g.cpu() for g in got]
+    assert max_rel_err(w, ref[1], 1e-3) <= 1e-4 and max_rel_err(rgb, ref[0], 1e-2) <= 1e-4
+    assert max_rel_err(depth, ref[2], 1e-1) <= 1e-4 and max_rel_err(ins, ref[3], 1e-2) <= 1e-4
+    assert float(acc.max()) <= 1.0 + 1e-5 and float(w.min()) >= 0.0                       # transmittance is a probability
+    assert ins.shape[1] == (k if keep else k - 1) and float(ins.min()) > 0.0 and float(ins.max()) < 1.0 + 1e-7
+
+
+@settings(**COMMON)
+@given(n=st.integers(1, 70), nb=st.integers(3, 130), ns=st.integers(2, 200), seed=st.integers(0, 2 ** 20), det=st.booleans(),
+       sparse=st.booleans())
+def test_sample_pdf_fuzz(n, nb, ns, seed, det, sparse):
+    from dmnerf_b200.helpers import sample_pdf
+    gen = torch.Generator().manual_seed(seed)
+    bins = (torch.rand(n, nb, generator=gen).sort(-1).values * 10 + 2)
+    w = torch.rand(n, nb - 1, generator=gen)
+    if sparse:
+        w = w * (torch.rand(n, nb - 1, generator=gen) < 0.2)                 # many empty bins: the 1e-5 guards matter
+    u = None if det else torch.rand(n, ns, generator=gen)
+    ref = O.sample_pdf(bins, w, ns, det=det, u=u).numpy()
+    got = sample_pdf(_cu(bins), _cu(w), ns, det=det, u=None if u is None else _cu(u)).cpu().numpy()
+    assert got.shape == ref.shape and np.isfinite(got).all()
+    assert frac_bad(got, ref, 1e-4, 1e-5) <= 2e-2           # jumps of the inverse CDF at (almost) empty bins may move a sample
+    assert got.min() >= float(bins.min()) - 1e-4 and got.max() <= float(bins.max()) + 1e-4
+    if det:
+        assert (np.diff(got, axis=-1) >= -1e-6).all()
+
+
+@settings(**COMMON)
+@given(n=st.integers(1, 70), na=st.integers(1, 130), nb=st.integers(1, 200), seed=st.integers(0, 2 ** 20), sort_b=st.booleans())
+def test_sort_concat_fuzz(n, na, nb, seed, sort_b):
+    from dmnerf_b200.helpers import sort_concat
+    gen = torch.Generator().manual_seed(seed)
+    a = (torch.rand(n, na, generator=gen) * 8).sort(-1).values
+    b = torch.rand(n, nb, generator=gen) * 8
+    b = b.sort(-1).values if sort_b else b
+    t = min(na, nb, 3)
+    b[:, :t] = a[:, :t]                                                    # ties between the two runs
+    ref = torch.sort(torch.cat([a, b], -1), -1).values
+    got = sort_concat(_cu(a), _cu(b)).cpu()
+    assert torch.equal(got, ref)
+
+
+@settings(**COMMON)
+@given(m=st.integers(1, 300), seed=st.integers(0, 2 ** 20), scale=st.sampled_from([0.01, 1.0, 20.0]))
+def test_posenc_fuzz(m, seed, scale):
+    from dmnerf_b200.embedder import get_embedder
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, 3, generator=gen) * scale
+    pe, ve = get_embedder(10)[0], get_embedder(4)[0]
+    assert max_rel_err(pe.embed(_cu(x)).cpu(), O.embed(x, 10), 1e-2) <= 1e-4
+    assert max_rel_err(ve.embed(_cu(x)).cpu(), O.embed(x, 4), 1e-2) <= 1e-4

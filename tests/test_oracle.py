@@ -149,3 +149,21 @@ def test_manipulator(golden_dir):
     # discrete decisions inside: bulk agreement (bit-exact on the generating machine)
     for got, key in ((res[0], "final_rgb"), (res[1], "final_ins"), (res[3], "tar_ins_accum")):
         assert (np.abs(got.numpy() - g[key]).max(-1) <= 1e-3).mean() >= 0.9, key
+
+
+def test_oracle_domain_properties():
+    """Size-independent properties of the path, on the oracle: sum of weights <= 1, the merged depths are sorted
+    and stay inside [near, far], deterministic importance sampling is monotone, the instance map lies in (0, 1)."""
+    gen = torch.Generator().manual_seed(3)
+    for n, s in ((5, 64), (3, 17)):
+        raw = torch.randn(n, s, 18, generator=gen) * 2
+        z = O.z_val_sample(n, 4.0, 15.0, s)
+        rd = torch.randn(n, 3, generator=gen)
+        rgb, w, depth, ins, acc = O.composite(raw, z, rd)
+        assert float(acc.max()) <= 1.0 + 1e-6 and float(w.min()) >= 0.0
+        assert float(ins.min()) > 0.0 and float(ins.max()) < 1.0
+        mid = .5 * (z[..., 1:] + z[..., :-1])
+        zs = O.sample_pdf(mid, w[..., 1:-1], 40, det=True)
+        assert bool((zs[..., 1:] >= zs[..., :-1] - 1e-6).all())
+        zf = torch.sort(torch.cat([z, zs], -1), -1).values
+        assert float(zf.min()) >= 4.0 - 1e-5 and float(zf.max()) <= 15.0 + 1e-5
