@@ -83,3 +83,27 @@ def test_posenc_fuzz(m, seed, scale):
     pe, ve = get_embedder(10)[0], get_embedder(4)[0]
     assert max_rel_err(pe.embed(_cu(x)).cpu(), O.embed(x, 10), 1e-2) <= 1e-4
     assert max_rel_err(ve.embed(_cu(x)).cpu(), O.embed(x, 4), 1e-2) <= 1e-4
+
+
+@settings(max_examples=8, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(m=st.sampled_from([1, 2, 31, 127, 128, 129, 255, 257, 640, 1000]), ins_num=st.sampled_from([1, 13, 59, 127]),
+       seed=st.integers(0, 2 ** 10))
+def test_network_kernels_ragged_batches(m, ins_num, seed):
+    """DM_NeRF.forward on the tensor-core kernel (and the fp32 kernel) for batch sizes around the 128-row tile and the
+    extremes of the object-head width, against the oracle."""
+    from dmnerf_b200 import synth, _lib
+    from dmnerf_b200.testing import model_from_weights, scale_err
+    w = synth.make_weights(500 + seed % 7, ins_num)
+    net = model_from_weights(w, DEV).eval()
+    gen = torch.Generator().manual_seed(seed)
+    pts = torch.rand(m, 3, generator=gen) * 6 - 3
+    vd = torch.randn(m, 3, generator=gen)
+    vd = vd / vd.norm(dim=-1, keepdim=True)
+    x = torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1)
+    ref = O.mlp_forward(O.to_torch(w), x).numpy()
+    with torch.no_grad():
+        for impl, tol in ((_lib.IMPL_UMMA, 1e-4), (_lib.IMPL_SIMT, 2e-5)):
+            got = net(_cu(x), impl=impl).cpu().numpy()
+            assert got.shape == ref.shape
+            for sl in (slice(0, 3), slice(3, 4), slice(4, None)):
+                assert scale_err(got[:, sl], ref[:, sl]) <= tol, (impl, m, ins_num, scale_err(got[:, sl], ref[:, sl]))
