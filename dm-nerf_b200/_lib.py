@@ -49,6 +49,11 @@ PROTOTYPES = {
     "dmnerf_sample_pdf": (C.c_int, [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
     "dmnerf_sort_concat": (C.c_int, [_f32p, _f32p, C.c_int64, C.c_int, C.c_int, _f32p, C.c_void_p]),
     "dmnerf_get_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
+    "dmnerf_get_rays_at": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p, C.c_int64, _f32p,
+                                     _f32p, C.c_void_p]),
+    "dmnerf_hungarian_costs": (C.c_int, [_f32p, C.c_void_p, C.c_int64, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "dmnerf_ins_loss_backward": (C.c_int, [_f32p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p,
+                                           _f32p, C.c_void_p]),
     "dmnerf_stratify": (C.c_int, [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int, _f32p, C.c_void_p]),
     "dmnerf_hier_sample": (C.c_int, [_f32p, _f32p, _f32p, C.c_int64, C.c_int, C.c_int, _f32p, C.c_void_p]),
     "dmnerf_act_floats_per_sample": (C.c_int, []),
@@ -116,7 +121,10 @@ def ptr(t):
     """Device (or host) pointer of a contiguous float32 tensor, or None."""
     if t is None:
         return None
-    assert t.is_contiguous(), "tensor must be contiguous"
+    import torch
+    if not t.is_contiguous() or t.dtype != torch.float32:
+        raise RuntimeError("native call needs a contiguous float32 tensor (got %s, contiguous=%s): convert it into a local "
+                           "first so the copy outlives the launch" % (t.dtype, t.is_contiguous()))
     return C.c_void_p(t.data_ptr())
 
 

@@ -43,9 +43,13 @@ def mlp_forward_rays(model, rays_o, rays_d, z, impl=_lib.IMPL_AUTO):
     slot = ctx.slot_for(model)
     ins_num = ctx.bind(slot, model)
     n, s = z.shape
+    # the converted copies must outlive the launch: a temporary freed inside the argument list would hand its block to the next
+    # same-size temporary in the caching allocator (rays_o aliasing rays_d)
+    ro, rd, zz = rays_o.reshape(-1, 3).contiguous().float(), rays_d.reshape(-1, 3).contiguous().float(), z.contiguous().float()
+    if ro.shape[0] != n or rd.shape[0] != n:
+        raise RuntimeError("mlp_forward_rays: %d / %d rays for %d depth rows" % (ro.shape[0], rd.shape[0], n))
     out = torch.empty((n, s, 4 + ins_num + 1), device=z.device, dtype=torch.float32)
-    _lib.check(ctx.lib.dmnerf_mlp_forward_rays(ctx.handle, slot, _lib.ptr(rays_o.contiguous().float()),
-                                               _lib.ptr(rays_d.contiguous().float()), _lib.ptr(z.contiguous().float()),
+    _lib.check(ctx.lib.dmnerf_mlp_forward_rays(ctx.handle, slot, _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(zz),
                                                n, s, _lib.ptr(out), impl, ctx.stream()), "dmnerf_mlp_forward_rays")
     return out
 

@@ -92,9 +92,11 @@ class CompositeFunction(torch.autograd.Function):
         n, s, c = raw.shape
         ctx = get_context(raw.device)
         d_raw = torch.empty_like(raw)
-        opt = lambda g: _lib.ptr(_f32(g)) if g is not None else None
+        # converted grads stay alive across the launch (a stride-0 expand from .sum().backward() is copied by _f32)
+        keep = [_f32(g) if g is not None else None for g in (g_rgb, g_depth, g_ins, g_w)]
         _lib.check(ctx.lib.dmnerf_composite_backward(_lib.ptr(raw), _lib.ptr(z), _lib.ptr(rd), n, s, c, int(fctx.keep),
-                                                     opt(g_rgb), opt(g_depth), None, opt(g_ins), opt(g_w), _lib.ptr(d_raw), 0,
+                                                     _lib.ptr(keep[0]), _lib.ptr(keep[1]), None, _lib.ptr(keep[2]),
+                                                     _lib.ptr(keep[3]), _lib.ptr(d_raw), 0,
                                                      ctx.stream()), "dmnerf_composite_backward")
         return d_raw, None, None, None
 
@@ -158,7 +160,6 @@ class RenderFunction(torch.autograd.Function):
         lib, st = ctx.lib, ctx.stream()
         ctx.bind(0, fctx.models[0]); ctx.bind(1, fctx.models[1])
         n, Cc = fctx.n, fctx.C
-        opt = lambda t: _lib.ptr(_f32(t)) if t is not None else None
         all_grads = []
         for net, tag, z, raw, ns in ((0, "coarse", z_c, raw_c, fctx.S), (1, "fine", z_f, raw_f, fctx.F)):
             g_raw = gd["raw_" + tag]

@@ -179,6 +179,29 @@ DMNERF_API int dmnerf_get_rays(const float* K_host, const float* c2w_host, int H
   return launch_rays(K_host, c2w_host, H, W, rays_o, rays_d, (cudaStream_t)stream);
 }
 
+DMNERF_API int dmnerf_get_rays_at(const float* K_host, const float* c2w_host, int H, int W, const int64_t* pixels, int64_t n,
+                                  float* rays_o, float* rays_d, void* stream) {
+  DMN_CHECK(K_host && c2w_host && (n == 0 || (pixels && rays_o && rays_d)), "get_rays_at: NULL argument");
+  DMN_CHECK(n >= 0, "get_rays_at: negative count");
+  return launch_rays_at(K_host, c2w_host, H, W, pixels, n, rays_o, rays_d, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_hungarian_costs(const float* pred, const int32_t* gt_row, int64_t n, int ins_num, float* cost_ce,
+                                      float* cost_siou, float* tp, float* col_sum, float* row_count, void* stream) {
+  DMN_CHECK(pred && gt_row && cost_ce && cost_siou && tp && col_sum && row_count, "hungarian_costs: NULL buffer");
+  return launch_hungarian_costs(pred, gt_row, n, ins_num, cost_ce, cost_siou, tp, col_sum, row_count, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_ins_loss_backward(const float* pred, const int32_t* gt_row, int64_t n, int ins_num,
+                                        const int32_t* row_of_col, int n_valid, const float* tp, const float* col_sum,
+                                        const float* row_count, const float* g_losses, float* d_pred, void* stream) {
+  DMN_CHECK(n >= 0, "ins_loss_backward: negative ray count");
+  DMN_CHECK(n == 0 || (pred && gt_row && row_of_col && tp && col_sum && row_count && g_losses && d_pred),
+            "ins_loss_backward: NULL buffer");
+  return launch_ins_loss_grad(pred, gt_row, n, ins_num, row_of_col, n_valid, tp, col_sum, row_count, g_losses, d_pred,
+                              (cudaStream_t)stream);
+}
+
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,
                                void* stream) {
   DMN_CHECK(n >= 0 && s >= 1, "stratify: bad sizes");

@@ -115,6 +115,8 @@ int launch_prep_z(const float* z_in, int64_t z_stride, const float* t_rand, int6
 int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int ni, float* z_fine,
                        cudaStream_t st);
 int launch_rays(const float* K9, const float* c2w12, int H, int W, float* rays_o, float* rays_d, cudaStream_t st);
+int launch_rays_at(const float* K9, const float* c2w12, int H, int W, const int64_t* pix, int64_t n, float* rays_o, float* rays_d,
+                   cudaStream_t st);
 // MLP, SIMT fp32 path.  Exactly one of x / (rays_o, rays_d, z) is used.
 int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
                     int64_t m, int s, float* out, float* acts, cudaStream_t st);
@@ -144,5 +146,11 @@ int launch_penalizer_backward(const float* raw, const float* z, const float* dep
                               float tol, float w, const void* state, const float* g_loss, float* d_raw, int accumulate,
                               cudaStream_t st);
 size_t penalizer_state_bytes();
+
+// Hungarian-matched instance loss (evaluator.cu)
+int launch_hungarian_costs(const float* pred, const int32_t* gt_row, int64_t n, int k, float* cost_ce, float* cost_siou,
+                           float* tp, float* s_sum, float* cnt, cudaStream_t st);
+int launch_ins_loss_grad(const float* pred, const int32_t* gt_row, int64_t n, int k, const int32_t* row_of_col, int n_valid,
+                         const float* tp, const float* s_sum, const float* cnt, const float* g3, float* d_pred, cudaStream_t st);
 
 }  // namespace dmnerf

@@ -233,6 +233,38 @@ __global__ void rays_kernel(Camera cam, int H, int W, float* __restrict__ rays_o
   }
 }
 
+// Rays of selected pixels only (training: get_select_full / get_select_crop, helpers.py:64-111, keep 1024-3072 of the H*W
+// rays of a frame): pix[i] = row * W + column of sample i.  Same arithmetic as rays_kernel, so the rows are bit-identical to
+// get_rays_k(...)[row, column].
+__global__ void rays_at_kernel(Camera cam, int W, const int64_t* __restrict__ pix, int64_t n, float* __restrict__ rays_o,
+                               float* __restrict__ rays_d) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t idx = pix[t];
+  const float i = (float)(idx % W), j = (float)(idx / W);
+  const float dx = __fdiv_rn(__fsub_rn(i, cam.K[2]), cam.K[0]);
+  const float dy = __fdiv_rn(__fsub_rn(j, cam.K[5]), cam.K[4]);
+  const float dz = cam.K[8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* R = cam.c2w + 4 * r;
+    rays_d[t * 3 + r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, R[0]), __fmul_rn(dy, R[1])), __fmul_rn(dz, R[2]));
+    rays_o[t * 3 + r] = R[3];
+  }
+}
+
+int launch_rays_at(const float* K9, const float* c2w12, int H, int W, const int64_t* pix, int64_t n, float* rays_o, float* rays_d,
+                   cudaStream_t st) {
+  DMN_CHECK(H >= 1 && W >= 1 && (int64_t)H * W <= (1LL << 31), "get_rays_at: bad image size %dx%d", H, W);
+  if (n == 0) return 0;
+  Camera cam;
+  for (int i = 0; i < 9; ++i) cam.K[i] = K9[i];
+  for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w12[i];
+  rays_at_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, W, pix, n, rays_o, rays_d);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
 int launch_rays(const float* K9, const float* c2w12, int H, int W, float* rays_o, float* rays_d, cudaStream_t st) {
   DMN_CHECK(H >= 1 && W >= 1 && (int64_t)H * W <= (1LL << 31), "get_rays: bad image size %dx%d", H, W);
   Camera cam;

@@ -11,4 +11,10 @@ if _ref and _os.path.exists(_os.path.join(_ref, "networks", "helpers.py")):
     _spec.loader.exec_module(_mod)
     globals().update({k: v for k, v in vars(_mod).items() if not k.startswith("__")})
 
-from dmnerf_b200.helpers import sample_pdf, z_val_sample, get_rays_k   # noqa: F401,E402
+from dmnerf_b200.helpers import sample_pdf, z_val_sample, get_rays_k, get_select_full, get_select_crop   # noqa: F401,E402
+
+# The reference functions re-exported above keep their OWN module globals: rebind the native names inside the loaded
+# reference module too, so that every remaining reference helper resolves them to the native versions.
+if "_mod" in globals():
+    for _name in ("sample_pdf", "z_val_sample", "get_rays_k", "get_select_full", "get_select_crop"):
+        setattr(_mod, _name, globals()[_name])

@@ -15,3 +15,13 @@ if _ref and _os.path.exists(_os.path.join(_ref, "networks", "manipulator.py")):
         pass
 
 from dmnerf_b200.manipulator import exchanger, manipulator_render, manipulator_nerf, manipulator   # noqa: F401,E402
+
+# manipulator_eval / manipulator_demo (manipulator.py:208-491) resolve `manipulator`, `exchanger`, ... through the reference
+# module's own globals: rebind them there, otherwise the reference drivers would keep calling the reference torch code.
+if "_mod" in globals():
+    from dmnerf_b200.helpers import sample_pdf as _sample_pdf, get_rays_k as _get_rays_k, z_val_sample as _z_val_sample
+    for _name, _fn in (("exchanger", exchanger), ("manipulator_render", manipulator_render),
+                       ("manipulator_nerf", manipulator_nerf), ("manipulator", manipulator), ("sample_pdf", _sample_pdf),
+                       ("get_rays_k", _get_rays_k), ("z_val_sample", _z_val_sample)):
+        if hasattr(_mod, _name):
+            setattr(_mod, _name, _fn)

@@ -1,0 +1,120 @@
+"""networks/evaluator.py:19-74 on the native kernels: the Hungarian-matched instance loss of the training step.
+
+    ins_criterion(pred_ins, gt_labels, ins_num) -> (ins_loss_sum, valid_ce, invalid_ce, valid_siou)     evaluator.py:19-37
+    hungarian(pred_ins, gt_ins, valid_ins_num, ins_num) -> (cost_ce, cost_siou, order_row, order_col)   evaluator.py:41-74
+    img2mse, mse2psnr, to8b                                                                             evaluator.py:11,14,15
+
+The two [ins x ins] cost matrices come out of ONE pass over the rays (csrc/evaluator.cu: gt is one-hot, so the reference's
+[ins x ins x N] broadcast collapses to per-row sums); the assignment is scipy's linear_sum_assignment on the host, exactly as
+in the reference (its only device->host hop: the [valid x ins] score matrix); the matched loss and its gradient w.r.t. the
+rendered instance map are evaluated on the device (autograd Function -> dmnerf_ins_loss_backward).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import get_context
+
+img2mse = lambda x, y: torch.mean((x - y) ** 2)                                        # evaluator.py:11
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)                              # evaluator.py:14
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))   # evaluator.py:15
+
+
+def _costs(pred, gt_row):
+    """pred [N,K] float32 contiguous, gt_row [N] int32 -> dict of device tensors (cost matrices + backward sums)."""
+    n, k = pred.shape
+    dev = pred.device
+    e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    out = {"cost_ce": e(k, k), "cost_siou": e(k, k), "tp": e(k, k), "col_sum": e(k), "row_count": e(k)}
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.dmnerf_hungarian_costs(_lib.ptr(pred), gt_row.data_ptr(), n, k, _lib.ptr(out["cost_ce"]),
+                                              _lib.ptr(out["cost_siou"]), _lib.ptr(out["tp"]), _lib.ptr(out["col_sum"]),
+                                              _lib.ptr(out["row_count"]), ctx.stream()), "dmnerf_hungarian_costs")
+    return out
+
+
+def _reorder(cost_matrix, valid_ins_num, ins_num):
+    """evaluator.py:42-50 (host): assignment on the valid rows, unmatched prediction channels appended."""
+    from scipy.optimize import linear_sum_assignment
+    scores = cost_matrix[:valid_ins_num].detach().cpu().numpy()
+    row_ind, col_ind = linear_sum_assignment(scores)
+    if ins_num - valid_ins_num > 0:
+        unmapped = np.array(list(set(range(ins_num)) - set(col_ind)))
+        col_ind = np.concatenate([col_ind, unmapped])
+    return row_ind, col_ind
+
+
+def _rows_of_dense_gt(gt_ins):
+    """Dense one-hot-or-zero gt_ins [N,K] -> row index per ray (-1 where the ray has no label)."""
+    has = gt_ins.sum(-1) > 0
+    return torch.where(has, gt_ins.argmax(-1), torch.full_like(has, -1, dtype=torch.int64)).to(torch.int32)
+
+
+def hungarian(pred_ins, gt_ins, valid_ins_num, ins_num):
+    """evaluator.py:41-74 for CUDA tensors (no gradient: use ins_criterion for the differentiable loss)."""
+    if not pred_ins.is_cuda:
+        raise RuntimeError("hungarian: expected CUDA tensors (no CPU fallback)")
+    pred = pred_ins.detach().contiguous().float()
+    gt_row = _rows_of_dense_gt(gt_ins.to(pred.device)).contiguous()
+    c = _costs(pred, gt_row)
+    order_row, order_col = _reorder(c["cost_ce"] + c["cost_siou"], valid_ins_num, ins_num)
+    return c["cost_ce"], c["cost_siou"], order_row, order_col
+
+
+class _MatchedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, pred_ins, gt_row, n_valid):
+        pred = pred_ins.detach().contiguous().float()
+        n, k = pred.shape
+        c = _costs(pred, gt_row)
+        order_row, order_col = _reorder(c["cost_ce"] + c["cost_siou"], n_valid, k)
+        dev = pred.device
+        rows = torch.as_tensor(np.asarray(order_row), device=dev, dtype=torch.int64)
+        cols = torch.as_tensor(np.asarray(order_col[:n_valid]), device=dev, dtype=torch.int64)
+        valid_ce = c["cost_ce"][rows, cols].mean()                                          # evaluator.py:28
+        valid_siou = c["cost_siou"][rows, cols].mean()                                      # evaluator.py:34
+        row_of_col = torch.full((k,), -1, device=dev, dtype=torch.int32)
+        row_of_col[cols] = rows.to(torch.int32)
+        if len(order_col) != n_valid:                                                       # evaluator.py:30-33
+            un = torch.as_tensor(np.asarray(order_col[n_valid:]), device=dev, dtype=torch.int64)
+            invalid_ce = c["col_sum"][un].sum() / float(n * len(un))
+        else:
+            invalid_ce = torch.zeros((), device=dev)
+        fctx.save_for_backward(pred, gt_row, row_of_col, c["tp"], c["col_sum"], c["row_count"])
+        fctx.n_valid = int(n_valid)
+        fctx.in_shape = pred_ins.shape
+        fctx.order = (order_row, order_col)
+        return valid_ce, invalid_ce, valid_siou
+
+    @staticmethod
+    def backward(fctx, g_ce, g_inv, g_siou):
+        pred, gt_row, row_of_col, tp, col_sum, row_count = fctx.saved_tensors
+        n, k = pred.shape
+        zero = pred.new_zeros(())
+        g3 = torch.stack([(g if g is not None else zero).reshape(()).float() for g in (g_ce, g_inv, g_siou)]).contiguous()
+        d_pred = torch.empty_like(pred)
+        ctx = get_context(pred.device)
+        _lib.check(ctx.lib.dmnerf_ins_loss_backward(_lib.ptr(pred), gt_row.data_ptr(), n, k, row_of_col.data_ptr(), fctx.n_valid,
+                                                    _lib.ptr(tp), _lib.ptr(col_sum), _lib.ptr(row_count), _lib.ptr(g3),
+                                                    _lib.ptr(d_pred), ctx.stream()), "dmnerf_ins_loss_backward")
+        return d_pred.reshape(fctx.in_shape), None, None
+
+
+def ins_criterion(pred_ins, gt_labels, ins_num):
+    """evaluator.py:19-37.  pred_ins [N, ins_num] (rendered instance probabilities, CUDA), gt_labels [N] (object ids)."""
+    if not pred_ins.is_cuda:
+        raise RuntimeError("ins_criterion: expected CUDA tensors (no CPU fallback)")
+    if pred_ins.dim() != 2 or pred_ins.shape[1] != ins_num or gt_labels.shape[0] != pred_ins.shape[0]:
+        raise RuntimeError("ins_criterion: pred_ins %s / gt_labels %s / ins_num %d are inconsistent"
+                           % (tuple(pred_ins.shape), tuple(gt_labels.shape), ins_num))
+    labels = gt_labels.to(pred_ins.device).reshape(-1)
+    valid = torch.unique(labels)                                                            # evaluator.py:21 (sorted)
+    n_valid = int(valid.numel())
+    if n_valid > ins_num:
+        raise RuntimeError("ins_criterion: %d distinct labels for ins_num %d" % (n_valid, ins_num))
+    gt_row = torch.searchsorted(valid, labels).to(torch.int32).contiguous()                 # column of the one-hot, :25
+    valid_ce, invalid_ce, valid_siou = _MatchedLoss.apply(pred_ins, gt_row, n_valid)
+    if n_valid == ins_num:
+        invalid_ce = torch.tensor([0], device=pred_ins.device)                              # evaluator.py:33
+    ins_loss_sum = valid_ce + invalid_ce + valid_siou                                       # evaluator.py:36
+    return ins_loss_sum, valid_ce, invalid_ce, valid_siou

@@ -16,7 +16,7 @@ from . import _lib
 from .engine import get_context
 from .autograd import mlp_forward_rays
 from .render import composite, _check_embedders
-from .helpers import sample_pdf
+from .helpers import sample_pdf, sort_concat
 
 
 def exchanger(ori_raw, tar_raws, ori_raw_pred, tar_raw_preds, move_labels):
@@ -79,7 +79,7 @@ def manipulator(position_embedder, view_embedder, model_coarse, model_fine, ori_
         _, w, _, _ = manipulator_render(coarse_raw, coarse_z, rays[1])
         mid = .5 * (coarse_z[..., 1:] + coarse_z[..., :-1])
         z_s = draw(mid, w[..., 1:-1])
-        z_full, _ = torch.sort(torch.cat([coarse_z, z_s], -1), -1)
+        z_full = sort_concat(coarse_z, z_s)                                   # sort(cat(.)) as one kernel
         raw_full, _ = nerf(rays, model_fine, z_full)
         _, _, _, ins_acc = manipulator_render(raw_full, z_full, rays[1])
         return z_s, ins_acc
@@ -98,11 +98,11 @@ def manipulator(position_embedder, view_embedder, model_coarse, model_fine, ori_
         _, ori_w, _, _ = manipulator_render(ori_raw, ori_z, ori_rays[1])
         mid = .5 * (ori_z[..., 1:] + ori_z[..., :-1])
         ori_samples = draw(mid, ori_w[..., 1:-1])
-        all_tar = torch.cat(tar_samples, -1)
-        ori_z2, _ = torch.sort(torch.cat([ori_z, ori_samples, all_tar], -1), -1)
+        extra = torch.cat([ori_samples] + tar_samples, -1)                     # samples every second-pass ray set shares
+        ori_z2 = sort_concat(ori_z, extra)
         ori_raw2, _ = nerf(ori_rays, model_fine, ori_z2)
         for idx, tar_rays in enumerate(f_tar_rays):
-            t_z2, _ = torch.sort(torch.cat([tar_zs[idx], ori_samples, all_tar], -1), -1)
+            t_z2 = sort_concat(tar_zs[idx], extra)
             tar_raws[idx], _ = nerf(tar_rays, model_fine, t_z2)
         ori_raw2, _, _, _ = exchanger(ori_raw2, tar_raws, ori_ins_acc, tar_accs, args.target_labels)
         final_rgb, _, _, final_ins = manipulator_render(ori_raw2, ori_z2, ori_rays[1])

@@ -49,3 +49,41 @@ def raw_errs(got, ref):
     got = np.asarray(got); ref = np.asarray(ref)
     groups = (slice(0, 3), slice(3, 4), slice(4, None))
     return max(scale_err(got[..., g], ref[..., g]) for g in groups), max(rel_l2(got[..., g], ref[..., g]) for g in groups)
+
+
+# ---- error-distribution statistics of a rendered map against the reference (parity at scale: tests/test_gpu_scale.py,
+#      tools/parity_at_scale.py, smoke()) ----------------------------------------------------------------------------------
+MAP_KEYS = ("rgb_coarse", "depth_coarse", "acc_coarse", "ins_coarse", "rgb_fine", "depth_fine", "acc_fine", "ins_fine")
+
+
+def error_stats(got, ref, rtol=1e-4):
+    """Per-RAY error distribution of a map [N] or [N,C] against the reference.  A value is "within rtol" when
+    |got - ref| <= rtol * max(|ref|, 0.1 * scale), scale = max |ref| over the map (values far below the map's scale are
+    judged against a tenth of it, not against themselves); a ray is within when all its channels are.  Errors are reported
+    relative to the scale: median / p99 / max over rays of the per-ray max error; psnr = 10 log10(scale^2 / mse)."""
+    got = np.asarray(got, dtype=np.float64).reshape(len(got), -1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(len(ref), -1)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = np.abs(got - ref)
+    ok = (err <= rtol * np.maximum(np.abs(ref), 0.1 * scale)).all(axis=1)
+    per_ray = err.max(axis=1) / scale
+    mse = float(np.mean((got - ref) ** 2))
+    return {"frac_within": float(ok.mean()), "median": float(np.median(per_ray)), "p99": float(np.quantile(per_ray, 0.99)),
+            "max": float(per_ray.max()), "psnr": float(10.0 * np.log10(scale * scale / max(mse, 1e-300))), "n": int(len(got))}
+
+
+def parity_table(ours, twin, ref, keys=MAP_KEYS):
+    """{key: {"ours": stats, "twin": stats}}: our maps and the reference's own fp64 twin, both against the fp32 reference."""
+    to_np = lambda t: t.detach().cpu().double().numpy() if hasattr(t, "detach") else np.asarray(t)
+    return {k: {"ours": error_stats(to_np(ours[k]), to_np(ref[k])), "twin": error_stats(to_np(twin[k]), to_np(ref[k]))}
+            for k in keys if k in ours and k in twin and k in ref}
+
+
+def format_parity_table(name, table):
+    lines = ["| %s | within 1e-4 (ours / fp64 twin) | median | p99 | max | PSNR dB |" % name, "|---|---|---|---|---|---|"]
+    for k, row in table.items():
+        o, t = row["ours"], row["twin"]
+        lines.append("| %s | %.4f / %.4f | %.1e / %.1e | %.1e / %.1e | %.1e / %.1e | %.1f / %.1f |" %
+                     (k, o["frac_within"], t["frac_within"], o["median"], t["median"], o["p99"], t["p99"], o["max"], t["max"],
+                      o["psnr"], t["psnr"]))
+    return "\n".join(lines)

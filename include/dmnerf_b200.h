@@ -113,6 +113,26 @@ DMNERF_API int dmnerf_sort_concat(const float* a, const float* b, int64_t n, int
  * -> rays_o, rays_d [H*W, 3] on the device, pixel-major like the reference's reshape(-1, 3). */
 DMNERF_API int dmnerf_get_rays(const float* K_host, const float* c2w_host, int H, int W, float* rays_o, float* rays_d, void* stream);
 
+/* The rays of selected pixels only -- the training-side ray selection get_select_full / get_select_crop,
+ * networks/helpers.py:64-111, builds all H*W rays per iteration to keep 1024-3072 of them: pixels [n] (DEVICE, int64,
+ * row * W + column) -> rays_o, rays_d [n,3], bit-identical to the rows get_rays_k would produce. */
+DMNERF_API int dmnerf_get_rays_at(const float* K_host, const float* c2w_host, int H, int W, const int64_t* pixels, int64_t n,
+                                  float* rays_o, float* rays_d, void* stream);
+
+/* Hungarian-matched instance loss, networks/evaluator.py:19-74 (ins_criterion / hungarian; train_dmsr.py:38-45).
+ * dmnerf_hungarian_costs: pred [N,ins_num] (rendered instance probabilities), gt_row [N] (int32: index of the ray's label among
+ * the sorted distinct labels of the batch, evaluator.py:21-25) -> cost_ce, cost_siou [ins_num,ins_num] (row = ground-truth
+ * object, column = prediction channel; evaluator.py:60-67) plus the sums the backward needs: tp [ins_num,ins_num],
+ * col_sum [ins_num] (sum_n pred), row_count [ins_num].  The assignment (scipy linear_sum_assignment, evaluator.py:45-47) runs on
+ * the host on the [valid x ins_num] corner of cost_ce + cost_siou, as in the reference.
+ * dmnerf_ins_loss_backward: d_pred [N,ins_num] = g[0] d valid_ce + g[1] d invalid_ce + g[2] d valid_siou (evaluator.py:27-36);
+ * row_of_col [ins_num] (DEVICE int32) = matched ground-truth row of every prediction channel or -1; g_losses = 3 DEVICE floats. */
+DMNERF_API int dmnerf_hungarian_costs(const float* pred, const int32_t* gt_row, int64_t n, int ins_num, float* cost_ce,
+                                      float* cost_siou, float* tp, float* col_sum, float* row_count, void* stream);
+DMNERF_API int dmnerf_ins_loss_backward(const float* pred, const int32_t* gt_row, int64_t n, int ins_num,
+                                        const int32_t* row_of_col, int n_valid, const float* tp, const float* col_sum,
+                                        const float* row_count, const float* g_losses, float* d_pred, void* stream);
+
 /* Coarse depths, networks/render.py:40-47: z_out[n, i] = z_in row (shared when z_row_stride = 0), jittered inside its
  * stratum by t_rand [N,S] when given. */
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,

@@ -302,3 +302,39 @@ def manipulator(p_coarse, p_fine, ori_rays, f_tar_rays, n_samples, n_importance,
     ori_raw2, _, _, _ = exchanger(ori_raw2, tar_raws, ori_ins_acc, tar_accs, target_labels)   # :201
     final_rgb, _, _, final_ins = manipulator_render(ori_raw2, ori_z2, ori_rays[1])    # :203
     return final_rgb, final_ins, tar_rgb, tar_accs[-1]
+
+
+def hungarian(pred_ins, gt_ins, valid_ins_num, ins_num):
+    """Matching, reference networks/evaluator.py:41-74.  pred_ins, gt_ins [N, ins_num] -> cost_ce, cost_siou
+    [ins_num, ins_num] (row = ground-truth object, column = prediction channel), order_row, order_col."""
+    from scipy.optimize import linear_sum_assignment
+    pred = pred_ins.permute([1, 0])[None, :, :]                                    # :52-55
+    gt = gt_ins.permute([1, 0])[:, None, :]
+    cost_ce = torch.mean(-gt * torch.log(pred + 1e-8) - (1 - gt) * torch.log(1 - pred + 1e-8), dim=-1)   # :57
+    tp = torch.sum(pred * gt, dim=-1)                                              # :60-64
+    fp = torch.sum(pred, dim=-1) - tp
+    fn = torch.sum(gt, dim=-1) - tp
+    cost_siou = 1.0 - tp / (tp + fp + fn + 1e-6)
+    with torch.no_grad():                                                          # reorder, :42-50
+        scores = (cost_ce + cost_siou)[:valid_ins_num].cpu().numpy()
+        row_ind, col_ind = linear_sum_assignment(scores)
+        if ins_num - valid_ins_num > 0:
+            unmapped = np.array(list(set(range(ins_num)) - set(col_ind)))
+            col_ind = np.concatenate([col_ind, unmapped])
+    return cost_ce, cost_siou, row_ind, col_ind
+
+
+def ins_criterion(pred_ins, gt_labels, ins_num):
+    """Hungarian-matched instance loss, reference networks/evaluator.py:19-37.  Returns (sum, valid_ce, invalid_ce, valid_siou)."""
+    valid = torch.unique(gt_labels)                                                # :21
+    gt_ins = torch.zeros(size=(gt_labels.shape[0], ins_num), dtype=pred_ins.dtype)
+    n_valid = len(valid)
+    gt_ins[..., :n_valid] = F.one_hot(gt_labels.long())[..., valid.long()].to(pred_ins.dtype)   # :25
+    cost_ce, cost_siou, order_row, order_col = hungarian(pred_ins, gt_ins, n_valid, ins_num)
+    valid_ce = torch.mean(cost_ce[order_row, order_col[:n_valid]])                 # :28
+    if not (len(order_col) == n_valid):
+        invalid_ce = torch.mean(pred_ins[:, order_col[n_valid:]])                  # :31
+    else:
+        invalid_ce = torch.tensor([0])
+    valid_siou = torch.mean(cost_siou[order_row, order_col[:n_valid]])             # :34
+    return valid_ce + invalid_ce + valid_siou, valid_ce, invalid_ce, valid_siou

@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from dmnerf_b200 import synth, _lib
-from dmnerf_b200.testing import make_models
+from dmnerf_b200.testing import make_models, model_from_weights
 
 DEV = "cuda"
 
@@ -171,25 +171,93 @@ def test_exchanger_matches_reference(golden_dir):
     assert int((out.cpu() != torch.from_numpy(g["ex_ori_raw"])).any(-1).sum()) > 50       # the case does exchange samples
 
 
+def _agree(a, b, tol=2e-3):
+    """fraction of rays whose map rows agree to `tol` (max over channels)"""
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b).max(-1) <= tol).mean())
+
+
+def _twin_manipulator(wc, wf, ori, f_tar, S, NI, near, far, labels, us):
+    """The oracle edit pipeline carried out in fp64 on the same inputs: how often do the discrete decisions inside
+    (arg-max labels, inverse-CDF bins) survive a change of arithmetic at all?"""
+    from oracle import dmnerf_oracle as O
+    d = torch.float64
+    with torch.no_grad():
+        return O.manipulator(O.to_torch(wc, d), O.to_torch(wf, d), ori.double(), [t.double() for t in f_tar], S, NI, near, far,
+                             labels, us=[u.double() for u in us])
+
+
 @pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_UMMA])
 def test_manipulator_pipeline_matches_reference(golden_dir, impl):
     """manipulator (networks/manipulator.py:137-205): two moved objects, same uniforms as the reference run.  The pipeline
-    contains discrete decisions (arg-max labels, importance sampling), so agreement is required for the bulk of the rays:
-    the coarse target render everywhere, the edited maps on >= 85 % of the rays to 2e-3."""
+    contains discrete decisions (arg-max labels, importance sampling), so agreement with the reference is measured as the
+    fraction of rays whose edited maps match to 2e-3 -- and the yard-stick is the reference's OWN arithmetic in fp64 on the
+    same inputs: the native path must agree with the fp32 reference as often as that twin does (40 rays: one ray = 0.025)."""
     from dmnerf_b200.manipulator import manipulator
     from dmnerf_b200.embedder import get_embedder
     g, nc, nf = _manip_setup(golden_dir)
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    labels = [int(v) for v in g["labels"]]
     args = types.SimpleNamespace(N_samples=int(g["n_samples"]), N_importance=int(g["n_importance"]), near=float(g["near"]),
-                                 far=float(g["far"]), target_labels=[int(v) for v in g["labels"]])
+                                 far=float(g["far"]), target_labels=labels)
     us = [cu(u) for u in g["us"]]
     rgb, ins, tar_rgb, tar_acc = manipulator(get_embedder(10)[0], get_embedder(4)[0], nc, nf, cu(g["ori"]), cu(g["f_tar"]), args,
                                              us=us, impl=impl)
     assert rgb.shape == g["final_rgb"].shape and ins.shape == g["final_ins"].shape and tar_acc.shape == g["tar_ins_accum"].shape
     np.testing.assert_allclose(tar_rgb.cpu().numpy(), g["tar_rgb"], rtol=0, atol=2e-4)
-    ok_rgb = (np.abs(rgb.cpu().numpy() - g["final_rgb"]).max(-1) <= 2e-3).mean()
-    ok_ins = (np.abs(ins.cpu().numpy() - g["final_ins"]).max(-1) <= 2e-3).mean()
-    assert ok_rgb >= 0.85 and ok_ins >= 0.85, (ok_rgb, ok_ins)
+    ins_num = int(g["ins_num"])
+    wc, wf = synth.make_weights(int(g["seed_c"]), ins_num), synth.make_weights(int(g["seed_f"]), ins_num)
+    wc["ins_linear.weight"], wc["ins_linear.bias"] = g["ins_w_c"], g["ins_b_c"]
+    wf["ins_linear.weight"], wf["ins_linear.bias"] = g["ins_w_f"], g["ins_b_f"]
+    twin = _twin_manipulator(wc, wf, torch.from_numpy(g["ori"]), list(torch.from_numpy(g["f_tar"])), args.N_samples,
+                             args.N_importance, args.near, args.far, labels, [torch.from_numpy(u) for u in g["us"]])
+    for ours, ref, tw, what in ((rgb, g["final_rgb"], twin[0], "rgb"), (ins, g["final_ins"], twin[1], "ins")):
+        r_ours, r_twin = _agree(ours, ref), _agree(tw, ref)
+        print("manipulator golden case, %s: ours %.3f, fp64 twin %.3f of rays within 2e-3" % (what, r_ours, r_twin))
+        assert r_ours >= r_twin - 0.05, (what, r_ours, r_twin)
+
+
+@pytest.mark.parametrize("impl", [_lib.IMPL_SIMT, _lib.IMPL_UMMA])
+def test_manipulator_pipeline_agreement_at_512_rays(impl):
+    """The same comparison on 512 rays (three moved objects), the fp32 oracle (pinned bit for bit to the reference by
+    oracle/make_golden_manipulator.py) run live as the reference, its fp64 twin as the yard-stick."""
+    from dmnerf_b200.manipulator import manipulator
+    from dmnerf_b200.embedder import get_embedder
+    from oracle import dmnerf_oracle as O
+    ins_num, n, S, NI = 13, 512, 16, 32
+    wc, wf = synth.make_weights(31, ins_num), synth.make_weights(32, ins_num)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for w in (wc, wf):                                   # wide instance heads: every label (and "empty") wins somewhere
+        w["ins_linear.weight"] = (w["ins_linear.weight"] * 400).astype(np.float32)
+        w["ins_linear.bias"] = (0.3 * rng.standard_normal(ins_num + 1)).astype(np.float32)
+    wl = synth.workload("dmsr_study")
+    sel = np.linspace(0, 307199, n).astype(np.int64)
+    ro, rd = torch.from_numpy(wl["rays_o"][sel]), torch.from_numpy(wl["rays_d"][sel])
+    ori = torch.stack([ro, rd], 0)
+    tars = []
+    for ang, sh in ((0.3, (0.4, -0.2, 0.1)), (-0.2, (-0.3, 0.1, 0.25)), (0.1, (0.1, 0.3, -0.2))):
+        c, s_ = float(np.cos(ang)), float(np.sin(ang))
+        R = torch.tensor([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], dtype=torch.float32)
+        tars.append(torch.stack([ro @ R.T + torch.tensor(sh), rd @ R.T], 0))
+    labels = [2, 7, 11]
+    gen = torch.Generator().manual_seed(11)
+    us = [torch.rand(n, NI, generator=gen) for _ in range(2 + len(tars))]
+    near, far = float(wl["near"]), float(wl["far"])
+    with torch.no_grad():
+        ref = O.manipulator(O.to_torch(wc), O.to_torch(wf), ori, tars, S, NI, near, far, labels, us=us)
+    twin = _twin_manipulator(wc, wf, ori, tars, S, NI, near, far, labels, us)
+    nc, nf = model_from_weights(wc, "cuda").eval(), model_from_weights(wf, "cuda").eval()
+    args = types.SimpleNamespace(N_samples=S, N_importance=NI, near=near, far=far, target_labels=labels)
+    before = _lib.launch_count()
+    got = manipulator(get_embedder(10)[0], get_embedder(4)[0], nc, nf, ori.cuda(), torch.stack(tars, 0).cuda(), args,
+                      us=[u.cuda() for u in us], impl=impl)
+    assert _lib.launch_count() - before >= 20
+    np.testing.assert_allclose(got[2].cpu().numpy(), ref[2].numpy(), rtol=0, atol=2e-4)      # coarse render of the last target
+    for i, what in ((0, "final_rgb"), (1, "final_ins"), (3, "tar_ins_accum")):
+        r_ours, r_twin = _agree(got[i], ref[i]), _agree(twin[i], ref[i])
+        print("manipulator 512 rays, %s: ours %.3f, fp64 twin %.3f of rays within 2e-3" % (what, r_ours, r_twin))
+        assert r_ours >= r_twin - 0.02, (what, r_ours, r_twin)
 
 
 def test_point_query_matches_embedded_forward():

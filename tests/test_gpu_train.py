@@ -256,3 +256,128 @@ def test_emptiness_penalizer_matches_reference(golden_dir, tag):
     z0 = torch.zeros(0, 64, device=DEV)
     l0 = ins_penalizer(torch.zeros(0, 64, 18, device=DEV), z0, torch.zeros(0, device=DEV), torch.zeros(0, 3, device=DEV), args)
     assert float(l0) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_hungarian_instance_loss_matches_reference(golden_dir, tag):
+    """networks/evaluator.py:19-74 on the native kernels: cost matrices, assignment, loss parts and d loss / d pred against the
+    values the unmodified reference produced (tests/golden/evaluator.npz, oracle/make_golden_evaluator.py)."""
+    from dmnerf_b200.evaluator import ins_criterion, hungarian
+    g = load(golden_dir, "evaluator.npz")
+    k = int(g["k_" + tag])
+    pred = cu(g["pred_" + tag]).requires_grad_(True)
+    lab = cu(g["labels_" + tag])
+    before = _lib.launch_count()
+    parts = ins_criterion(pred, lab, k)
+    parts[0].sum().backward()
+    assert _lib.launch_count() - before >= 2
+    got = np.array([float(x.detach().float().sum()) for x in parts])
+    np.testing.assert_allclose(got, g["loss_" + tag], rtol=1e-5, atol=1e-7)
+    gref = g["grad_" + tag]
+    assert scale_err(pred.grad.cpu().numpy(), gref) <= 1e-5
+    np.testing.assert_allclose(pred.grad.cpu().numpy(), gref, rtol=2e-4, atol=1e-9)
+    valid = torch.unique(lab)
+    gt = torch.zeros(lab.shape[0], k, device=DEV)
+    gt[:, :len(valid)] = torch.nn.functional.one_hot(lab.long())[..., valid.long()].float()
+    ce, siou, rows, cols = hungarian(pred.detach(), gt, len(valid), k)
+    np.testing.assert_allclose(ce.cpu().numpy(), g["cost_ce_" + tag], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(siou.cpu().numpy(), g["cost_siou_" + tag], rtol=1e-5, atol=1e-6)
+    assert list(cols[:len(valid)]) == list(g["order_col_" + tag][:len(valid)])
+    assert sorted(cols) == list(range(k))
+
+
+def test_ray_selection_generates_only_the_selected_rays(golden_dir):
+    """get_select_full / get_select_crop (helpers.py:64-111) natively: same numpy draws, rays bit-identical to the rows of the
+    full get_rays_k grid, colours / labels gathered at the same pixels."""
+    from dmnerf_b200.helpers import get_select_full, get_select_crop, get_rays_k
+    wl = synth.workload("dmsr_study")
+    H, W = 96, 128
+    K = synth.dmsr_intrinsics(H, W)
+    pose = cu(wl["c2w"])
+    gen = torch.Generator().manual_seed(5)
+    rgb = torch.rand(H, W, 3, generator=gen).to(DEV)
+    lab = torch.randint(0, 13, (H, W), generator=gen).to(torch.int16).to(DEV)
+    ro, rd = get_rays_k(H, W, K, pose)
+    np.random.seed(11)
+    expect = np.random.choice(H * W, size=[1024], replace=False)
+    np.random.seed(11)
+    tc, ti, rays = get_select_full(rgb, pose, K, lab, 1024)
+    e = torch.from_numpy(expect).to(DEV)
+    assert torch.equal(rays[0], ro.reshape(-1, 3)[e]) and torch.equal(rays[1], rd.reshape(-1, 3)[e])
+    assert torch.equal(tc, rgb.reshape(-1, 3)[e]) and torch.equal(ti, lab.reshape(-1)[e])
+    # crop variant: 30 % labelled pixels last, the rest from the crop mask, in the reference's draw order
+    crop = np.zeros((H, W), dtype=np.int64); crop[8:80, 10:100] = 1
+    ins_index = np.flatnonzero((crop.reshape(-1) == 1) & (np.arange(H * W) % 7 == 0))
+    np.random.seed(12)
+    n_ins = int(1000 * 0.3)
+    labeled = ins_index[np.random.choice(len(ins_index), size=[n_ins], replace=False)]
+    crop_idx = np.where(crop.reshape(-1) == 1)[0]
+    n_un = len(set(crop_idx) - set(labeled))
+    unl = crop_idx[np.random.choice(n_un, size=[1000 - n_ins], replace=False)]
+    np.random.seed(12)
+    tc, ti, rays, got_n = get_select_crop(rgb, pose, K, lab, ins_index, crop, 1000)
+    sel = torch.from_numpy(np.concatenate([unl, labeled])).to(DEV)
+    assert got_n == n_ins and rays.shape == (2, 1000, 3)
+    assert torch.equal(rays[1], rd.reshape(-1, 3)[sel]) and torch.equal(tc, rgb.reshape(-1, 3)[sel])
+    assert torch.equal(ti, lab.reshape(-1)[torch.from_numpy(labeled).to(DEV)])
+
+
+def test_reference_training_iteration_through_the_dropin_imports():
+    """One iteration of train_dmsr.py:23-64 written against the drop-in `networks` package exactly as the reference script
+    imports it (ray selection -> dm_nerf -> MSE + Hungarian instance loss + emptiness penalizer -> backward -> Adam), every
+    stage on the native kernels (launch counter) and making progress over a few steps."""
+    import sys
+    drop = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dm-nerf_b200", "dropin")
+    saved = {k: v for k, v in sys.modules.items() if k == "networks" or k.startswith("networks.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, drop)
+    try:
+        from networks.render import dm_nerf
+        from networks.dm_nerf import get_embedder, DM_NeRF
+        from networks.penalizer import ins_penalizer
+        from networks.helpers import get_select_full, z_val_sample
+        from networks.evaluator import ins_criterion, img2mse, mse2psnr
+        import networks.render as nr_mod
+        assert "dmnerf_b200" in nr_mod.dm_nerf.__module__
+        H, W, ins_num, n_train = 48, 64, 13, 512
+        wl = synth.workload("dmsr_study")
+        K = synth.dmsr_intrinsics(H, W)
+        pose = cu(wl["c2w"])
+        gen = torch.Generator().manual_seed(9)
+        gt_rgb = torch.rand(H, W, 3, generator=gen).to(DEV)
+        gt_label = (torch.arange(H * W).reshape(H, W) * 7 // (H * W)).to(torch.int16).to(DEV)      # 7 objects present
+        torch.manual_seed(0); np.random.seed(0)
+        pe, _ = get_embedder(10); ve, _ = get_embedder(4)
+        mc, mf = DM_NeRF(8, 256, 63, 27, [4], ins_num).to(DEV), DM_NeRF(8, 256, 63, 27, [4], ins_num).to(DEV)
+        mc.train(); mf.train()
+        opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=5e-4, betas=(0.9, 0.999))
+        args = types.SimpleNamespace(perturb=1.0, N_importance=128, is_train=True, N_ins=None, N_train=n_train, near=4.0, far=15.0,
+                                     N_samples=64, ins_num=ins_num, tolerance=0.05, deta_w=0.05, penalize=True)
+        z_val_coarse = z_val_sample(args.N_train, args.near, args.far, args.N_samples, device=DEV)
+        before = _lib.launch_count()
+        losses = []
+        for it in range(3):
+            np.random.seed(1)                                   # same pixels every iteration: the loss must go down
+            target_c, target_i, batch_rays = get_select_full(gt_rgb, pose, K, gt_label, args.N_train)
+            all_info = dm_nerf(batch_rays, pe, ve, mc, mf, z_val_coarse, args)
+            rgb_loss = img2mse(all_info["rgb_coarse"], target_c) + img2mse(all_info["rgb_fine"], target_c)
+            ins_c = ins_criterion(all_info["ins_coarse"], target_i, args.ins_num)
+            ins_f = ins_criterion(all_info["ins_fine"], target_i, args.ins_num)
+            total = ins_c[0] + ins_f[0] + rgb_loss
+            total = total + ins_penalizer(all_info["raw_coarse"], all_info["z_vals_coarse"], all_info["depth_coarse"], batch_rays[1], args) \
+                + ins_penalizer(all_info["raw_fine"], all_info["z_vals_fine"], all_info["depth_fine"], batch_rays[1], args)
+            opt.zero_grad()
+            total.backward()
+            opt.step()
+            assert torch.isfinite(mse2psnr(img2mse(all_info["rgb_fine"], target_c))).all()
+            assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in list(mc.parameters()) + list(mf.parameters()))
+            assert float(mf.ins_linear.weight.grad.abs().max()) > 0 and float(mc.mlps[0].weight.grad.abs().max()) > 0
+            losses.append(float(total.sum()))
+        assert _lib.launch_count() - before > 60          # ray selection, render, losses, backward: all native launches
+        assert losses[-1] < losses[0], losses
+    finally:
+        sys.path.remove(drop)
+        for k in [k for k in sys.modules if k == "networks" or k.startswith("networks.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -130,6 +130,26 @@ def test_penalizer(golden_dir):
         close(raw.grad, g["grad_" + tag], atol=1e-9)
 
 
+def test_evaluator(golden_dir):
+    """Oracle Hungarian-matched instance loss (networks/evaluator.py:19-74) against the reference's loss parts, cost matrices,
+    assignment and gradient w.r.t. the rendered instance map."""
+    g = load(golden_dir, "evaluator.npz")
+    for tag in ("a", "b", "c"):
+        k = int(g["k_" + tag])
+        pred = torch.from_numpy(g["pred_" + tag]).clone().requires_grad_(True)
+        lab = torch.from_numpy(g["labels_" + tag])
+        parts = O.ins_criterion(pred, lab, k)
+        parts[0].sum().backward()
+        close(torch.stack([x.detach().float().sum() for x in parts]), g["loss_" + tag])
+        close(pred.grad, g["grad_" + tag], atol=1e-9)
+        valid = torch.unique(lab)
+        gt = torch.zeros(lab.shape[0], k)
+        gt[:, :len(valid)] = torch.nn.functional.one_hot(lab.long())[..., valid.long()]
+        ce, siou, _, cols = O.hungarian(pred.detach(), gt, len(valid), k)
+        close(ce, g["cost_ce_" + tag]); close(siou, g["cost_siou_" + tag])
+        assert list(cols) == list(g["order_col_" + tag])
+
+
 def test_manipulator(golden_dir):
     """Oracle edit pipeline (networks/manipulator.py:18-205) against the reference run stored in manipulator.npz."""
     g = load(golden_dir, "manipulator.npz")
