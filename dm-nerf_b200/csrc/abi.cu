@@ -241,7 +241,7 @@ DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const 
   DMN_CHECK(net == 0 || net == 1, "mlp_backward: net must be 0 or 1");
   DMN_CHECK(m >= 0 && grads, "mlp_backward: bad arguments");
   DMN_CHECK(m == 0 || (acts && d_out && scratch), "mlp_backward: NULL buffer");
-  return launch_mlp_backward(ctx->net[net], acts, d_out, m, grads, scratch, feats_missing, (cudaStream_t)stream);
+  return launch_mlp_backward(ctx->net[net], &ctx->packed[net], acts, d_out, m, grads, scratch, feats_missing, (cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_composite_backward(const float* raw, const float* z, const float* rays_d, int64_t n, int s, int c,

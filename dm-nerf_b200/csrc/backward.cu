@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "ray_ops.cuh"
+#include "umma_api.cuh"
 
 namespace dmnerf {
 
@@ -491,11 +492,126 @@ static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStr
   return 0;
 }
 
-size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (2 * 128 + 4 * 256); }
+size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (2 * 128 + 8 * 256) + 2 * 128 * 256 + 2 * 128; }
+
+// DMNERF_BWD_IMPL=gemm: per-layer dX GEMM kernels instead of the fused gradient chain (round-1 path; cross-check / A-B timing).
+static bool bwd_use_chain() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DMNERF_BWD_IMPL");
+    v = (e && (strcmp(e, "simt") == 0 || strcmp(e, "gemm") == 0)) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// C[m, n] (+)= sum_k A[m, k] W[n, k] + rowscale[m] * bias[n]   (small dense products of the folded head gradients)
+__global__ void __launch_bounds__(256) small_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                       const float* __restrict__ rowscale, const float* __restrict__ bias,
+                                                       float* __restrict__ Cm, int ldc, int M, int N, int K) {
+  __shared__ float As[GK][GT + 1];
+  __shared__ float Ws[GK][GT + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int idx = tid; idx < GT * GK; idx += 256) {
+      const int r = idx / GK, c = idx % GK;
+      As[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.0f;
+      Ws[c][r] = (n0 + r < N && k0 + c < K) ? W[(size_t)(n0 + r) * ldw + k0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < N) Cm[(size_t)mm * ldc + n] = acc[i][j] + (rowscale ? rowscale[mm] * bias[n] : 0.0f);
+    }
+  }
+}
+
+// The training backward with the fused gradient chain (bwd_chain.cu) and the heads folded like in the forward:
+//   S1 = d rgb_hid, S2 = d ins_hid                      (bwd_heads_kernel, masks from ActPlanes::bits)
+//   dY7..dY0                                            (bwd_chain_kernel: one launch, gradients stay in tensor memory)
+//   dW(l) = dY(l)^T X(l-1), db(l) = colsum dY(l)         (tcgen05 dW GEMMs over the saved planes)
+//   P = S1^T h7, Q = S2^T h7  ->  the four feature / hidden head gradients by small dense products:
+//     dW_rgb_hid[:, :256] = P W_rf^T + c1 (x) b_rf,  dW_rgb_feat = W_rh[:, :256]^T P,  db_rgb_feat = W_rh[:, :256]^T c1   (c1 = colsum S1)
+//     (rgb_feat = h7 W_rf^T + b_rf is never materialised; same for the instance branch with Q, c2)
+static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, float* acts, const float* d_out, int64_t m,
+                              float* const* grads, float* scratch, int feats_missing, cudaStream_t st) {
+  const int ins1 = p.ins_num + 1, C = 4 + ins1;
+  const ActPlanes ap = act_planes(acts, m);
+  float* S1 = scratch;
+  float* S2 = S1 + m * 128;
+  float* dY[8];
+  for (int l = 0; l < 8; ++l) dY[l] = S2 + m * 128 + (size_t)l * m * 256;
+  float* P = dY[7] + m * 256;
+  float* Q = P + 128 * 256;
+  float* c1 = Q + 128 * 256;
+  float* c2 = c1 + 128;
+  auto gw = [&](int l) { return grads[2 * l]; };
+  auto gb = [&](int l) { return grads[2 * l + 1]; };
+  DMN_CUDA(cudaMemsetAsync(P, 0, (2 * 128 * 256 + 256) * sizeof(float), st));
+  int rc = 0;
+#define R(x) do { if ((rc = (x))) return rc; } while (0)
+  if (!feats_missing) R(launch_mask_bits(acts, m, st));          // exact-fp32 forward: masks from its planes
+  const float* d_rgb = d_out;
+  const float* d_sig = d_out + 3;
+  const float* d_ins = d_out + 4;
+  R(launch_bwd_heads(p, d_out, m, ap.bits, S1, S2, st));
+  R(launch_bwd_chain(packed, p, S1, d_out, ap.bits, m, dY, st));
+  // ---- output layers (dm_nerf.py:101-103)
+  R(gemm_tn(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, m, 3, 128, st));     R(colsum(d_rgb, C, gb(L_RGB_OUT), m, 3, st));
+  R(gemm_tn(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, m, ins1, 128, st));  R(colsum(d_ins, C, gb(L_INS_OUT), m, ins1, st));
+  R(gemm_tn(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, m, 1, 256, st));        R(colsum(d_sig, C, gb(L_DENSITY), m, 1, st));
+  // ---- folded head layers (dm_nerf.py:89-99)
+  R(gemm_tn(S1, 128, ap.h[7], 256, P, 256, m, 128, 256, st, c1));
+  R(gemm_tn(S2, 128, ap.h[7], 256, Q, 256, m, 128, 256, st, c2));
+  R(gemm_tn(S1, 128, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));       // view-direction columns
+  small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256);
+  DMN_LAUNCH_OK();
+  small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256);
+  DMN_LAUNCH_OK();
+  DMN_CUDA(cudaMemcpyAsync(gb(L_RGB_HID), c1, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DMN_CUDA(cudaMemcpyAsync(gb(L_INS_HID), c2, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  R(gemm_tn(p.w[L_RGB_HID], 283, P, 256, gw(L_RGB_FEAT), 256, 128, 256, 256, st));                 // W_rh[:, :256]^T P
+  R(gemm_tn(p.w[L_RGB_HID], 283, c1, 1, gb(L_RGB_FEAT), 1, 128, 256, 1, st));
+  R(gemm_tn(p.w[L_INS_HID], 256, Q, 256, gw(L_INS_FEAT), 256, 128, 256, 256, st));
+  R(gemm_tn(p.w[L_INS_HID], 256, c2, 1, gb(L_INS_FEAT), 1, 128, 256, 1, st));
+  // ---- trunk (dm_nerf.py:83-87)
+  for (int l = 7; l >= 0; --l) {
+    const int kin = layer_in(l);
+    if (l == 0) {
+      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st));
+      R(colsum(dY[0], 256, gb(0), m, 256, st));
+    } else {
+      R(gemm_tn(dY[l], 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));
+      if (l == 5) R(gemm_tn(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));    // skip input [h, pts]
+    }
+  }
+#undef R
+  return 0;
+}
 
 // grads: 30 device pointers in state_dict order (weight, bias per layer); overwritten with the gradient of this call.
-int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads, float* scratch,
-                        int feats_missing, cudaStream_t st) {
+int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* acts, const float* d_out, int64_t m, float* const* grads,
+                        float* scratch, int feats_missing, cudaStream_t st) {
   DMN_CHECK(p.bound, "mlp_backward: weights not bound");
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   for (int l = 0; l < N_LAYERS; ++l) {
@@ -504,6 +620,8 @@ int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int
     DMN_CUDA(cudaMemsetAsync(grads[2 * l + 1], 0, (size_t)layer_out(l, p.ins_num) * sizeof(float), st));
   }
   if (m == 0) return 0;
+  if (bwd_use_tc() && bwd_use_chain() && packed && umma_available(*packed) && m >= 512)
+    return mlp_backward_chain(p, *packed, acts, d_out, m, grads, scratch, feats_missing, st);
   const ActPlanes ap = act_planes(acts, m);
   float* S1 = scratch;                  // d rgb_hid  [m,128]
   float* S2 = S1 + m * 128;             // d ins_hid  [m,128]

@@ -48,9 +48,12 @@ __host__ __device__ inline int layer_in(int l) {
 // Activations saved by the training forward of one network (planes of row-major [M, width] matrices, in this order):
 //   H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128] | emb [M,90]
 // (the 90-wide plane comes last so every other plane starts 16-byte aligned for any M)
-constexpr int ACT_FLOATS_PER_SAMPLE = CH_IN + 8 * W_HID + 2 * W_HID + 2 * (W_HID / 2);   // 2906
+// ... | bits: ReLU masks, 1 bit per unit, [10 planes][M][8 words] (planes 0..7 = H0..H7, 8 = rgb_hid, 9 = ins_hid (4 words used);
+//           bit c of word w = unit 32 w + c is positive) -- what the fused gradient chain (bwd_chain.cu) reads instead of the planes
+constexpr int ACT_BITS_PLANES = 10, ACT_BITS_WORDS = 8;
+constexpr int ACT_FLOATS_PER_SAMPLE = CH_IN + 8 * W_HID + 2 * W_HID + 2 * (W_HID / 2) + ACT_BITS_PLANES * ACT_BITS_WORDS;   // 2986
 struct ActPlanes {
-  float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid;
+  float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid; uint32_t* bits;
 };
 __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
   ActPlanes a;
@@ -60,7 +63,8 @@ __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
   a.ins_feat = p; p += m * W_HID;
   a.rgb_hid = p; p += m * (W_HID / 2);
   a.ins_hid = p; p += m * (W_HID / 2);
-  a.emb = p;
+  a.emb = p; p += m * CH_IN;
+  a.bits = reinterpret_cast<uint32_t*>(p);
   return a;
 }
 
@@ -126,8 +130,14 @@ int launch_composite_backward(const float* raw, const float* z, const float* ray
                               const float* g_weights, float* d_raw, int accumulate, cudaStream_t st);
 // feats_missing != 0: the forward that filled `acts` did not materialise rgb_feat / ins_feat (tensor-core kernel, folded
 // heads); the backward recomputes those two planes from h7 first.
-int launch_mlp_backward(const NetParams& p, float* acts, const float* d_out, int64_t m, float* const* grads,
+struct UmmaWeights;
+int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* acts, const float* d_out, int64_t m, float* const* grads,
                         float* scratch, int feats_missing, cudaStream_t st);
+// Fused gradient chain (bwd_chain.cu)
+int launch_mask_bits(float* acts, int64_t m, cudaStream_t st);
+int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s1, float* s2, cudaStream_t st);
+int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint32_t* bits, int64_t m,
+                     float* const* dy, cudaStream_t st);
 size_t mlp_backward_scratch_floats(int64_t m);
 
 // Tensor-core GEMMs of the backward (gemm_umma.cu): split-bf16 three-pass tcgen05 kernels for the wide layer shapes.

@@ -29,53 +29,19 @@
 #include <vector>
 
 #include "ray_ops.cuh"
-#include "umma.cuh"
+#include "uk_pipe.cuh"
 #include "umma_api.cuh"
 
 namespace dmnerf {
 namespace uk {
 
 using namespace umma;
-
-constexpr int TILE_M = 128;
-constexpr int NS = 8;                      // weight ring stages
-constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
-constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
-constexpr int N_STEPS = 19;                 // 16 trunk half-steps, instance hidden, colour hidden (+ head on CUDA cores), instance head
-constexpr int T_INS_HID = 16, T_RGB_HID = 17, T_INS_OUT = 18;
-// fp32 side table of a network (KArgs::bias): per-step bias rows, then the small layers evaluated on CUDA cores
-constexpr int B_WD = N_STEPS * 128;        // density_linear weights [256]
-constexpr int B_BD = B_WD + 256;           // density bias (+3 pad)
-constexpr int B_WRGB = B_BD + 4;           // rgb_linear weights [3][128]
-constexpr int B_BRGB = B_WRGB + 3 * 128;   // rgb_linear bias (+1 pad)
-constexpr int B_TOTAL = B_BRGB + 4;
-constexpr int MAX_CHUNKS = 5;
-constexpr int MAX_STAGES = 160;
-constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TMEM lane quadrants x 4 column groups
-constexpr int CHUNK_THREADS = 256;         // threads that produce one 64-column K chunk of a half-step's output
-constexpr int N_THREADS = 128 + EPI_THREADS;
-
-// tensor-memory column map (512 columns x 128 lanes x 32 bit) -- completely used:
-//   two fp32 accumulators [128 x 128] and two activation slots, each holding a [128 x 128] activation block (one K-half of
-//   a 256-wide layer input) as split bf16: 64 columns of hi halves + 64 columns of lo halves (2 bf16 per 32-bit column).
-// Every trunk MMA therefore takes its A operand from tensor memory (no shared-memory read for A); the position / direction
-// embeddings, used by 4 of the 73 K chunks of a tile, live in shared memory instead.
-constexpr uint32_t TC_ACC = 0;             // two accumulators: [0,128) and [128,256)
-constexpr uint32_t TC_SLOT = 256;          // slot s at 256 + 128 s: hi of chunk c at +32 c, lo of chunk c at +64 + 32 c
-constexpr uint32_t SLOT_COLS = 128, SLOT_LO = 64;
-
-// shared-memory map (offsets from the 1024-aligned base)
-constexpr uint32_t SM_E_HI = 0;                                 // position embedding, K-major SW128 slabs [128 rows][64 bf16]
-constexpr uint32_t SM_E_LO = SM_E_HI + CHUNK_BYTES;
-constexpr uint32_t SM_D_HI = SM_E_LO + CHUNK_BYTES;             // direction embedding (32 of the 64 K columns used)
-constexpr uint32_t SM_D_LO = SM_D_HI + CHUNK_BYTES;
-constexpr uint32_t SM_RING = SM_D_LO + CHUNK_BYTES;
-constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
-constexpr uint32_t SM_FUSED = SM_MISC + 9216;                   // per-unit state of the fused render kernel
-constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
-
 enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..3 = slot*2 + chunk
+
+#ifdef DMN_KPROF
+__device__ long long g_kprof[160][16];
+__device__ long long g_ktrace[4][64];     // CTA 0, tile KTRACE_TILE: [mma step ready | mma step issued | epi acc_full seen | epi arrived][step]
+#endif
 
 struct Step {
   int8_t n_chunks;
@@ -94,15 +60,6 @@ struct Program {
   int32_t ins_num;
 };
 
-struct Misc {                  // lives at SM_MISC
-  uint64_t full[NS], empty[NS];
-  uint64_t acc_full[2], epi_done[2][2], inputs_ready;   // epi_done[accumulator][64-column chunk]
-  uint64_t a_free;             // the odd half-step of a layer has finished reading slot 0 (its even half-step may overwrite it)
-  uint32_t tmem_base;
-  int32_t abort_flag;
-  float4 part[4][TILE_M];      // per column group and row: partial dot products of the rgb head (xyz) and of the density (w)
-};
-
 // Shared state of the fused render kernel: one work unit = 2 rays = 1 coarse tile (2 x 64 samples) + 3 fine tiles (2 x 192).
 constexpr int FS = 64, FI = 128, FF = FS + FI;        // the fused path is specialised for 64 + 128 samples
 constexpr int ACC_W = 5 + DMNERF_MAX_INS + 1 + 3;      // rgb3, depth, acc, ins_num+1 (padded)
@@ -119,7 +76,6 @@ struct Fused {
 };
 static_assert(sizeof(Fused) <= 12288, "Fused state does not fit its shared-memory block");
 
-static_assert(sizeof(Misc) <= 9216, "Misc does not fit its shared-memory block");
 
 struct KArgs {
   const uint8_t* image;        // packed bf16 operand image (fused: coarse network)
@@ -139,86 +95,6 @@ struct KArgs {
   float* acts;                 // training forward (RAW mode): ActPlanes base, or nullptr
   int32_t* status;             // device error word
 };
-
-// ------------------------------------------------------------------------------------------------ in-kernel cycle profile
-// Diagnostics build only (-DDMN_KPROF, tools/kprof.py): where do the MMA warp and one epilogue thread spend their cycles.
-#ifdef DMN_KPROF
-__device__ long long g_kprof[160][16];
-__device__ long long g_ktrace[4][64];     // CTA 0, tile KTRACE_TILE: [mma step ready | mma step issued | epi acc_full seen | epi arrived][step]
-#define KTRACE_TILE 100
-#define KP_T0() const long long kp_t0 = clock64()
-#define KP_ADD(i) kp[i] += clock64() - kp_t0
-#else
-#define KP_T0() ((void)0)
-#define KP_ADD(i) ((void)0)
-#endif
-
-// ------------------------------------------------------------------------------------------------ bounded waits
-// Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
-// On a timeout the abort flag is raised and execution simply continues: every later wait returns at once, the kernel
-// drains (with garbage results) and the host sees the status word -- no divergent early exits in the role loops.
-__device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*(volatile int32_t*)&misc->abort_flag) return;
-    if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
-      atomicExch(&misc->abort_flag, code);
-      atomicCAS(status, 0, code);
-      return;
-    }
-  }
-}
-__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
-  if (!mbar_try_wait(bar, parity)) slow_wait(bar, parity, misc, code, status);
-}
-
-// Position in the weight ring (warp-uniform).
-struct Ring {
-  uint32_t slot, phase;
-  __device__ __forceinline__ void advance() {
-    if (++slot == NS) { slot = 0; phase ^= 1; }
-  }
-};
-
-// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi and A_lo*W_hi) and the W_lo stage (A_hi*W_lo).
-// Executed by the whole (converged) MMA warp; one elected lane issues.
-// A_SMEM = false: a_hi / a_lo are tensor-memory addresses (activation slots);  true: shared-memory descriptors (embeddings).
-template <int KS, bool A_SMEM>
-__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_hi, uint64_t a_lo,
-                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status,
-                                            long long* kp) {
-  const uint32_t s_hi = ring.slot, p_hi = ring.phase;
-  ring.advance();
-  const uint32_t s_lo = ring.slot, p_lo = ring.phase;
-  ring.advance();
-  const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
-  const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
-  if (elect_one()) {
-    { KP_T0(); wait_bar(&misc->full[s_hi], p_hi, misc, 204, status); KP_ADD(4); }
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K; +8 TMEM columns likewise
-      if (A_SMEM) {
-        mma_ss(d_tmem, a_hi + 2 * k, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-        mma_ss(d_tmem, a_lo + 2 * k, wh + 2 * k, idesc, 1u);
-      } else {
-        mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
-        mma_ts(d_tmem, (uint32_t)a_lo + k * 8, wh + 2 * k, idesc, 1u);
-      }
-    }
-    mma_commit(&misc->empty[s_hi]);
-    { KP_T0(); wait_bar(&misc->full[s_lo], p_lo, misc, 205, status); KP_ADD(5); }
-    tc_fence_after();
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      if (A_SMEM) mma_ss(d_tmem, a_hi + 2 * k, wl + 2 * k, idesc, 1u);
-      else mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wl + 2 * k, idesc, 1u);
-    }
-    mma_commit(&misc->empty[s_lo]);
-  }
-  __syncwarp();
-  accum = 1;
-}
 
 // ------------------------------------------------------------------------------------------------ prologue helpers
 // sin and cos of one argument with |a| < ~1e5: three-constant Cody-Waite reduction by pi/2 + the single-precision minimax
@@ -273,44 +149,6 @@ __device__ __forceinline__ void fill_embedding(const float v[3], float* vals /* 
       }
     }
   }
-}
-
-// 8 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+8): one 16-byte unit each).
-__device__ __forceinline__ void store_split8_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
-  const uint32_t o = sw128_offset(row, k0);
-  *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-// 16 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+16)).
-__device__ __forceinline__ void store_split16_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const uint32_t o = sw128_offset(row, k0 + 8 * u);
-    *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
-    *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-  }
-}
-
-// 32 fp32 values -> bf16 hi and bf16 lo, both into TMEM (16 columns each).
-__device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t tmem_hi, uint32_t tmem_lo) {
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
-  tmem_st_x16(tmem_hi, hi);
-  tmem_st_x16(tmem_lo, lo);
-}
-
-// 32 consecutive fp32 values of one row to global memory (training forward keeps the activations, common.cuh ActPlanes).
-__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -766,6 +604,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
                                     : ((t == T_RGB_HID) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
               store_row32(dst + col, f);
+              uint32_t bw = 0;                       // ReLU mask of these 32 units, 1 bit each (ActPlanes::bits)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) bw |= (f[i] > 0.0f ? 1u : 0u) << i;
+              const int plane = (t < 16) ? (t >> 1) : ((t == T_RGB_HID) ? 8 : 9);
+              ap.bits[((int64_t)plane * a.m + row) * ACT_BITS_WORDS + ((t < 16) ? (t & 1) * 4 + cg : cg)] = bw;
             }
           }
           // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11.
@@ -1017,6 +860,7 @@ static void build_program(Program& P, int ins_num) {
 // ------------------------------------------------------------------------------------------------ host: packing
 struct PackStage {            // one entry per (step, chunk): produces the W_hi and the W_lo stage
   const float* src; int ld; int n_base; int n_valid; int col_base; int k_valid; int n_rows; uint32_t off_hi; uint32_t off_lo;
+  int transposed;             // 0: B[n][k] = src[n_base + n][col_base + k];  1: B[n][k] = src[col_base + k][n_base + n]
 };
 
 __global__ void fold_kernel(const float* __restrict__ w2, int ld2, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -1053,7 +897,9 @@ __global__ void pack_kernel(const PackStage* __restrict__ stages, int n_entries,
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k = 8 * u + 2 * j + h;
-        v[h] = (n < ps.n_valid && k < ps.k_valid) ? ps.src[(size_t)(ps.n_base + n) * ps.ld + ps.col_base + k] : 0.0f;
+        v[h] = !(n < ps.n_valid && k < ps.k_valid) ? 0.0f
+               : (ps.transposed ? ps.src[(size_t)(ps.col_base + k) * ps.ld + ps.n_base + n]
+                                : ps.src[(size_t)(ps.n_base + n) * ps.ld + ps.col_base + k]);
       }
       umma::split_bf16x2(v[0], v[1], hi[j], lo[j]);
     }
@@ -1088,6 +934,7 @@ __global__ void bias_kernel(NetParams p, const float* __restrict__ fold_b_rgb, c
 struct UmmaExtra {            // hangs off UmmaWeights::image allocation bookkeeping
   uk::Program prog;
   float* fold_w_rgb; float* fold_w_ins; float* fold_b; uk::PackStage* d_entries; int32_t* d_status;
+  uint8_t* bwd_image;         // operand image of the gradient chain (bwd_chain.cu)
 };
 
 static UmmaExtra* extra_of(const UmmaWeights& w) { return reinterpret_cast<UmmaExtra*>(w.extra); }
@@ -1102,12 +949,16 @@ void umma_weights_free(UmmaWeights& w) {
     if (x->fold_b) cudaFree(x->fold_b);
     if (x->d_entries) cudaFree(x->d_entries);
     if (x->d_status) cudaFree(x->d_status);
+    if (x->bwd_image) cudaFree(x->bwd_image);
     delete x;
   }
   w = UmmaWeights();
 }
 
 bool umma_available(const UmmaWeights& w) { return w.ready; }
+const uint8_t* umma_bwd_image(const UmmaWeights& w) { return w.extra ? extra_of(w)->bwd_image : nullptr; }
+const float* umma_fold_w_rgb(const UmmaWeights& w) { return w.extra ? extra_of(w)->fold_w_rgb : nullptr; }
+int32_t* umma_status_word(const UmmaWeights& w) { return w.extra ? extra_of(w)->d_status : nullptr; }
 
 int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
   using namespace uk;
@@ -1124,7 +975,8 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
     DMN_CUDA(cudaMalloc((void**)&x->fold_w_rgb, 128 * 283 * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_w_ins, 128 * 256 * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->fold_b, 256 * sizeof(float)));
-    DMN_CUDA(cudaMalloc((void**)&x->d_entries, MAX_STAGES * sizeof(PackStage)));
+    DMN_CUDA(cudaMalloc((void**)&x->d_entries, (MAX_STAGES + BWD_IMAGE_STAGES / 2) * sizeof(PackStage)));
+    DMN_CUDA(cudaMalloc((void**)&x->bwd_image, (size_t)BWD_IMAGE_STAGES * STAGE_BYTES));
     DMN_CUDA(cudaMalloc((void**)&x->d_status, sizeof(int32_t)));
     DMN_CUDA(cudaMemsetAsync(x->d_status, 0, sizeof(int32_t), st));
   }
@@ -1161,9 +1013,30 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
     }
   }
   DMN_CHECK((int)ent.size() * 2 == x->prog.n_stages && (int)ent.size() <= MAX_STAGES, "umma pack: stage table mismatch");
+  const size_t n_fwd = ent.size();
+  // gradient chain (bwd_chain.cu): transposed operands, B[n = input unit][k = output unit] = W[k][n], in consumption order
+  {
+    uint32_t off = 0;
+    auto add = [&](const float* src, int ld, int n_base, int row_base) {
+      PackStage e;
+      memset(&e, 0, sizeof(e));
+      e.src = src; e.ld = ld; e.n_base = n_base; e.n_valid = 128; e.col_base = row_base; e.k_valid = 64; e.n_rows = 128;
+      e.transposed = 1; e.off_hi = off; e.off_lo = off + STAGE_BYTES;
+      off += 2 * STAGE_BYTES;
+      ent.push_back(e);
+    };
+    for (int h = 0; h < 2; ++h)                       // d h7 = d rgb_hid [., 128] x W_fold [128][256 (+27)]
+      for (int c = 0; c < 2; ++c) add(x->fold_w_rgb, 283, h * 128, 64 * c);
+    for (int l = 7; l >= 1; --l)                      // d h(l-1) = dY(l) [., 256] x W(l) [256][256 (+63 for the skip layer)]
+      for (int h = 0; h < 2; ++h)
+        for (int c = 0; c < 4; ++c) add(p.w[l], layer_in(l), h * 128, 64 * c);
+    DMN_CHECK((ent.size() - n_fwd) * 2 == (size_t)BWD_IMAGE_STAGES, "umma pack: backward stage table mismatch");
+  }
   DMN_CUDA(cudaMemcpyAsync(x->d_entries, ent.data(), ent.size() * sizeof(PackStage), cudaMemcpyHostToDevice, st));
   DMN_CUDA(cudaStreamSynchronize(st));               // `ent` is a host temporary
-  pack_kernel<<<(unsigned)ent.size(), 256, 0, st>>>(x->d_entries, (int)ent.size(), (uint8_t*)w.image);
+  pack_kernel<<<(unsigned)n_fwd, 256, 0, st>>>(x->d_entries, (int)n_fwd, (uint8_t*)w.image);
+  DMN_LAUNCH_OK();
+  pack_kernel<<<(unsigned)(ent.size() - n_fwd), 256, 0, st>>>(x->d_entries + n_fwd, (int)(ent.size() - n_fwd), x->bwd_image);
   DMN_LAUNCH_OK();
   bias_kernel<<<8, 256, 0, st>>>(p, x->fold_b, x->fold_b + 128, w.bias);
   DMN_LAUNCH_OK();

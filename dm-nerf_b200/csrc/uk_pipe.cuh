@@ -1,0 +1,179 @@
+// Shared device-side pieces of the persistent tcgen05 pipelines (mlp_umma.cu: forward network / fused render kernel;
+// bwd_chain.cu: fused gradient chain of the training backward): tensor-memory and shared-memory maps, the barrier block,
+// bounded waits, the weight ring and the issue of one 64-wide K chunk, and the split-bf16 store helpers.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace dmnerf {
+namespace uk {
+
+using namespace umma;
+
+constexpr int TILE_M = 128;
+constexpr int NS = 8;                      // weight ring stages
+constexpr int STAGE_BYTES = 16384;         // up to [128 rows][64 bf16]
+constexpr int CHUNK_BYTES = 16384;         // activation slab [128 rows][64 bf16]
+constexpr int N_STEPS = 19;                 // 16 trunk half-steps, instance hidden, colour hidden (+ head on CUDA cores), instance head
+constexpr int T_INS_HID = 16, T_RGB_HID = 17, T_INS_OUT = 18;
+// fp32 side table of a network (KArgs::bias): per-step bias rows, then the small layers evaluated on CUDA cores
+constexpr int B_WD = N_STEPS * 128;        // density_linear weights [256]
+constexpr int B_BD = B_WD + 256;           // density bias (+3 pad)
+constexpr int B_WRGB = B_BD + 4;           // rgb_linear weights [3][128]
+constexpr int B_BRGB = B_WRGB + 3 * 128;   // rgb_linear bias (+1 pad)
+constexpr int B_TOTAL = B_BRGB + 4;
+constexpr int MAX_CHUNKS = 5;
+constexpr int MAX_STAGES = 160;
+constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TMEM lane quadrants x 4 column groups
+constexpr int CHUNK_THREADS = 256;         // threads that produce one 64-column K chunk of a half-step's output
+constexpr int N_THREADS = 128 + EPI_THREADS;
+
+// tensor-memory column map (512 columns x 128 lanes x 32 bit) -- completely used:
+//   two fp32 accumulators [128 x 128] and two activation slots, each holding a [128 x 128] activation block (one K-half of
+//   a 256-wide layer input) as split bf16: 64 columns of hi halves + 64 columns of lo halves (2 bf16 per 32-bit column).
+// Every trunk MMA therefore takes its A operand from tensor memory (no shared-memory read for A); the position / direction
+// embeddings, used by 4 of the 73 K chunks of a tile, live in shared memory instead.
+constexpr uint32_t TC_ACC = 0;             // two accumulators: [0,128) and [128,256)
+constexpr uint32_t TC_SLOT = 256;          // slot s at 256 + 128 s: hi of chunk c at +32 c, lo of chunk c at +64 + 32 c
+constexpr uint32_t SLOT_COLS = 128, SLOT_LO = 64;
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t SM_E_HI = 0;                                 // position embedding, K-major SW128 slabs [128 rows][64 bf16]
+constexpr uint32_t SM_E_LO = SM_E_HI + CHUNK_BYTES;
+constexpr uint32_t SM_D_HI = SM_E_LO + CHUNK_BYTES;             // direction embedding (32 of the 64 K columns used)
+constexpr uint32_t SM_D_LO = SM_D_HI + CHUNK_BYTES;
+constexpr uint32_t SM_RING = SM_D_LO + CHUNK_BYTES;
+constexpr uint32_t SM_MISC = SM_RING + NS * STAGE_BYTES;
+constexpr uint32_t SM_FUSED = SM_MISC + 9216;                   // per-unit state of the fused render kernel
+constexpr uint32_t SMEM_BYTES = SM_FUSED + 12288;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an SM");
+
+struct Misc {                  // lives at SM_MISC
+  uint64_t full[NS], empty[NS];
+  uint64_t acc_full[2], epi_done[2][2], inputs_ready;   // epi_done[accumulator][64-column chunk]
+  uint64_t a_free;             // the odd half-step of a layer has finished reading slot 0 (its even half-step may overwrite it)
+  uint32_t tmem_base;
+  int32_t abort_flag;
+  float4 part[4][TILE_M];      // per column group and row: partial dot products of the rgb head (xyz) and of the density (w)
+};
+
+static_assert(sizeof(Misc) <= 9216, "Misc does not fit its shared-memory block");
+
+// ------------------------------------------------------------------------------------------------ in-kernel cycle profile
+// Diagnostics build only (-DDMN_KPROF, tools/kprof.py): where do the MMA warp and one epilogue thread spend their cycles.
+#ifdef DMN_KPROF
+#define KTRACE_TILE 100
+#define KP_T0() const long long kp_t0 = clock64()
+#define KP_ADD(i) kp[i] += clock64() - kp_t0
+#else
+#define KP_T0() ((void)0)
+#define KP_ADD(i) ((void)0)
+#endif
+
+// ------------------------------------------------------------------------------------------------ bounded waits
+// Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
+// On a timeout the abort flag is raised and execution simply continues: every later wait returns at once, the kernel
+// drains (with garbage results) and the host sees the status word -- no divergent early exits in the role loops.
+static __device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*(volatile int32_t*)&misc->abort_flag) return;
+    if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
+      atomicExch(&misc->abort_flag, code);
+      atomicCAS(status, 0, code);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  if (!mbar_try_wait(bar, parity)) slow_wait(bar, parity, misc, code, status);
+}
+
+// Position in the weight ring (warp-uniform).
+struct Ring {
+  uint32_t slot, phase;
+  __device__ __forceinline__ void advance() {
+    if (++slot == NS) { slot = 0; phase ^= 1; }
+  }
+};
+
+// One 64-wide K chunk of one half-step: consumes the W_hi stage (A_hi*W_hi and A_lo*W_hi) and the W_lo stage (A_hi*W_lo).
+// Executed by the whole (converged) MMA warp; one elected lane issues.
+// A_SMEM = false: a_hi / a_lo are tensor-memory addresses (activation slots);  true: shared-memory descriptors (embeddings).
+template <int KS, bool A_SMEM>
+__device__ __forceinline__ void issue_chunk(Misc* misc, Ring& ring, uint32_t ring_base, uint64_t a_hi, uint64_t a_lo,
+                                            uint32_t d_tmem, uint32_t idesc, uint32_t& accum, int32_t* status,
+                                            long long* kp) {
+  const uint32_t s_hi = ring.slot, p_hi = ring.phase;
+  ring.advance();
+  const uint32_t s_lo = ring.slot, p_lo = ring.phase;
+  ring.advance();
+  const uint64_t wh = make_sdesc_sw128(ring_base + s_hi * STAGE_BYTES);
+  const uint64_t wl = make_sdesc_sw128(ring_base + s_lo * STAGE_BYTES);
+  if (elect_one()) {
+    { KP_T0(); wait_bar(&misc->full[s_hi], p_hi, misc, 204, status); KP_ADD(4); }
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {               // +2 on a descriptor = +32 bytes = 16 bf16 along K; +8 TMEM columns likewise
+      if (A_SMEM) {
+        mma_ss(d_tmem, a_hi + 2 * k, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+        mma_ss(d_tmem, a_lo + 2 * k, wh + 2 * k, idesc, 1u);
+      } else {
+        mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wh + 2 * k, idesc, k == 0 ? accum : 1u);
+        mma_ts(d_tmem, (uint32_t)a_lo + k * 8, wh + 2 * k, idesc, 1u);
+      }
+    }
+    mma_commit(&misc->empty[s_hi]);
+    { KP_T0(); wait_bar(&misc->full[s_lo], p_lo, misc, 205, status); KP_ADD(5); }
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      if (A_SMEM) mma_ss(d_tmem, a_hi + 2 * k, wl + 2 * k, idesc, 1u);
+      else mma_ts(d_tmem, (uint32_t)a_hi + k * 8, wl + 2 * k, idesc, 1u);
+    }
+    mma_commit(&misc->empty[s_lo]);
+  }
+  __syncwarp();
+  accum = 1;
+}
+
+// 8 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+8): one 16-byte unit each).
+__device__ __forceinline__ void store_split8_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  const uint32_t o = sw128_offset(row, k0);
+  *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// 16 fp32 values -> bf16 hi and bf16 lo into two K-major SW128 slabs (row `row`, K columns [k0, k0+16)).
+__device__ __forceinline__ void store_split16_smem(const float* vals, uint8_t* slab_hi, uint8_t* slab_lo, int row, int k0) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t o = sw128_offset(row, k0 + 8 * u);
+    *reinterpret_cast<uint4*>(slab_hi + o) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+    *reinterpret_cast<uint4*>(slab_lo + o) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+  }
+}
+
+// 32 fp32 values -> bf16 hi and bf16 lo, both into TMEM (16 columns each).
+__device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t tmem_hi, uint32_t tmem_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  tmem_st_x16(tmem_hi, hi);
+  tmem_st_x16(tmem_lo, lo);
+}
+
+// 32 consecutive fp32 values of one row to global memory (training forward keeps the activations, common.cuh ActPlanes).
+__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+}  // namespace uk
+}  // namespace dmnerf

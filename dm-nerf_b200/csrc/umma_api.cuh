@@ -16,6 +16,13 @@ struct UmmaWeights {
   bool ready = false;
 };
 
+// Backward operand image (bwd_chain.cu): the transposed weights of the gradient chain in consumption order, 16 KB stages:
+// head fold 2 half-steps x 2 chunks, layers 7..1 x 2 half-steps x 4 chunks, hi + lo each.
+constexpr int BWD_IMAGE_STAGES = (2 * 2 + 14 * 4) * 2;
+const uint8_t* umma_bwd_image(const UmmaWeights& w);
+const float* umma_fold_w_rgb(const UmmaWeights& w);      // [128][283]: W_rgb_hid[:, :256] W_rgb_feat | W_rgb_hid[:, 256:]
+int32_t* umma_status_word(const UmmaWeights& w);
+
 int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st);
 void umma_weights_free(UmmaWeights& w);
 bool umma_available(const UmmaWeights& w);

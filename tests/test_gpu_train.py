@@ -203,6 +203,12 @@ def test_tensor_core_training_forward_saves_the_reference_activations(m):
     assert scale_err(planes["ins_hid"], ih.numpy()) <= 1e-4
     out = O.mlp_forward(p, x).numpy()
     assert scale_err(raw.cpu().numpy(), out) <= 1e-4
+    # ReLU masks, 1 bit per unit (what the fused gradient chain reads): [10 planes][m][8 words] after the embedded inputs
+    bits = acts[off:off + 10 * m * 8].view(np.uint32).reshape(10, m, 8)
+    for pl, name in enumerate(["h%d" % l for l in range(8)] + ["rgb_hid", "ins_hid"]):
+        width = planes[name].shape[1]
+        unpacked = ((bits[pl][:, :width // 32, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(m, width)
+        assert np.array_equal(unpacked.astype(bool), planes[name] > 0), name
 
 
 @pytest.mark.parametrize("ins_num", [13, 59])
