@@ -492,7 +492,7 @@ static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStr
   return 0;
 }
 
-size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (2 * 128 + 8 * 256) + 2 * 128 * 256 + 2 * 128; }
+size_t mlp_backward_scratch_floats(int64_t m) { return (size_t)m * (256 + 8 * 256) + 256 * 256 + 256 + 256; }
 
 // DMNERF_BWD_IMPL=gemm: per-layer dX GEMM kernels instead of the fused gradient chain (round-1 path; cross-check / A-B timing).
 static bool bwd_use_chain() {
@@ -553,37 +553,51 @@ __global__ void __launch_bounds__(256) small_nt_kernel(const float* __restrict__
 //   P = S1^T h7, Q = S2^T h7  ->  the four feature / hidden head gradients by small dense products:
 //     dW_rgb_hid[:, :256] = P W_rf^T + c1 (x) b_rf,  dW_rgb_feat = W_rh[:, :256]^T P,  db_rgb_feat = W_rh[:, :256]^T c1   (c1 = colsum S1)
 //     (rgb_feat = h7 W_rf^T + b_rf is never materialised; same for the instance branch with Q, c2)
+// out[c] += sum_m A[m, c] for a narrow row-major matrix (C <= 132 columns): coalesced sweep of the flat array, per-block bins.
+__global__ void __launch_bounds__(256) colsum_flat_kernel(const float* __restrict__ A, int C, int64_t total, float* __restrict__ out) {
+  __shared__ float bins[4 + DMNERF_MAX_INS + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bins[c] = 0.0f;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&bins[(int)(i % C)], A[i]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out[c], bins[c]);
+}
+
 static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, float* acts, const float* d_out, int64_t m,
                               float* const* grads, float* scratch, int feats_missing, cudaStream_t st) {
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   const ActPlanes ap = act_planes(acts, m);
-  float* S1 = scratch;
-  float* S2 = S1 + m * 128;
+  float* S12 = scratch;                               // d rgb_hid | d ins_hid  [m,256]
   float* dY[8];
-  for (int l = 0; l < 8; ++l) dY[l] = S2 + m * 128 + (size_t)l * m * 256;
-  float* P = dY[7] + m * 256;
-  float* Q = P + 128 * 256;
-  float* c1 = Q + 128 * 256;
-  float* c2 = c1 + 128;
+  for (int l = 0; l < 8; ++l) dY[l] = S12 + m * 256 + (size_t)l * m * 256;
+  float* PQ = dY[7] + m * 256;                        // [S1 | S2]^T h7: rows 0..127 = P, 128..255 = Q
+  float* c12 = PQ + 256 * 256;                        // column sums of S1 | S2
+  float* cs = c12 + 256;                              // column sums of d_out [C]
+  float* P = PQ, *Q = PQ + 128 * 256, *c1 = c12, *c2 = c12 + 128;
   auto gw = [&](int l) { return grads[2 * l]; };
   auto gb = [&](int l) { return grads[2 * l + 1]; };
-  DMN_CUDA(cudaMemsetAsync(P, 0, (2 * 128 * 256 + 256) * sizeof(float), st));
+  DMN_CUDA(cudaMemsetAsync(PQ, 0, (256 * 256 + 256 + 256) * sizeof(float), st));
   int rc = 0;
 #define R(x) do { if ((rc = (x))) return rc; } while (0)
   if (!feats_missing) R(launch_mask_bits(acts, m, st));          // exact-fp32 forward: masks from its planes
   const float* d_rgb = d_out;
   const float* d_sig = d_out + 3;
   const float* d_ins = d_out + 4;
-  R(launch_bwd_heads(p, d_out, m, ap.bits, S1, S2, st));
-  R(launch_bwd_chain(packed, p, S1, d_out, ap.bits, m, dY, st));
-  // ---- output layers (dm_nerf.py:101-103)
-  R(gemm_tn(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, m, 3, 128, st));     R(colsum(d_rgb, C, gb(L_RGB_OUT), m, 3, st));
-  R(gemm_tn(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, m, ins1, 128, st));  R(colsum(d_ins, C, gb(L_INS_OUT), m, ins1, st));
-  R(gemm_tn(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, m, 1, 256, st));        R(colsum(d_sig, C, gb(L_DENSITY), m, 1, st));
-  // ---- folded head layers (dm_nerf.py:89-99)
-  R(gemm_tn(S1, 128, ap.h[7], 256, P, 256, m, 128, 256, st, c1));
-  R(gemm_tn(S2, 128, ap.h[7], 256, Q, 256, m, 128, 256, st, c2));
-  R(gemm_tn(S1, 128, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));       // view-direction columns
+  R(launch_bwd_heads(p, d_out, m, ap.bits, S12, st));
+  R(launch_bwd_chain(packed, p, S12, d_out, ap.bits, m, dY, st));
+  // ---- output layers (dm_nerf.py:101-103): weight gradients, and the three bias gradients from one sweep over d_out
+  R(gemm_tn(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, m, 3, 128, st));
+  R(gemm_tn(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, m, ins1, 128, st));
+  R(gemm_tn(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, m, 1, 256, st));
+  colsum_flat_kernel<<<148 * 4, 256, 0, st>>>(d_out, C, m * C, cs);
+  DMN_LAUNCH_OK();
+  DMN_CUDA(cudaMemcpyAsync(gb(L_RGB_OUT), cs, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DMN_CUDA(cudaMemcpyAsync(gb(L_DENSITY), cs + 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DMN_CUDA(cudaMemcpyAsync(gb(L_INS_OUT), cs + 4, ins1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // ---- folded head layers (dm_nerf.py:89-99): one GEMM against h7 for both branches
+  R(gemm_tn(S12, 256, ap.h[7], 256, PQ, 256, m, 256, 256, st, c12));
+  R(gemm_tn(S12, 256, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));      // view-direction columns
   small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256);
   DMN_LAUNCH_OK();
   small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256);
@@ -598,8 +612,7 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   for (int l = 7; l >= 0; --l) {
     const int kin = layer_in(l);
     if (l == 0) {
-      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st));
-      R(colsum(dY[0], 256, gb(0), m, 256, st));
+      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st, gb(0)));
     } else {
       R(gemm_tn(dY[l], 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));
       if (l == 5) R(gemm_tn(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));    // skip input [h, pts]
@@ -614,8 +627,11 @@ int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* ac
                         float* scratch, int feats_missing, cudaStream_t st) {
   DMN_CHECK(p.bound, "mlp_backward: weights not bound");
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
+  const bool prezeroed = (feats_missing & 2) != 0;      // flags: bit 0 = feature planes missing, bit 1 = grads already zero
+  feats_missing &= 1;
   for (int l = 0; l < N_LAYERS; ++l) {
     DMN_CHECK(grads[2 * l] && grads[2 * l + 1], "mlp_backward: gradient buffer %d is NULL", 2 * l);
+    if (prezeroed) continue;
     DMN_CUDA(cudaMemsetAsync(grads[2 * l], 0, (size_t)layer_out(l, p.ins_num) * layer_in(l) * sizeof(float), st));
     DMN_CUDA(cudaMemsetAsync(grads[2 * l + 1], 0, (size_t)layer_out(l, p.ins_num) * sizeof(float), st));
   }

@@ -31,7 +31,7 @@ constexpr uint32_t C_SMEM_BYTES = SM_FUSED;          // slabs + ring + barrier b
 
 struct CArgs {
   const uint8_t* image;       // backward operand image
-  const float* s1;            // d rgb_hid, already masked [M,128]
+  const float* s1;            // d rgb_hid, already masked: columns 0..127 of the [M,256] head-gradient plane (128..255 = d ins_hid)
   const float* d_out;         // d raw [M, C]: column 3 = d sigma
   int32_t ldc;
   const float* w_dens;        // density_linear.weight [256]
@@ -40,14 +40,6 @@ struct CArgs {
   int64_t m;
   int32_t* status;
 };
-
-__device__ __forceinline__ void store_row32_v8(float* __restrict__ dst, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
-                 "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,7 +158,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
       const int64_t rowp = (blockIdx.x + tp * gridDim.x) * TILE_M + r;
       float v[32];
       if (rowp < a.m) {
-        const float4* src = reinterpret_cast<const float4*>(a.s1 + rowp * 128 + cg * 32);
+        const float4* src = reinterpret_cast<const float4*>(a.s1 + rowp * 256 + cg * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const float4 q = __ldg(src + i); v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
       } else {
@@ -231,7 +223,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
           tc_fence_before();
           mbar_arrive(&misc->epi_done[acc][c]);
         }
-        if (valid) store_row32_v8(a.dy[layer] + row * W_HID + col, f);
+#ifndef DMN_EXP_CHAIN_NOSTORE      /* timing experiment: no gradient planes written (results are garbage) */
+        if (valid) store_row32(a.dy[layer] + row * W_HID + col, f);
+#endif
         if (t == 3 && ti + 1 < my_tiles) prologue(ti + 1);   // the slabs were last read by half-step 1
       }
     }
@@ -243,10 +237,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
 
 // ------------------------------------------------------------------------------------------------ head gradients
 // d rgb_hid = mask . (d_rgb W_rgb_out), d ins_hid = mask . (d_ins W_ins_out)   (dm_nerf.py:102-103 backwards, K = 3 / ins_num+1)
+// written side by side into one [M,256] plane so that ONE dW GEMM against h7 serves both branches.
 // One thread per (row, hidden unit); the head weights live in shared memory.
 __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict__ d_out, int C, int64_t m, const float* __restrict__ w_rgb,
                                                         const float* __restrict__ w_ins, int ins1, const uint32_t* __restrict__ bits,
-                                                        float* __restrict__ s1, float* __restrict__ s2, int rows_per_block) {
+                                                        float* __restrict__ s12, int rows_per_block) {
   extern __shared__ float sm[];
   float* wi = sm;                         // [ins1][128]
   float* wr = wi + ins1 * 128;            // [3][128]
@@ -264,8 +259,8 @@ __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 3; ++k) a1 = fmaf(drow[k], wr[k * 128 + j], a1);
     for (int k = 0; k < ins1; ++k) a2 = fmaf(drow[4 + k], wi[k * 128 + j], a2);
-    s1[row * 128 + j] = ((br >> (j & 31)) & 1u) ? a1 : 0.0f;
-    s2[row * 128 + j] = ((bi >> (j & 31)) & 1u) ? a2 : 0.0f;
+    s12[row * 256 + j] = ((br >> (j & 31)) & 1u) ? a1 : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
+    s12[row * 256 + 128 + j] = ((bi >> (j & 31)) & 1u) ? a2 : 0.0f;
   }
 }
 
@@ -302,15 +297,15 @@ int launch_mask_bits(float* acts, int64_t m, cudaStream_t st) {
   return 0;
 }
 
-int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s1, float* s2, cudaStream_t st) {
+int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s12, cudaStream_t st) {
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   if (m == 0) return 0;
   const int rows = 64;
   const size_t smem = (size_t)((ins1 + 3) * 128 + C) * sizeof(float);
   static PerDeviceOnce once;
   if (once.first()) DMN_CUDA(cudaFuncSetAttribute(bk::bwd_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-  bk::bwd_heads_kernel<<<(unsigned)((m + rows - 1) / rows), 128, smem, st>>>(d_out, C, m, p.w[L_RGB_OUT], p.w[L_INS_OUT], ins1, bits, s1,
-                                                                           s2, rows);
+  bk::bwd_heads_kernel<<<(unsigned)((m + rows - 1) / rows), 128, smem, st>>>(d_out, C, m, p.w[L_RGB_OUT], p.w[L_INS_OUT], ins1, bits, s12,
+                                                                           rows);
   DMN_LAUNCH_OK();
   return 0;
 }

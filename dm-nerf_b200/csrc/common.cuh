@@ -135,7 +135,7 @@ int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* ac
                         float* scratch, int feats_missing, cudaStream_t st);
 // Fused gradient chain (bwd_chain.cu)
 int launch_mask_bits(float* acts, int64_t m, cudaStream_t st);
-int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s1, float* s2, cudaStream_t st);
+int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s12, cudaStream_t st);
 int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint32_t* bits, int64_t m,
                      float* const* dy, cudaStream_t st);
 size_t mlp_backward_scratch_floats(int64_t m);

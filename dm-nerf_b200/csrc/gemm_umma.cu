@@ -412,17 +412,38 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
 }
 
 // C[n, k] += sum_cta partial[cta][n][k]  (k < kb valid columns of the NB-wide partials);  transpose: C[k, n] instead
-// (the product was computed with the roles of the two operands exchanged).
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int NA, int NB, int kb, float* __restrict__ C,
-                                       int ldc, int transpose) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NA * NB) return;
-  const int n = idx / NB, k = idx % NB;
-  if (k >= kb) return;
-  float s = 0.0f;
-  for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * NA * NB + idx];
-  if (transpose) C[(size_t)k * ldc + n] += s;
-  else C[(size_t)n * ldc + k] += s;
+// (the product was computed with the roles of the two operands exchanged).  64 float4 columns x 4 slice groups per block: every
+// thread keeps several independent 16-byte loads in flight (the slices were just written: they come from L2).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int NA, int NB, int kb,
+                                                              float* __restrict__ C, int ldc, int transpose) {
+  __shared__ float4 red[4][64];
+  const int q = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int idx4 = blockIdx.x * 64 + q, total4 = NA * NB / 4;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (idx4 < total4) {
+    const float4* src = reinterpret_cast<const float4*>(partial) + idx4;
+    const size_t stride = (size_t)total4;
+    int c = grp;
+    for (; c + 4 < n_cta; c += 8) {
+      const float4 x = __ldcs(src + (size_t)c * stride), y = __ldcs(src + (size_t)(c + 4) * stride);
+      s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w;
+      s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
+    }
+    if (c < n_cta) { const float4 x = __ldcs(src + (size_t)c * stride); s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w; }
+  }
+  red[grp][q] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+  __syncthreads();
+  if (grp != 0 || idx4 >= total4) return;
+  const float4 a = red[0][q], b = red[1][q], c = red[2][q], d = red[3][q];
+  const float v[4] = {(a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w)};
+  const int idx = idx4 * 4, n = idx / NB, k0 = idx % NB;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = k0 + e;
+    if (k >= kb) continue;
+    if (transpose) C[(size_t)k * ldc + n] += v[e];
+    else C[(size_t)n * ldc + k] += v[e];
+  }
 }
 
 // Scratch of the GEMM launches, one set per CUDA device of the process (launches on a device are stream-ordered, so one packed
@@ -527,7 +548,7 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
   else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
   else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
   DMN_LAUNCH_OK();
-  reduce_partials_kernel<<<(N * NB + 255) / 256, 256, 0, st>>>(scratch, (int)grid, N, NB, K, C, ldc, transpose);
+  reduce_partials_kernel<<<(N * NB / 4 + 63) / 64, 256, 0, st>>>(scratch, (int)grid, N, NB, K, C, ldc, transpose);
   DMN_LAUNCH_OK();
   return 0;
 }

@@ -603,7 +603,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               const ActPlanes ap = act_planes(a.acts, a.m);
               float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
                                     : ((t == T_RGB_HID) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
+#ifndef DMN_EXP_FWD_NOACTSTORE      /* timing experiment: activation planes not written (results are garbage) */
               store_row32(dst + col, f);
+#endif
               uint32_t bw = 0;                       // ReLU mask of these 32 units, 1 bit each (ActPlanes::bits)
 #pragma unroll
               for (int i = 0; i < 32; ++i) bw |= (f[i] > 0.0f ? 1u : 0u) << i;

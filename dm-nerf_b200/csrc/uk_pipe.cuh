@@ -169,10 +169,14 @@ __device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t t
   tmem_st_x16(tmem_lo, lo);
 }
 
-// 32 consecutive fp32 values of one row to global memory (training forward keeps the activations, common.cuh ActPlanes).
+// 32 consecutive fp32 values of one row (128 B, 32-byte aligned) to global memory as four 256-bit stores: every store is a
+// whole 32-byte sector (a 128-bit store leaves half-sector partial writes for the L2 to merge, at twice the request count).
 __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float* v) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 4; ++i)
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+                 "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                 : "memory");
 }
 
 }  // namespace uk

@@ -151,14 +151,18 @@ DMNERF_API int64_t dmnerf_mlp_backward_scratch_floats(int64_t m);
 
 /* DM_NeRF.forward with saved activations.  Pass either x [M,90] (rays_* NULL) or rays_o/rays_d [N,3] + z [N,S] (x NULL,
  * m = N*S).  out [M,C].  impl: DMNERF_IMPL_SIMT = exact fp32; DMNERF_IMPL_UMMA / AUTO = the tensor-core kernel, whose folded heads
- * do not produce the rgb_feature / ins_feature planes -- pass feats_missing = 1 to dmnerf_mlp_backward in that case. */
+ * do not produce the rgb_feature / ins_feature planes -- pass feats_missing = 1 to dmnerf_mlp_backward in that case.  Both
+ * kernels also keep the ReLU masks (1 bit per unit) the fused gradient chain of the backward reads. */
 DMNERF_API int dmnerf_mlp_forward_train(dmnerf_ctx* ctx, int net, const float* x, const float* rays_o, const float* rays_d,
                              const float* z, int64_t m, int s, float* out, float* acts, int impl, void* stream);
 
 /* Gradient of a scalar loss w.r.t. the 30 parameters of network `net` given d_out = dL/d(out) [M,C] and the activations
  * saved by dmnerf_mlp_forward_train.  grads: 30 device buffers (state_dict order, parameter shapes), overwritten.
  * Gradient routing follows the reference (networks/dm_nerf.py:95: the instance branch reads h.detach()).
- * scratch: dmnerf_mlp_backward_scratch_floats(m) floats. */
+ * scratch: dmnerf_mlp_backward_scratch_floats(m) floats.  feats_missing is a flag word: bit 0 = the forward did not write the
+ * feature planes (tensor-core forward), bit 1 = the caller has already zero-filled `grads` (one fill instead of 30 memsets).
+ * M >= 512: one fused tcgen05 kernel carries the gradient through the trunk (it never leaves the SM between layers) and
+ * tcgen05 GEMMs form the weight gradients; smaller batches and DMNERF_BWD_IMPL=simt use fp32 CUDA-core kernels. */
 DMNERF_API int dmnerf_mlp_backward(dmnerf_ctx* ctx, int net, float* acts, const float* d_out, int64_t m, float* const* grads,
                         float* scratch, int feats_missing, void* stream);
 
