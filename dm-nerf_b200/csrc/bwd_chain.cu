@@ -181,27 +181,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
       for (int t = 0; t < C_STEPS; ++t) {
         const uint32_t g = (uint32_t)ti * C_STEPS + t, acc = g & 1;
         const uint32_t acc_addr = tbase + lane_sel + TC_ACC + acc * 128;
-        const int p = t >> 1, h = t & 1, layer = 7 - p;      // this half-step produces dY(layer)[:, h*128 + cg*32 ...]
-        const int col = h * 128 + cg * 32;
-        const int c = cg >> 1;                               // 64-column K chunk of the destination slot
-        const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + h * SLOT_COLS + c * 32 + (cg & 1) * 16;
-        // fetched before the accumulator is waited for
-        const uint32_t mbits = valid ? __ldg(a.bits + ((int64_t)layer * a.m + row) * 8 + h * 4 + cg) : 0u;
+        const int p = t >> 1, h = t & 1, layer = 7 - p;      // this half-step produces dY(layer)[:, h*128 + ...]
+        // this thread's columns inside the half-step (uk_pipe.cuh): f[0..15] <-> colA + i, f[16..31] <-> colB + i
+        const int colA = epi_col_a(cg), colB = epi_col_b(cg);
+        const int cA = colA >> 6, cB = colB >> 6;
+        const uint32_t slot_addr = tbase + lane_sel + TC_SLOT + h * SLOT_COLS;
+        const uint32_t hiA = slot_addr + cA * 32 + ((colA & 63) >> 1), hiB = slot_addr + cB * 32 + ((colB & 63) >> 1);
+        // ReLU masks of the two 16-unit groups, fetched before the accumulator is waited for
+        const uint16_t* bh = reinterpret_cast<const uint16_t*>(a.bits + ((int64_t)layer * a.m + row) * 8);
+        const uint32_t mA = valid ? (uint32_t)__ldg(bh + ((h * 128 + colA) >> 4)) : 0u;
+        const uint32_t mB = valid ? (uint32_t)__ldg(bh + ((h * 128 + colB) >> 4)) : 0u;
         wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 311, a.status);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld_x32(acc_addr + cg * 32, v);
+        if constexpr (EPI_SPLIT) { tmem_ld_x16(acc_addr + colA, v); tmem_ld_x16(acc_addr + colB, v + 16); }
+        else tmem_ld_x32(acc_addr + colA, v);
         tmem_ld_wait();
         if (t >= 14) {                       // nothing goes back to a slot: the accumulator is all the MMA warp waits for
           tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc][c]);
+          if constexpr (EPI_SPLIT) { mbar_arrive(&misc->epi_done[acc][0]); mbar_arrive(&misc->epi_done[acc][1]); }
+          else mbar_arrive(&misc->epi_done[acc][cA]);
         }
         float f[32];
         if (t < 2) {                         // + d sigma (x) w_density (dm_nerf.py:101)
-          const float4* w4 = reinterpret_cast<const float4*>(a.w_dens + col);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const float4 wd = __ldg(w4 + jj);
+            const float4 wd = __ldg(reinterpret_cast<const float4*>(a.w_dens + h * 128 + (jj < 4 ? colA : colB)) + (jj & 3));
             f[4 * jj + 0] = fmaf(dsig, wd.x, __uint_as_float(v[4 * jj + 0]));
             f[4 * jj + 1] = fmaf(dsig, wd.y, __uint_as_float(v[4 * jj + 1]));
             f[4 * jj + 2] = fmaf(dsig, wd.z, __uint_as_float(v[4 * jj + 2]));
@@ -212,19 +217,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = ((mbits >> i) & 1u) ? f[i] : 0.0f;      // ReLU of layer `layer` (dm_nerf.py:85)
+        for (int i = 0; i < 16; ++i) {                         // ReLU of layer `layer` (dm_nerf.py:85)
+          f[i] = ((mA >> i) & 1u) ? f[i] : 0.0f;
+          f[16 + i] = ((mB >> i) & 1u) ? f[16 + i] : 0.0f;
+        }
         if (t < 14) {
           if (h == 0 && t >= 2) {            // slot 0 still feeds the odd half-step issued behind this one
             wait_bar(&misc->a_free, (uint32_t)(ti * 6 + (p - 1)) & 1u, misc, 312, a.status);
             tc_fence_after();
           }
-          store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
+          if constexpr (EPI_SPLIT) {
+            store_split16_tmem(f, hiA, hiA + SLOT_LO);           // K chunk 0 first: published half an epilogue earlier
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&misc->epi_done[acc][0]);
+            store_split16_tmem(f + 16, hiB, hiB + SLOT_LO);
+          } else {
+            store_split32_tmem(f, hiA, hiA + SLOT_LO);
+          }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&misc->epi_done[acc][c]);
+          mbar_arrive(&misc->epi_done[acc][EPI_SPLIT ? 1 : cA]);
         }
 #ifndef DMN_EXP_CHAIN_NOSTORE      /* timing experiment: no gradient planes written (results are garbage) */
-        if (valid) store_row32(a.dy[layer] + row * W_HID + col, f);
+        if (valid) {
+          float* dst = a.dy[layer] + row * W_HID + h * 128;
+          store_row16(dst + colA, f);
+          store_row16(dst + colB, f + 16);
+        }
 #endif
         if (t == 3 && ti + 1 < my_tiles) prologue(ti + 1);   // the slabs were last read by half-step 1
       }

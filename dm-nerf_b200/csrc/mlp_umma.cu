@@ -299,9 +299,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           uint32_t accum = 0;
           slot_chunk(0, 0, d_tmem, idesc128, accum); slot_chunk(0, 1, d_tmem, idesc128, accum);
           if (h == 1) release_slot0();
+#ifndef DMN_EXP_NO_NEEDEPI    /* timing experiment only (results are garbage): slot 1 is read without waiting for its epilogue */
           if (h == 0) { KP_T0(); need_epi(g - 1, 0); KP_ADD(1); }
+#endif
           slot_chunk(1, 0, d_tmem, idesc128, accum);
+#ifndef DMN_EXP_NO_NEEDEPI
           if (h == 0) { KP_T0(); need_epi(g - 1, 1); KP_ADD(2); }
+#endif
           slot_chunk(1, 1, d_tmem, idesc128, accum);
           if (l == 5) issue_chunk<4, true>(misc, ring, ring_base, e_hi, e_lo, d_tmem, idesc128, accum, a.status, kp);
           finish(acc);
@@ -537,13 +541,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           // column groups are done.  The bias is fetched before the accumulator is waited for (L1 is tiny next to 224 KB of
           // shared memory: these loads usually come from L2).
           const int slot = t & 1;
-          const int c = cg >> 1;                                                    // K chunk of the output
-          const int col = cg * 32;                                                  // first of this thread's 32 columns
-          const uint32_t hi_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS + c * 32 + (cg & 1) * 16;
+          // this thread's columns inside the half-step: f[0..15] <-> colA + i (K chunk cA), f[16..31] <-> colB + i (K chunk cB)
+          const int colA = epi_col_a(cg), colB = epi_col_b(cg);
+          const int cA = colA >> 6, cB = colB >> 6;
+          const uint32_t slot_addr = tbase + lane_sel + TC_SLOT + slot * SLOT_COLS;
+          const uint32_t hiA = slot_addr + cA * 32 + ((colA & 63) >> 1), hiB = slot_addr + cB * 32 + ((colB & 63) >> 1);
           float4 bb[8];
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) bb[jj] = __ldg(b4 + jj);
+          for (int jj = 0; jj < 4; ++jj) {
+            bb[jj] = __ldg(reinterpret_cast<const float4*>(bias + colA) + jj);
+            bb[4 + jj] = __ldg(reinterpret_cast<const float4*>(bias + colB) + jj);
+          }
           { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
           tc_fence_after();
 #ifdef DMN_KPROF
@@ -551,11 +559,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[2][(ti - KTRACE_TILE) * 20 + t] = kp_body0;
 #endif
           uint32_t v[32];
-          tmem_ld_x32(acc_addr + col, v);
+          if constexpr (EPI_SPLIT) { tmem_ld_x16(acc_addr + colA, v); tmem_ld_x16(acc_addr + colB, v + 16); }
+          else tmem_ld_x32(acc_addr + colA, v);
           tmem_ld_wait();
           if (t == T_RGB_HID) {       // nothing goes back to a slot: the accumulator is all the MMA warp waits for
             tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc][c]);
+            if constexpr (EPI_SPLIT) { mbar_arrive(&misc->epi_done[acc][0]); mbar_arrive(&misc->epi_done[acc][1]); }
+            else mbar_arrive(&misc->epi_done[acc][cA]);
           }
           float f[32];
 #pragma unroll
@@ -566,10 +576,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             f[4 * jj + 3] = fmaxf(__uint_as_float(v[4 * jj + 3]) + bb[jj].w, 0.0f);
           }
           auto density_partial = [&]() {   // density_linear (dm_nerf.py:101) on the final trunk activation, fp32 CUDA cores
-            const float4* w4 = reinterpret_cast<const float4*>(bias_base + B_WD + (t - 14) * 128 + col);
+            const float* wbase = bias_base + B_WD + (t - 14) * 128;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const float4 ww = __ldg(w4 + jj);
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(wbase + (jj < 4 ? colA : colB)) + (jj & 3));
               dens_acc = fmaf(f[4 * jj + 0], ww.x, dens_acc);
               dens_acc = fmaf(f[4 * jj + 1], ww.y, dens_acc);
               dens_acc = fmaf(f[4 * jj + 2], ww.z, dens_acc);
@@ -580,11 +590,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             if ((t & 1) == 0 && t >= 2) {
               // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
               KP_T0();
+#ifndef DMN_EXP_NO_AFREE      /* timing experiment only (results are garbage): the even epilogue does not wait for slot 0 */
               wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
+#endif
               KP_ADD(9);
               tc_fence_after();
             }
-            store_split32_tmem(f, hi_addr, hi_addr + SLOT_LO);
+            if constexpr (EPI_SPLIT) {
+              store_split16_tmem(f, hiA, hiA + SLOT_LO);             // K chunk 0 first: published half an epilogue earlier
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&misc->epi_done[acc][0]);
+              store_split16_tmem(f + 16, hiB, hiB + SLOT_LO);
+            } else {
+              store_split32_tmem(f, hiA, hiA + SLOT_LO);
+            }
             if (t == 15) {            // publish before this half-step's arrive: the arrive orders it ahead of the reader
               density_partial();      // (epi_done 15 -> MMA warp -> acc_full 17 -> colour-head epilogue)
               misc->part[cg][r].w = dens_acc;
@@ -592,7 +612,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc][c]);
+            mbar_arrive(&misc->epi_done[acc][EPI_SPLIT ? 1 : cA]);
 #ifdef DMN_KPROF
             if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[3][(ti - KTRACE_TILE) * 20 + t] = clock64();
 #endif
@@ -604,13 +624,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
                                     : ((t == T_RGB_HID) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
 #ifndef DMN_EXP_FWD_NOACTSTORE      /* timing experiment: activation planes not written (results are garbage) */
-              store_row32(dst + col, f);
+              store_row16(dst + colA, f);
+              store_row16(dst + colB, f + 16);
 #endif
-              uint32_t bw = 0;                       // ReLU mask of these 32 units, 1 bit each (ActPlanes::bits)
+              uint32_t bwa = 0, bwb = 0;             // ReLU masks of these 2 x 16 units, 1 bit each (ActPlanes::bits)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) bw |= (f[i] > 0.0f ? 1u : 0u) << i;
+              for (int i = 0; i < 16; ++i) { bwa |= (f[i] > 0.0f ? 1u : 0u) << i; bwb |= (f[16 + i] > 0.0f ? 1u : 0u) << i; }
               const int plane = (t < 16) ? (t >> 1) : ((t == T_RGB_HID) ? 8 : 9);
-              ap.bits[((int64_t)plane * a.m + row) * ACT_BITS_WORDS + ((t < 16) ? (t & 1) * 4 + cg : cg)] = bw;
+              uint16_t* bh = reinterpret_cast<uint16_t*>(ap.bits + ((int64_t)plane * a.m + row) * ACT_BITS_WORDS);
+              const int ua = ((t < 16) ? (t & 1) * 128 : 0) + colA, ub = ((t < 16) ? (t & 1) * 128 : 0) + colB;   // unit index
+              bh[ua >> 4] = (uint16_t)bwa;           // bit c of 32-bit word w = unit 32 w + c  (little-endian halves)
+              bh[ub >> 4] = (uint16_t)bwb;
             }
           }
           // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11.
@@ -623,10 +647,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           // ---------------- colour hidden layer: the 3-wide rgb head on CUDA cores (fp32), 32 columns per thread
           {
             float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
-            const float4* w0 = reinterpret_cast<const float4*>(bias_base + B_WRGB + col);
+            const int colA = epi_col_a(cg), colB = epi_col_b(cg);
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-              const float4 wa = __ldg(w0 + jj), wb = __ldg(w0 + 32 + jj), wc = __ldg(w0 + 64 + jj);
+              const float4* w0 = reinterpret_cast<const float4*>(bias_base + B_WRGB + (jj < 4 ? colA : colB)) + (jj & 3);
+              const float4 wa = __ldg(w0), wb = __ldg(w0 + 32), wc = __ldg(w0 + 64);
               p0 = fmaf(f[4 * jj + 0], wa.x, p0); p0 = fmaf(f[4 * jj + 1], wa.y, p0); p0 = fmaf(f[4 * jj + 2], wa.z, p0); p0 = fmaf(f[4 * jj + 3], wa.w, p0);
               p1 = fmaf(f[4 * jj + 0], wb.x, p1); p1 = fmaf(f[4 * jj + 1], wb.y, p1); p1 = fmaf(f[4 * jj + 2], wb.z, p1); p1 = fmaf(f[4 * jj + 3], wb.w, p1);
               p2 = fmaf(f[4 * jj + 0], wc.x, p2); p2 = fmaf(f[4 * jj + 1], wc.y, p2); p2 = fmaf(f[4 * jj + 2], wc.z, p2); p2 = fmaf(f[4 * jj + 3], wc.w, p2);
@@ -735,6 +760,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         tc_fence_after();
         if (cg >= 2) {
           // the instance head is drained by column groups 0 and 1 (256 threads, q = 64-column half) alone
+          if constexpr (EPI_SPLIT) {                 // every epilogue thread is counted on the chunk barriers
+            mbar_arrive(&misc->epi_done[acc][0]);
+            mbar_arrive(&misc->epi_done[acc][1]);
+          }
         } else {
           // instance head (N = pad16(ins_num+1))                                 (dm_nerf.py:103,105)
           if constexpr (!FUSED) {
@@ -757,20 +786,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             asm volatile("bar.sync 2, 256;" ::: "memory");     // weights of this tile (fz->w) are complete
             const float wgt = fz->w[r];
             const int lane_i = r & 31;
-            for (int c0 = q * 64; c0 < st.n && c0 < q * 64 + 64; c0 += 16) {
+            const int c_end = (st.n < q * 64 + 64) ? st.n : q * 64 + 64;
+            bool arrived = false;
+            for (int c0 = q * 64; c0 < c_end; c0 += 16) {
               uint32_t v[16];
               tmem_ld_x16(acc_addr + c0, v);
               tmem_ld_wait();
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float pv = (c0 + jj < n_ins1) ? __fmul_rn(wgt, __uint_as_float(v[jj]) + __ldg(bias + c0 + jj)) : 0.0f;
-                pv = warp_sum(pv);
-                if (lane_i == 0 && c0 + jj < n_ins1) fz->accum[rl][si >> 5][5 + c0 + jj] = pv;
+              if (c0 + 16 >= c_end) {                  // last block in registers: the accumulator is drained
+                tc_fence_before();
+                mbar_arrive(&misc->epi_done[acc][0]);
+                mbar_arrive(&misc->epi_done[acc][1]);
+                arrived = true;
               }
+              // 16 channels x 32 rows (one ray, one 32-sample chunk per warp) -> 16 sums with a transposing butterfly: every
+              // round halves the channels a lane carries (8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5); lanes 2c, 2c + 1 end up
+              // with channel c0 + c.  Fixed order: bit-reproducible.
+              float x[16];
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj)
+                x[jj] = (c0 + jj < n_ins1) ? __fmul_rn(wgt, __uint_as_float(v[jj]) + __ldg(bias + c0 + jj)) : 0.0f;
+#pragma unroll
+              for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                const bool up = (lane_i & bit) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                  const float send = up ? x[i] : x[half + i], keep = up ? x[half + i] : x[i];
+                  x[i] = __fadd_rn(keep, __shfl_xor_sync(FULL, send, bit));
+                }
+              }
+              const float tot = __fadd_rn(x[0], __shfl_xor_sync(FULL, x[0], 1));
+              const int ch = c0 + (lane_i >> 1);
+              if ((lane_i & 1) == 0 && ch < n_ins1) fz->accum[rl][si >> 5][5 + ch] = tot;
             }
-            tc_fence_before();
-            mbar_arrive(&misc->epi_done[acc][0]);
-            mbar_arrive(&misc->epi_done[acc][1]);
+            if (!arrived) {                            // no channel block in this 64-column half
+              tc_fence_before();
+              mbar_arrive(&misc->epi_done[acc][0]);
+              mbar_arrive(&misc->epi_done[acc][1]);
+            }
             asm volatile("bar.sync 2, 256;" ::: "memory");     // all running sums of this tile are in
             // ---- rays that end in this tile: write their maps (render.py:19-26) and clear the sums
             const int done_lo = (j == 0) ? 0 : ((j == 2) ? 0 : ((j == 3) ? 1 : 2));

@@ -25,7 +25,17 @@ constexpr int B_TOTAL = B_BRGB + 4;
 constexpr int MAX_CHUNKS = 5;
 constexpr int MAX_STAGES = 160;
 constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TMEM lane quadrants x 4 column groups
-constexpr int CHUNK_THREADS = 256;         // threads that produce one 64-column K chunk of a half-step's output
+// Column ownership of an epilogue thread inside a 128-column half-step.  EPI_SPLIT: 16 columns of K chunk 0 (columns
+// [16 cg, +16)) and then 16 columns of K chunk 1 ([64 + 16 cg, +16)): chunk 0 of a half-step's output is published after half of
+// the epilogue, so the next layer's MMAs on it are queued well before the tensor pipe runs dry (with 32 contiguous columns per
+// thread both chunks appear at the very end, a hair later than the pipe needs them: ~0.7 k idle cycles per layer).
+#ifndef DMN_EPI_SPLIT
+#define DMN_EPI_SPLIT 1
+#endif
+constexpr bool EPI_SPLIT = DMN_EPI_SPLIT != 0;
+constexpr int CHUNK_THREADS = EPI_SPLIT ? 512 : 256;   // arrivals that publish one 64-column K chunk of a half-step's output
+__host__ __device__ constexpr int epi_col_a(int cg) { return EPI_SPLIT ? 16 * cg : 32 * cg; }
+__host__ __device__ constexpr int epi_col_b(int cg) { return EPI_SPLIT ? 64 + 16 * cg : 32 * cg + 16; }
 constexpr int N_THREADS = 128 + EPI_THREADS;
 
 // tensor-memory column map (512 columns x 128 lanes x 32 bit) -- completely used:
@@ -76,7 +86,11 @@ static_assert(sizeof(Misc) <= 9216, "Misc does not fit its shared-memory block")
 // drains (with garbage results) and the host sees the status word -- no divergent early exits in the role loops.
 static __device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
   const long long t0 = clock64();
+#ifdef DMN_WAIT_HINT_NS
+  while (!mbar_try_wait_hint(bar, parity, DMN_WAIT_HINT_NS)) {
+#else
   while (!mbar_try_wait(bar, parity)) {
+#endif
     if (*(volatile int32_t*)&misc->abort_flag) return;
     if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
       atomicExch(&misc->abort_flag, code);
@@ -167,6 +181,24 @@ __device__ __forceinline__ void store_split32_tmem(const float* vals, uint32_t t
   for (int j = 0; j < 16; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
   tmem_st_x16(tmem_hi, hi);
   tmem_st_x16(tmem_lo, lo);
+}
+
+// 16 fp32 values -> bf16 hi and bf16 lo, both into TMEM (8 columns each).
+__device__ __forceinline__ void store_split16_tmem(const float* vals, uint32_t tmem_hi, uint32_t tmem_lo) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_bf16x2(vals[2 * j], vals[2 * j + 1], hi[j], lo[j]);
+  tmem_st_x8(tmem_hi, hi);
+  tmem_st_x8(tmem_lo, lo);
+}
+
+// 16 consecutive fp32 values of one row (64 B, 32-byte aligned) to global memory as two 256-bit stores.
+__device__ __forceinline__ void store_row16(float* __restrict__ dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+                 "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                 : "memory");
 }
 
 // 32 consecutive fp32 values of one row (128 B, 32-byte aligned) to global memory as four 256-bit stores: every store is a
