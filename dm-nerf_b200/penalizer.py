@@ -42,7 +42,7 @@ class _Penalizer(torch.autograd.Function):
         raw_c, z_c, d_c, rd_c, state = fctx.saved_tensors
         ctx = get_context(raw_c.device)
         n, s, c = raw_c.shape
-        d_raw = torch.zeros_like(raw_c)
+        d_raw = torch.empty_like(raw_c)           # the kernel writes every channel (zeros for rgb / sigma)
         g = g_loss.detach().reshape(-1)[:1].contiguous().float()
         _lib.check(ctx.lib.dmnerf_penalizer_backward(_lib.ptr(raw_c), _lib.ptr(z_c), _lib.ptr(d_c), _lib.ptr(rd_c), n, s, c,
                                                      fctx.cfg[0], fctx.cfg[1], state.data_ptr(), _lib.ptr(g), _lib.ptr(d_raw), 0,

@@ -200,8 +200,9 @@ DMNERF_API int dmnerf_exchanger(float* ori_raw, const float* const* tar_raws, co
 /* "Emptiness" regulariser on the per-sample object logits: emptiness_penalizer / ins_penalizer, networks/penalizer.py:5-62
  * (train_dmsr.py:53-60).  raw [N,S,C], z_vals [N,S], depth [N] (the rendered depth map, treated as a constant),
  * rays_d [N,3] -> loss[1] (device).  `state` is caller-provided device scratch of dmnerf_penalizer_state_bytes() bytes that
- * carries the mask populations from the forward to the backward call.  Backward: d_raw[..., 4:] (+)= g_loss[0] * dL/draw
- * (g_loss is a DEVICE scalar; channels 0..3 of d_raw are not touched). */
+ * carries the mask populations from the forward to the backward call.  Backward (g_loss is a DEVICE scalar): accumulate == 0
+ * writes d_raw = g_loss[0] * dL/draw for EVERY channel (zeros in channels 0..3: no zero-fill needed); accumulate != 0 adds the
+ * gradient to channels 4.. and leaves channels 0..3 untouched. */
 DMNERF_API int64_t dmnerf_penalizer_state_bytes(void);
 DMNERF_API int dmnerf_penalizer_forward(const float* raw, const float* z_vals, const float* depth, const float* rays_d, int64_t n,
                                         int s, int c, float tolerance, float deta_w, void* state, float* loss, void* stream);

@@ -390,3 +390,58 @@ def test_reference_training_iteration_through_the_dropin_imports():
         for k in [k for k in sys.modules if k == "networks" or k.startswith("networks.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def _noisy_oracle_grads(w, x, G, amp, seed):
+    """Oracle autograd with zero-mean noise of relative amplitude `amp` (x the layer's rms) injected into every pre-activation:
+    a stand-in for ANY forward arithmetic that is accurate to ~amp (e.g. the split-bf16 tensor-core products)."""
+    p = O.to_torch(w)
+    for v in p.values():
+        v.requires_grad_(True)
+    gen = torch.Generator().manual_seed(seed)
+    real_lin = O._lin
+
+    def noisy(pp, name, inp):
+        out = real_lin(pp, name, inp)
+        if out.shape[-1] >= 128:                       # hidden layers (the ReLU inputs); the narrow heads stay exact
+            out = out + (amp * out.detach().pow(2).mean().sqrt()) * torch.randn(out.shape, generator=gen)
+        return out
+
+    O._lin = noisy
+    try:
+        (O.mlp_forward(p, x) * G).sum().backward()
+    finally:
+        O._lin = real_lin
+    return {k: v.grad.numpy() for k, v in p.items()}
+
+
+def test_tensor_core_gradient_deviation_is_relu_flip_sensitivity():
+    """With the tensor-core forward the parameter gradients deviate from the exact ones by up to ~5e-3 relative L2 although every
+    activation is accurate to ~1e-5: units sitting within that distance of zero get the other ReLU branch.  This is a property of
+    the loss surface, not of the kernels: injecting 1e-5 noise into the ORACLE's pre-activations moves its own gradients by the
+    same amount, and the native path must stay inside a small multiple of that band."""
+    m, ins_num = 4096, 13
+    w = synth.make_weights(21, ins_num)
+    gen = torch.Generator().manual_seed(9)
+    pts = torch.rand(m, 3, generator=gen) * 6 - 3
+    vd = torch.randn(m, 3, generator=gen)
+    vd = vd / vd.norm(dim=-1, keepdim=True)
+    x = torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1)
+    G = torch.randn(m, 4 + ins_num + 1, generator=gen)
+    exact = _noisy_oracle_grads(w, x, G, 0.0, 0)
+    noisy = [_noisy_oracle_grads(w, x, G, 1e-5, s) for s in (1, 2)]
+    net = model_from_weights(w, DEV).train()
+    y = net(x.to(DEV), impl=_lib.IMPL_UMMA)
+    (y * G.to(DEV)).sum().backward()
+    from dmnerf_b200.engine import get_context
+    get_context(torch.device(DEV)).sync_check()
+    worst = 0.0
+    for k, prm in net.named_parameters():
+        if exact[k].size < 128:
+            continue                                     # tiny bias vectors of the heads: relL2 is not meaningful
+        ours = rel_l2(prm.grad.cpu().numpy(), exact[k])
+        band = max(rel_l2(n[k], exact[k]) for n in noisy)
+        worst = max(worst, ours)
+        print("%-34s relL2 ours %.2e   oracle with 1e-5 activation noise %.2e" % (k, ours, band))
+        assert ours <= 6.0 * band + 2e-4, (k, ours, band)
+    assert worst <= 2e-2
