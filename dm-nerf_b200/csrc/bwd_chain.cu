@@ -259,28 +259,46 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
 // d rgb_hid = mask . (d_rgb W_rgb_out), d ins_hid = mask . (d_ins W_ins_out)   (dm_nerf.py:102-103 backwards, K = 3 / ins_num+1)
 // written side by side into one [M,256] plane so that ONE dW GEMM against h7 serves both branches.
 // One thread per (row, hidden unit); the head weights live in shared memory.
+constexpr int HEAD_ROWS = 4;        // rows per iteration: one barrier pair per 4 rows
 __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict__ d_out, int C, int64_t m, const float* __restrict__ w_rgb,
                                                         const float* __restrict__ w_ins, int ins1, const uint32_t* __restrict__ bits,
                                                         float* __restrict__ s12, int rows_per_block) {
   extern __shared__ float sm[];
   float* wi = sm;                         // [ins1][128]
   float* wr = wi + ins1 * 128;            // [3][128]
-  float* drow = wr + 3 * 128;             // [C]
+  float* drow = wr + 3 * 128;             // [HEAD_ROWS][C]: contiguous rows of d_out
   const int j = threadIdx.x;
   for (int k = 0; k < ins1; ++k) wi[k * 128 + j] = w_ins[k * 128 + j];
   for (int k = 0; k < 3; ++k) wr[k * 128 + j] = w_rgb[k * 128 + j];
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  for (int64_t row = r0; row < r0 + rows_per_block && row < m; ++row) {
+  const int64_t r1 = (r0 + rows_per_block < m) ? r0 + rows_per_block : m;
+  for (int64_t row = r0; row < r1; row += HEAD_ROWS) {
+    const int nr = (int)((r1 - row < HEAD_ROWS) ? r1 - row : HEAD_ROWS);
     __syncthreads();
-    if (j < C) drow[j] = d_out[row * C + j];
+    for (int i = j; i < nr * C; i += 128) drow[i] = d_out[row * C + i];
     __syncthreads();
-    const uint32_t br = bits[((int64_t)8 * m + row) * 8 + (j >> 5)], bi = bits[((int64_t)9 * m + row) * 8 + (j >> 5)];
-    float a1 = 0.0f, a2 = 0.0f;
+    float a1[HEAD_ROWS], a2[HEAD_ROWS];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) a1 = fmaf(drow[k], wr[k * 128 + j], a1);
-    for (int k = 0; k < ins1; ++k) a2 = fmaf(drow[4 + k], wi[k * 128 + j], a2);
-    s12[row * 256 + j] = ((br >> (j & 31)) & 1u) ? a1 : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
-    s12[row * 256 + 128 + j] = ((bi >> (j & 31)) & 1u) ? a2 : 0.0f;
+    for (int q = 0; q < HEAD_ROWS; ++q) { a1[q] = 0.0f; a2[q] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float wv = wr[k * 128 + j];
+#pragma unroll
+      for (int q = 0; q < HEAD_ROWS; ++q) a1[q] = fmaf(drow[q * C + k], wv, a1[q]);
+    }
+    for (int k = 0; k < ins1; ++k) {
+      const float wv = wi[k * 128 + j];
+#pragma unroll
+      for (int q = 0; q < HEAD_ROWS; ++q) a2[q] = fmaf(drow[q * C + 4 + k], wv, a2[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < HEAD_ROWS; ++q) {
+      if (q >= nr) break;
+      const int64_t rq = row + q;
+      const uint32_t br = bits[((int64_t)8 * m + rq) * 8 + (j >> 5)], bi = bits[((int64_t)9 * m + rq) * 8 + (j >> 5)];
+      s12[rq * 256 + j] = ((br >> (j & 31)) & 1u) ? a1[q] : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
+      s12[rq * 256 + 128 + j] = ((bi >> (j & 31)) & 1u) ? a2[q] : 0.0f;
+    }
   }
 }
 
@@ -321,7 +339,7 @@ int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const ui
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   if (m == 0) return 0;
   const int rows = 64;
-  const size_t smem = (size_t)((ins1 + 3) * 128 + C) * sizeof(float);
+  const size_t smem = (size_t)((ins1 + 3) * 128 + bk::HEAD_ROWS * C) * sizeof(float);
   static PerDeviceOnce once;
   if (once.first()) DMN_CUDA(cudaFuncSetAttribute(bk::bwd_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   bk::bwd_heads_kernel<<<(unsigned)((m + rows - 1) / rows), 128, smem, st>>>(d_out, C, m, p.w[L_RGB_OUT], p.w[L_INS_OUT], ins1, bits, s12,

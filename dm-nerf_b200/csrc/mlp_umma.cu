@@ -920,21 +920,24 @@ struct PackStage {            // one entry per (step, chunk): produces the W_hi 
 __global__ void fold_kernel(const float* __restrict__ w2, int ld2, const float* __restrict__ w1, const float* __restrict__ b1,
                             const float* __restrict__ b2, int extra_cols, float* __restrict__ wout, float* __restrict__ bout) {
   // wout[n][k] = sum_j w2[n][j] w1[j][k] (k < 256);  wout[n][256 + e] = w2[n][256 + e];  bout[n] = sum_j w2[n][j] b1[j] + b2[n]
-  // grid (128 output rows, 3 column blocks of 128): one output element per thread, so the 256-long fp64 chains of a row run
-  // side by side (this kernel is on the critical path of every training step: the weights change, the fold is redone)
-  const int n = blockIdx.x, ldo = 256 + extra_cols;
-  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < ldo + 1; k += gridDim.y * blockDim.x) {
+  // grid (128 output rows, column blocks): FOUR lanes per output element, each with a 64-long fp64 chain, combined by shuffles
+  // (this kernel is on the critical path of every training step: the weights change, the fold is redone)
+  const int n = blockIdx.x, ldo = 256 + extra_cols, sub = threadIdx.x & 3;
+  const int per_block = blockDim.x >> 2;
+  for (int k0 = blockIdx.y * per_block; k0 < ldo + 1; k0 += gridDim.y * per_block) {
+    const int k = k0 + (threadIdx.x >> 2);
+    double s = 0.0;
     if (k < 256) {
-      double s = 0.0;
-      for (int j = 0; j < 256; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)w1[(size_t)j * 256 + k];
-      wout[(size_t)n * ldo + k] = (float)s;
-    } else if (k < ldo) {
-      wout[(size_t)n * ldo + k] = w2[(size_t)n * ld2 + k];
-    } else {
-      double s = (double)b2[n];
-      for (int j = 0; j < 256; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)b1[j];
-      bout[n] = (float)s;
+      for (int j = sub * 64; j < sub * 64 + 64; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)w1[(size_t)j * 256 + k];
+    } else if (k == ldo) {
+      for (int j = sub * 64; j < sub * 64 + 64; ++j) s += (double)w2[(size_t)n * ld2 + j] * (double)b1[j];
     }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (sub != 0 || k > ldo) continue;
+    if (k < 256) wout[(size_t)n * ldo + k] = (float)s;
+    else if (k < ldo) wout[(size_t)n * ldo + k] = w2[(size_t)n * ld2 + k];
+    else bout[n] = (float)(s + (double)b2[n]);
   }
 }
 
@@ -1036,9 +1039,9 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
   }
   UmmaExtra* x = extra_of(w);
   // fold the activation-free feature layers into the following hidden layers (fp64 accumulate)
-  fold_kernel<<<dim3(128, 3), 128, 0, st>>>(p.w[L_RGB_HID], 283, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], p.b[L_RGB_HID], 27, x->fold_w_rgb, x->fold_b);
+  fold_kernel<<<dim3(128, 5), 256, 0, st>>>(p.w[L_RGB_HID], 283, p.w[L_RGB_FEAT], p.b[L_RGB_FEAT], p.b[L_RGB_HID], 27, x->fold_w_rgb, x->fold_b);
   DMN_LAUNCH_OK();
-  fold_kernel<<<dim3(128, 3), 128, 0, st>>>(p.w[L_INS_HID], 256, p.w[L_INS_FEAT], p.b[L_INS_FEAT], p.b[L_INS_HID], 0, x->fold_w_ins, x->fold_b + 128);
+  fold_kernel<<<dim3(128, 5), 256, 0, st>>>(p.w[L_INS_HID], 256, p.w[L_INS_FEAT], p.b[L_INS_FEAT], p.b[L_INS_HID], 0, x->fold_w_ins, x->fold_b + 128);
   DMN_LAUNCH_OK();
   // one PackStage per (step, chunk)
   std::vector<PackStage> ent;

@@ -13,9 +13,15 @@ out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 go = os.path.join(ROOT, "gpurun_out")
 
-# 1. launch list (gpu__time_duration per launch) -> per-kernel share
-lp = os.path.join(go, "launches.csv")
-if os.path.exists(lp):
+# 1. launch lists (gpu__time_duration per launch) -> per-kernel share
+LISTS = (("launches.csv", "launches", "python bench.py --steps 1 --warmup 3 --no-cpu-baseline"),
+         ("launches_render.csv", "launches_render", "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train (first 80 launches)"),
+         ("launches_train.csv", "launches_train", "python tools/train_step.py 3 (three BASELINE-configs[3] training steps: forward + backward + Adam)"))
+for lname, oname, cmd in LISTS:
+  lp = os.path.join(go, lname)
+  if not os.path.exists(lp):
+    continue
+  if True:
     rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
     hdr = rows[0]
     ik, iv, ig, ib = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
@@ -25,9 +31,9 @@ if os.path.exists(lp):
         a[0] += 1
         a[1] += float(r[iv].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
-    with open(os.path.join(out, "%s_launches.md" % tag), "w") as f:
-        f.write("# ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (gpu__time_duration.sum, "
-                "--clock-control none; cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | grid | block |\n|---|---|---|---|---|---|\n")
+    with open(os.path.join(out, "%s_%s.md" % (tag, oname)), "w") as f:
+        f.write("# ncu launch list of `%s` (gpu__time_duration.sum, "
+                "--clock-control none; cold-cache, serialised: compare SHARES)\n\n| kernel | launches | total ms | share | grid | block |\n|---|---|---|---|---|---|\n" % cmd)
         for k, (n, t, g, b) in agg.items():
             f.write("| `%s` | %d | %.3f | %.1f%% | %s | %s |\n" % (k, n, t / 1e6, 100 * t / tot, g, b))
     print("wrote launches summary")
@@ -35,7 +41,15 @@ if os.path.exists(lp):
 # 2. full-set captures -> key metrics
 for rep, fname, title in (("prof_fused.ncu-rep", "ncu_fused_render", "one launch of `mlp_umma_kernel<true>`: the fused render kernel over one "
                            "640x480 frame (307 200 rays, 64+128 samples) as launched by bench.py"),
-                          ("prof_umma.ncu-rep", "ncu_fine_mlp", "one launch of `mlp_umma_kernel<false>` (unfused fine network, 37 888 rays x 192 samples)")):
+                          ("prof_umma.ncu-rep", "ncu_fine_mlp", "one launch of `mlp_umma_kernel<false>` (unfused fine network, 37 888 rays x 192 samples)"),
+                          ("r02_fused.ncu-rep", "ncu_fused_render", "one launch of `mlp_umma_kernel<true>`: the fused render kernel over one 640x480 "
+                           "frame (307 200 rays, 64+128 samples; tools/prof_fused.py 307200)"),
+                          ("r02_chain.ncu-rep", "ncu_bwd_chain", "one launch of `bwd_chain_kernel`: the fused gradient chain of the fine network inside a "
+                           "training step (196 608 samples; tools/train_step.py)"),
+                          ("r02_fwdtrain.ncu-rep", "ncu_train_forward", "one launch of `mlp_umma_kernel<false>` with activations kept: the fine network's "
+                           "training forward (196 608 samples; tools/train_step.py)"),
+                          ("r02_dw.ncu-rep", "ncu_dw_gemm", "one launch of `gemm_tn_tc_kernel` (dW = dY^T X of one trunk layer of the fine network) inside a "
+                           "training step")):
   rp = os.path.join(go, rep)
   if os.path.exists(rp):
       raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
