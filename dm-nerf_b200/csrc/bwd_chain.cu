@@ -240,10 +240,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
           mbar_arrive(&misc->epi_done[acc][EPI_SPLIT ? 1 : cA]);
         }
 #ifndef DMN_EXP_CHAIN_NOSTORE      /* timing experiment: no gradient planes written (results are garbage) */
-        if (valid) {
+        {
           float* dst = a.dy[layer] + row * W_HID + h * 128;
-          store_row16(dst + colA, f);
-          store_row16(dst + colB, f + 16);
+          if constexpr (EPI_SPLIT) {
+            const bool ok_other = (row ^ 1) < a.m;
+            store_row16_paired(dst + colA, W_HID, f, valid, ok_other, r & 31);
+            store_row16_paired(dst + colB, W_HID, f + 16, valid, ok_other, r & 31);
+          } else {
+            store_row32_quad(dst + colA, W_HID, f, row - (r & 3), a.m, r & 31);
+          }
         }
 #endif
         if (t == 3 && ti + 1 < my_tiles) prologue(ti + 1);   // the slabs were last read by half-step 1

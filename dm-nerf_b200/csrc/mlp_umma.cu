@@ -619,22 +619,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             if (t == 14) density_partial();      // off the critical path
           }
           if constexpr (!FUSED) {
-            if (a.acts && valid) {                   // training forward: keep the post-activation values (ActPlanes)
+            if (a.acts) {                            // training forward: keep the post-activation values (ActPlanes)
               const ActPlanes ap = act_planes(a.acts, a.m);
+              const int width = (t < 16) ? W_HID : W_HID / 2;
               float* dst = (t < 16) ? ap.h[t >> 1] + row * W_HID + (t & 1) * 128
                                     : ((t == T_RGB_HID) ? ap.rgb_hid : ap.ins_hid) + row * (W_HID / 2);
 #ifndef DMN_EXP_FWD_NOACTSTORE      /* timing experiment: activation planes not written (results are garbage) */
-              store_row16(dst + colA, f);
-              store_row16(dst + colB, f + 16);
+              if constexpr (EPI_SPLIT) {
+                const bool ok_other = (row ^ 1) < a.m;
+                store_row16_paired(dst + colA, width, f, valid, ok_other, r & 31);
+                store_row16_paired(dst + colB, width, f + 16, valid, ok_other, r & 31);
+              } else {
+                store_row32_quad(dst + colA, width, f, row - (r & 3), a.m, r & 31);
+              }
 #endif
-              uint32_t bwa = 0, bwb = 0;             // ReLU masks of these 2 x 16 units, 1 bit each (ActPlanes::bits)
+              if (valid) {
+                uint32_t bwa = 0, bwb = 0;           // ReLU masks of these 2 x 16 units, 1 bit each (ActPlanes::bits)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { bwa |= (f[i] > 0.0f ? 1u : 0u) << i; bwb |= (f[16 + i] > 0.0f ? 1u : 0u) << i; }
-              const int plane = (t < 16) ? (t >> 1) : ((t == T_RGB_HID) ? 8 : 9);
-              uint16_t* bh = reinterpret_cast<uint16_t*>(ap.bits + ((int64_t)plane * a.m + row) * ACT_BITS_WORDS);
-              const int ua = ((t < 16) ? (t & 1) * 128 : 0) + colA, ub = ((t < 16) ? (t & 1) * 128 : 0) + colB;   // unit index
-              bh[ua >> 4] = (uint16_t)bwa;           // bit c of 32-bit word w = unit 32 w + c  (little-endian halves)
-              bh[ub >> 4] = (uint16_t)bwb;
+                for (int i = 0; i < 16; ++i) { bwa |= (f[i] > 0.0f ? 1u : 0u) << i; bwb |= (f[16 + i] > 0.0f ? 1u : 0u) << i; }
+                const int plane = (t < 16) ? (t >> 1) : ((t == T_RGB_HID) ? 8 : 9);
+                uint16_t* bh = reinterpret_cast<uint16_t*>(ap.bits + ((int64_t)plane * a.m + row) * ACT_BITS_WORDS);
+                const int ua = ((t < 16) ? (t & 1) * 128 : 0) + colA, ub = ((t < 16) ? (t & 1) * 128 : 0) + colB;   // unit index
+                bh[ua >> 4] = (uint16_t)bwa;         // bit c of 32-bit word w = unit 32 w + c  (little-endian halves)
+                bh[ub >> 4] = (uint16_t)bwb;
+              }
             }
           }
           // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11.
