@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
         const uint16_t* bh = reinterpret_cast<const uint16_t*>(a.bits + ((int64_t)layer * a.m + row) * 8);
         const uint32_t mA = valid ? (uint32_t)__ldg(bh + ((h * 128 + colA) >> 4)) : 0u;
         const uint32_t mB = valid ? (uint32_t)__ldg(bh + ((h * 128 + colB) >> 4)) : 0u;
-        wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 311, a.status);
+        wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 311, a.status);
         tc_fence_after();
         uint32_t v[32];
         if constexpr (EPI_SPLIT) { tmem_ld_x16(acc_addr + colA, v); tmem_ld_x16(acc_addr + colB, v + 16); }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
         }
         if (t < 14) {
           if (h == 0 && t >= 2) {            // slot 0 still feeds the odd half-step issued behind this one
-            wait_bar(&misc->a_free, (uint32_t)(ti * 6 + (p - 1)) & 1u, misc, 312, a.status);
+            wait_bar_warp(&misc->a_free, (uint32_t)(ti * 6 + (p - 1)) & 1u, misc, 312, a.status);
             tc_fence_after();
           }
           if constexpr (EPI_SPLIT) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
             store_row16_paired(dst + colA, W_HID, f, valid, ok_other, r & 31);
             store_row16_paired(dst + colB, W_HID, f + 16, valid, ok_other, r & 31);
           } else {
-            store_row32_quad(dst + colA, W_HID, f, row - (r & 3), a.m, r & 31);
+            if (valid) store_row32(dst + colA, f);
           }
         }
 #endif

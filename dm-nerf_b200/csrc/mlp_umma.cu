@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             bb[jj] = __ldg(reinterpret_cast<const float4*>(bias + colA) + jj);
             bb[4 + jj] = __ldg(reinterpret_cast<const float4*>(bias + colB) + jj);
           }
-          { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+          { KP_T0(); wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
           tc_fence_after();
 #ifdef DMN_KPROF
           const long long kp_body0 = clock64();
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
               KP_T0();
 #ifndef DMN_EXP_NO_AFREE      /* timing experiment only (results are garbage): the even epilogue does not wait for slot 0 */
-              wait_bar(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
+              wait_bar_warp(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
 #endif
               KP_ADD(9);
               tc_fence_after();
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 store_row16_paired(dst + colA, width, f, valid, ok_other, r & 31);
                 store_row16_paired(dst + colB, width, f + 16, valid, ok_other, r & 31);
               } else {
-                store_row32_quad(dst + colA, width, f, row - (r & 3), a.m, r & 31);
+                if (valid) store_row32(dst + colA, f);
               }
 #endif
               if (valid) {
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           continue;
         }
         const Step& st = prog.step[t];
-        { KP_T0(); wait_bar(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+        { KP_T0(); wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
         tc_fence_after();
         if (cg >= 2) {
           // the instance head is drained by column groups 0 and 1 (256 threads, q = 64-column half) alone

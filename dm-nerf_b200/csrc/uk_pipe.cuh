@@ -30,10 +30,9 @@ constexpr int EPI_THREADS = 512;           // 16 prologue / epilogue warps: 4 TM
 // the epilogue, so the next layer's MMAs on it are queued well before the tensor pipe runs dry (with 32 contiguous columns per
 // thread both chunks appear at the very end, a hair later than the pipe needs them: ~0.7 k idle cycles per layer).
 // Measured (profiles/r02_ab_and_kprof.md): the split mapping changes the fused render kernel by < 0.5 % (the kernel is bound by
-// board power, not by these dependency waits), while 32 CONTIGUOUS columns per thread let four lanes write whole 128-byte lines
-// of the training planes: the default is the contiguous mapping.
+// board power, not by these dependency waits).  DMN_EPI_SPLIT=0 selects 32 contiguous columns per thread (round-1 mapping).
 #ifndef DMN_EPI_SPLIT
-#define DMN_EPI_SPLIT 0
+#define DMN_EPI_SPLIT 1
 #endif
 constexpr bool EPI_SPLIT = DMN_EPI_SPLIT != 0;
 constexpr int CHUNK_THREADS = EPI_SPLIT ? 512 : 256;   // arrivals that publish one 64-column K chunk of a half-step's output
@@ -104,6 +103,13 @@ static __device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Mi
 }
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
   if (!mbar_try_wait(bar, parity)) slow_wait(bar, parity, misc, code, status);
+}
+
+// Wait executed by a WHOLE warp (prologue / epilogue roles): the lanes can leave the spin at different times, and what follows
+// (tcgen05.ld/st .sync.aligned, named barriers, warp shuffles) needs all 32 of them together -- reconverge explicitly.
+__device__ __forceinline__ void wait_bar_warp(uint64_t* bar, uint32_t parity, Misc* misc, int code, int32_t* status) {
+  wait_bar(bar, parity, misc, code, status);
+  __syncwarp();
 }
 
 // Position in the weight ring (warp-uniform).
@@ -211,6 +217,7 @@ __device__ __forceinline__ void store_row16(float* __restrict__ dst, const float
 // ok_own / ok_other: the two rows exist.  All 32 lanes must call it.
 __device__ __forceinline__ void store_row16_paired(float* __restrict__ dst, int64_t row_stride, const float* v, bool ok_own,
                                                    bool ok_other, int lane) {
+  __syncwarp();
   const bool odd = (lane & 1) != 0;
   float x[8];
 #pragma unroll
@@ -229,40 +236,6 @@ __device__ __forceinline__ void store_row16_paired(float* __restrict__ dst, int6
   if (ok_odd)
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pb), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]),
                  "f"(b[5]), "f"(b[6]), "f"(b[7]) : "memory");
-}
-
-// Four neighbouring lanes (rows 4k..4k+3 of the tile) store their 32-column groups TOGETHER: a 4 x 4 transpose of 8-float
-// blocks in two shuffle rounds, after which lane q holds block q of all four rows and every 256-bit store instruction writes
-// whole 128-byte lines (8 per instruction instead of 32 scattered sectors).  `dst` = this lane's own row (column of v[0]);
-// row_base = index of the quad's first row; all 32 lanes must call it.
-__device__ __forceinline__ void store_row32_quad(float* __restrict__ dst, int64_t row_stride, const float* v, int64_t row_base,
-                                                 int64_t n_rows, int lane) {
-  const int q = lane & 3;
-  const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0;
-  // round 1 (xor 1): lanes with bit 0 clear keep blocks 0, 2 and receive the partner's blocks 0, 2; the others blocks 1, 3
-  float xe[2][8], xo[2][8];             // [lower / upper block][8 floats] of the pair's even row / odd row
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float r0 = __shfl_xor_sync(0xffffffffu, b0 ? v[i] : v[8 + i], 1);          // partner's lower block of MY parity
-    const float r1 = __shfl_xor_sync(0xffffffffu, b0 ? v[16 + i] : v[24 + i], 1);    // partner's upper block of MY parity
-    xe[0][i] = b0 ? r0 : v[i];        xe[1][i] = b0 ? r1 : v[16 + i];
-    xo[0][i] = b0 ? v[8 + i] : r0;    xo[1][i] = b0 ? v[24 + i] : r1;
-  }
-  // round 2 (xor 2): lanes with bit 1 clear keep the lower blocks and receive the other pair's lower blocks; the others upper
-  float t[4][8];                         // block q of rows row_base + 0..3
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float re = __shfl_xor_sync(0xffffffffu, b1 ? xe[0][i] : xe[1][i], 2);
-    const float ro = __shfl_xor_sync(0xffffffffu, b1 ? xo[0][i] : xo[1][i], 2);
-    t[0][i] = b1 ? re : xe[0][i];   t[1][i] = b1 ? ro : xo[0][i];       // rows of pair A (quad rows 0, 1)
-    t[2][i] = b1 ? xe[1][i] : re;   t[3][i] = b1 ? xo[1][i] : ro;       // rows of pair B (quad rows 2, 3)
-  }
-  float* base = dst - (int64_t)q * row_stride + 8 * q;      // quad row 0, this lane's 8-float block
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (row_base + i < n_rows)
-      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base + (int64_t)i * row_stride), "f"(t[i][0]),
-                   "f"(t[i][1]), "f"(t[i][2]), "f"(t[i][3]), "f"(t[i][4]), "f"(t[i][5]), "f"(t[i][6]), "f"(t[i][7]) : "memory");
 }
 
 // 32 consecutive fp32 values of one row (128 B, 32-byte aligned) to global memory as four 256-bit stores: every store is a
