@@ -112,8 +112,11 @@ def render_rays(rays_o, rays_d, model_coarse, model_fine, z_vals_coarse, perturb
 class LazyRenderDict(dict):
     """Result of an inference dm_nerf() call.  The per-ray maps come from the single fused kernel; the per-sample tensors
     the reference also returns (`raw_*`, `z_vals_*`: consumed only by the training-time penalizer) are produced on
-    first access by re-rendering through the stage-by-stage kernels with the same random draws; entries that already exist
-    (the per-ray maps, possibly sliced by the caller) are left untouched."""
+    first access (indexing, `in`, get, keys / values / items, iteration, len) by re-rendering through the stage-by-stage kernels
+    with the same random draws; entries that already exist (the per-ray maps, possibly sliced by the caller) are left untouched.
+    Note: the lazily produced `z_vals_fine` / `raw_fine` come from that second render; on isolated rays an importance sample may
+    land in the neighbouring bin compared with the fused kernel's own fine depths (same arithmetic, different reduction order
+    in the coarse weights' last bits), so they describe the same distribution but are not bit-identical to what produced the maps."""
     LAZY = ("raw_fine", "raw_coarse", "z_vals_fine", "z_vals_coarse", "weights_fine", "weights_coarse")
 
     def __init__(self, data, rerender):
@@ -143,6 +146,23 @@ class LazyRenderDict(dict):
     def items(self):
         self._materialise()
         return super().items()
+
+    def values(self):
+        self._materialise()
+        return super().values()
+
+    def get(self, key, default=None):
+        if key in self.LAZY:
+            self._materialise()
+        return super().get(key, default)
+
+    def __iter__(self):
+        self._materialise()
+        return super().__iter__()
+
+    def __len__(self):
+        self._materialise()
+        return super().__len__()
 
 
 def dm_nerf(rays, position_embedder, view_embedder, model_coarse, model_fine, z_vals_coarse, args):

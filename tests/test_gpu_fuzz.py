@@ -53,7 +53,28 @@ def test_sample_pdf_fuzz(n, nb, ns, seed, det, sparse):
     ref = O.sample_pdf(bins, w, ns, det=det, u=u).numpy()
     got = sample_pdf(_cu(bins), _cu(w), ns, det=det, u=None if u is None else _cu(u)).cpu().numpy()
     assert got.shape == ref.shape and np.isfinite(got).all()
-    assert frac_bad(got, ref, 1e-4, 1e-5) <= 2e-2           # jumps of the inverse CDF at (almost) empty bins may move a sample
+    tol = 1e-5 + 1e-4 * np.abs(ref)
+    bad = np.abs(got - ref) > tol
+    assert bad.sum() <= max(2, 2e-2 * bad.size), (int(bad.sum()), bad.size)      # a tiny draw may have one or two ill-conditioned samples
+    if bad.any():
+        # Every miss must be one the inverse CDF itself makes ill-conditioned -- not an arithmetic error of the kernel:
+        #  (a) u within a few ulp of a CDF knot (searchsorted picks the neighbouring bin),
+        #  (b) a 3e-7 perturbation of the CDF (2 ulp of a value in [0,1]) already moves the sample by more than half the tolerance
+        #      (tiny denom = almost empty bin, helpers.py:150-152), or
+        #  (c) the reference's own arithmetic in fp64 lands elsewhere too.
+        uu = (torch.linspace(0.0, 1.0, ns).expand(n, ns) if det else u).double()
+        wd = w.double() + 1e-5
+        cdf = torch.cat([torch.zeros(n, 1, dtype=torch.float64), torch.cumsum(wd / wd.sum(-1, keepdim=True), -1)], -1)
+        knot = (uu[..., None] - cdf[:, None, :]).abs().min(-1).values.numpy() <= 4e-7                       # (a)
+        inds = torch.searchsorted(cdf.float().contiguous(), uu.float().contiguous(), right=True)
+        below, above = (inds - 1).clamp(min=0), inds.clamp(max=cdf.shape[-1] - 1)
+        denom = (torch.gather(cdf, -1, above) - torch.gather(cdf, -1, below))
+        width = (torch.gather(bins.double(), -1, above) - torch.gather(bins.double(), -1, below)).abs()
+        cond = (width * 3e-7 / denom.clamp(min=1e-12)).numpy() > 0.5 * tol                                    # (b)
+        twin = O.sample_pdf(bins.double(), w.double(), ns, det=det, u=None if u is None else u.double()).numpy()
+        twin_bad = np.abs(twin - ref) > tol                                                                   # (c)
+        unexplained = bad & ~(knot | cond | twin_bad)
+        assert not unexplained.any(), (int(unexplained.sum()), int(bad.sum()), got[unexplained][:4], ref[unexplained][:4])
     assert got.min() >= float(bins.min()) - 1e-4 and got.max() <= float(bins.max()) + 1e-4
     if det:
         assert (np.diff(got, axis=-1) >= -1e-6).all()

@@ -140,3 +140,50 @@ def test_z_val_sample_matches_reference_formula(golden_dir):
     assert z.shape == (7, 64) and z.stride(0) == 0
     np.testing.assert_array_equal(z[3].numpy(), g["z"])
     np.testing.assert_array_equal(z_val_sample(2, 0.0, 6.5, 64)[1].numpy(), g["z_replica"])
+
+
+def test_lazy_render_dict_behaves_like_a_dict():
+    """dm_nerf()'s inference result: the lazily produced per-sample tensors must show up through every dict access path."""
+    from dmnerf_b200.render import LazyRenderDict
+    calls = []
+
+    def rerender():
+        calls.append(1)
+        return {"rgb_fine": "again", "raw_fine": "RF", "raw_coarse": "RC", "z_vals_fine": "ZF", "z_vals_coarse": "ZC",
+                "weights_fine": "WF", "weights_coarse": "WC"}
+
+    d = LazyRenderDict({"rgb_fine": "fused", "depth_fine": "D"}, rerender)
+    assert "raw_fine" in d and not calls                     # membership does not trigger the second render
+    assert d["rgb_fine"] == "fused" and not calls
+    assert d.get("raw_fine") == "RF" and calls == [1]
+    assert d["rgb_fine"] == "fused"                          # existing entries are kept
+    assert set(d) >= {"raw_coarse", "z_vals_fine", "weights_coarse", "rgb_fine"} and len(d) == 8 and calls == [1]
+    d2 = LazyRenderDict({"rgb_fine": "fused"}, rerender)
+    assert "RF" in list(d2.values()) and d2.get("nope", 7) == 7
+    with pytest.raises(KeyError):
+        d2["nope"]
+
+
+def test_hungarian_host_logic_matches_the_oracle():
+    """The host half of the matched instance loss (assignment on the valid rows + unmatched channels appended, evaluator.py:42-50)
+    and the dense-gt -> row-index conversion, against the oracle's restatement on random cost matrices."""
+    from dmnerf_b200.evaluator import _reorder, _rows_of_dense_gt
+    from oracle import dmnerf_oracle as O
+    gen = torch.Generator().manual_seed(4)
+    for k, valid in ((13, 6), (59, 20), (6, 6)):
+        cost = torch.rand(k, k, generator=gen)
+        rows, cols = _reorder(cost, valid, k)
+        from scipy.optimize import linear_sum_assignment
+        r2, c2 = linear_sum_assignment(cost[:valid].numpy())
+        assert list(rows) == list(r2) and list(cols[:valid]) == list(c2)
+        assert sorted(cols) == list(range(k))
+    lab = torch.tensor([3, 0, 3, 7, 0])
+    valid = torch.unique(lab)
+    gt = torch.zeros(5, 9)
+    gt[:, :3] = torch.nn.functional.one_hot(lab)[..., valid].float()
+    assert _rows_of_dense_gt(gt).tolist() == [1, 0, 1, 2, 0]
+    gt[4] = 0
+    assert _rows_of_dense_gt(gt).tolist() == [1, 0, 1, 2, -1]
+    # and the oracle's ins_criterion runs on the same tiny case (sanity of the fixture generator's path)
+    pred = torch.sigmoid(torch.randn(5, 9, generator=gen))
+    assert np.isfinite(float(O.ins_criterion(pred, lab.float(), 9)[0].sum()))
