@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               rs[6] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(rs[3], rs[3]), __fmul_rn(rs[4], rs[4])), __fmul_rn(rs[5], rs[5])));
               rs[7] = ok ? 1.0f : 0.0f;
             }
-            asm volatile("bar.sync 3, 512;" ::: "memory");
+            named_bar_sync<3, 512>();
           }
           rlp = r >> 6; sip = r & 63;
         } else {
@@ -672,11 +672,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           // group 0 to composite this tile and draw the importance samples, then prepares the first fine tile in one piece
           // (the instance head of this tile is drained afterwards, off the critical path).
           if (cg != 0) {
-            asm volatile("bar.arrive 4, 512;" ::: "memory");
+            named_bar_arrive<4, 512>();
             if (early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_D | PRO_DONE); KP_ADD(10); }
           } else {
             if (early_ok(ti + 1)) prologue(ti + 1, PRO_DONE);
-            asm volatile("bar.sync 4, 512;" ::: "memory");
+            named_bar_sync<4, 512>();
             // rgb_linear (dm_nerf.py:102,105) and density_linear (dm_nerf.py:101): add the four column groups' partial
             // dot products in a fixed order
             const float4 s0 = misc->part[0][r], s1 = misc->part[1][r], s2 = misc->part[2][r], s3 = misc->part[3][r];
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               float excl = __shfl_up_sync(FULL, incl, 1);
               if (lane_i == 0) excl = 1.0f;
               if (lane_i == 31) fz->tot[wi] = incl;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              named_bar_sync<1, 128>();
               // transmittance entering this warp = carry of the ray x products of earlier warps of the same ray in this tile
               const int first_w = (j == 0) ? (rl * 2) : ((j == 2) ? (rl * 2) : 0);   // first warp of my ray inside this tile
               float pre = (FUSED && j >= 2) ? fz->carry[j][rl] : 1.0f;
@@ -735,30 +735,31 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               const int rr = r >> 6, t64 = r & 63;
               fz->vals[rr][t64] = fz->zc[rr][t64];
               if (t64 < FS - 1) fz->bins[rr][t64] = __fmul_rn(0.5f, __fadd_rn(fz->zc[rr][t64 + 1], fz->zc[rr][t64]));
-              asm volatile("bar.sync 1, 128;" ::: "memory");          // bins and this tile's weights fz->w are complete
+              named_bar_sync<1, 128>();          // bins and this tile's weights fz->w are complete
               const int64_t ray = item * 2 + rr;
               const float* wr = fz->w + rr * FS;
               const float* uu = (a.u && fz->ray[u_cur][rr][7] != 0.0f) ? a.u + ray * FI : nullptr;
               if (t64 < 32) ray_build_cdf([&](int k) { return wr[k + 1]; }, FS - 1, fz->cdf[rr], t64);
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              named_bar_sync<1, 128>();
               for (int sidx = t64; sidx < FI; sidx += 64)
                 fz->vals[rr][FS + sidx] = ray_sample_at(fz->bins[rr], fz->cdf[rr], FS - 1, uu ? uu[sidx] : linspace01(sidx, FI));
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              named_bar_sync<1, 128>();
               // both runs ascending (always, for the deterministic linspace)?  One vote for the pair keeps the barrier simple.
               const bool mine = (uu == nullptr) && ray_sorted_part(fz->vals[rr] + FS, FI, t64, 64) && ray_sorted_part(fz->vals[rr], FS, t64, 64);
               int all_sorted;
+              __syncwarp();
               asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.and.pred q, 1, 128, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
                            : "=r"(all_sorted) : "r"((int)mine) : "memory");
               if (all_sorted) ray_merge_part(fz->vals[rr], FS, fz->vals[rr] + FS, FI, fz->zf[rr], t64, 64);
               else ray_rank_part(fz->vals[rr], FF, fz->zf[rr], t64, 64);
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              named_bar_sync<1, 128>();
               if (a.zf_out && fz->ray[u_cur][rr][7] != 0.0f)
                 for (int k = t64; k < FF; k += 64) a.zf_out[ray * FF + k] = fz->zf[rr][k];
             }
           }
           }
           if (FUSED && j == 0) {
-            asm volatile("bar.sync 3, 512;" ::: "memory");            // fine depths visible to every prologue thread
+            named_bar_sync<3, 512>();            // fine depths visible to every prologue thread
             if (ti + 1 < my_tiles) { KP_T0(); prologue(ti + 1, PRO_ALL); KP_ADD(10); }
           }
           continue;
@@ -791,7 +792,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             mbar_arrive(&misc->epi_done[acc][1]);
           } else {
             // instance logits weighted by the (detached) weights: sum_i w_i raw_i[4+k]   (render.py:22-24)
-            asm volatile("bar.sync 2, 256;" ::: "memory");     // weights of this tile (fz->w) are complete
+            named_bar_sync<2, 256>();     // weights of this tile (fz->w) are complete
             const float wgt = fz->w[r];
             const int lane_i = r & 31;
             const int c_end = (st.n < q * 64 + 64) ? st.n : q * 64 + 64;
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
               mbar_arrive(&misc->epi_done[acc][0]);
               mbar_arrive(&misc->epi_done[acc][1]);
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");     // all running sums of this tile are in
+            named_bar_sync<2, 256>();     // all running sums of this tile are in
             // ---- rays that end in this tile: write their maps (render.py:19-26) and clear the sums
             const int done_lo = (j == 0) ? 0 : ((j == 2) ? 0 : ((j == 3) ? 1 : 2));
             const int done_hi = (j == 0) ? 2 : ((j == 2) ? 1 : ((j == 3) ? 2 : 2));

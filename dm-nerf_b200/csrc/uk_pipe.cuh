@@ -112,6 +112,19 @@ __device__ __forceinline__ void wait_bar_warp(uint64_t* bar, uint32_t parity, Mi
   __syncwarp();
 }
 
+// Named barriers are executed by whole warps and are .aligned: reconverge first (the lanes of a warp can be in different
+// convergence groups after a spin-wait; a warp arriving in two pieces would be counted twice).
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_sync() {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_arrive() {
+  __syncwarp();
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
 // Position in the weight ring (warp-uniform).
 struct Ring {
   uint32_t slot, phase;

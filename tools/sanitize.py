@@ -31,5 +31,21 @@ with torch.no_grad():
 nc.train(); nf.train()
 out = render_rays_grad(ro, rd, nc, nf, z, perturb=1.0)
 (out["rgb_fine"].sum() + out["ins_fine"].sum() + out["raw_coarse"].sum() * 1e-3).backward()
+# round-2 kernels: ray selection, Hungarian-matched loss, penalizer (both tile sizes), exchanger-free edit primitives
+import types                                             # noqa: E402
+from dmnerf_b200.helpers import get_select_full          # noqa: E402
+from dmnerf_b200.evaluator import ins_criterion          # noqa: E402
+from dmnerf_b200.penalizer import ins_penalizer          # noqa: E402
+img = torch.rand(48, 64, 3, device=dev)
+lab = (torch.arange(48 * 64, device=dev).reshape(48, 64) % 5).to(torch.int16)
+np.random.seed(0)
+tc, ti, rays = get_select_full(img, torch.from_numpy(wl["c2w"]).to(dev), synth.dmsr_intrinsics(48, 64), lab, 64)
+pred = torch.sigmoid(torch.randn(64, 13, device=dev)).requires_grad_(True)
+ins_criterion(pred, ti, 13)[0].sum().backward()
+pargs = types.SimpleNamespace(tolerance=0.05, deta_w=0.05)
+for cc in (18, 64, 132):
+    praw = torch.randn(9, 50, cc, device=dev, requires_grad=True)
+    pz = torch.rand(9, 50, device=dev).sort(-1).values * 11 + 4
+    ins_penalizer(praw, pz, pz[:, 20].clone(), torch.randn(9, 3, device=dev), pargs).sum().backward()
 get_context(dev).sync_check()
 print("sanitize run ok", float(a["rgb_fine"].sum()), float(b["rgb_fine"].sum()), float(c["rgb_fine"].sum()))
