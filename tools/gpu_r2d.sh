@@ -1,8 +1,8 @@
 #!/bin/bash
 # Round-2 GPU session D: full parity suite + ncu evidence (launch lists, full-set captures of the four tensor-core kernels).
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --durations=5 > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.txt
-tail -12 gpurun_out/pytest_gpu.txt
+# (parity suite: run by tools/gpu_final.sh)
+
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_render.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/bench_under_ncu.txt 2>&1; echo "launch list (render) exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_train.csv \
