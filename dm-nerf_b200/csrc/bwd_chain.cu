@@ -35,7 +35,7 @@ struct CArgs {
   const float* d_out;         // d raw [M, C]: column 3 = d sigma
   int32_t ldc;
   const float* w_dens;        // density_linear.weight [256]
-  const uint32_t* bits;       // ActPlanes::bits: [10 planes][M][8 words]
+  const uint16_t* bits;       // ActPlanes::bits: [10 planes][16 groups][M] (row-fastest 16-bit groups)
   float* dy[8];               // dY(l) [M,256], l = 0..7
   int64_t m;
   int32_t* status;
@@ -188,9 +188,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
         const uint32_t slot_addr = tbase + lane_sel + TC_SLOT + h * SLOT_COLS;
         const uint32_t hiA = slot_addr + cA * 32 + ((colA & 63) >> 1), hiB = slot_addr + cB * 32 + ((colB & 63) >> 1);
         // ReLU masks of the two 16-unit groups, fetched before the accumulator is waited for
-        const uint16_t* bh = reinterpret_cast<const uint16_t*>(a.bits + ((int64_t)layer * a.m + row) * 8);
-        const uint32_t mA = valid ? (uint32_t)__ldg(bh + ((h * 128 + colA) >> 4)) : 0u;
-        const uint32_t mB = valid ? (uint32_t)__ldg(bh + ((h * 128 + colB) >> 4)) : 0u;
+        const uint32_t mA = valid ? (uint32_t)__ldg(a.bits + act_bits_index(layer, (h * 128 + colA) >> 4, row, a.m)) : 0u;
+        const uint32_t mB = valid ? (uint32_t)__ldg(a.bits + act_bits_index(layer, (h * 128 + colB) >> 4, row, a.m)) : 0u;
         wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 311, a.status);
         tc_fence_after();
         uint32_t v[32];
@@ -266,7 +265,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
 // One thread per (row, hidden unit); the head weights live in shared memory.
 constexpr int HEAD_ROWS = 4;        // rows per iteration: one barrier pair per 4 rows
 __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict__ d_out, int C, int64_t m, const float* __restrict__ w_rgb,
-                                                        const float* __restrict__ w_ins, int ins1, const uint32_t* __restrict__ bits,
+                                                        const float* __restrict__ w_ins, int ins1, const uint16_t* __restrict__ bits,
                                                         float* __restrict__ s12, int rows_per_block) {
   extern __shared__ float sm[];
   float* wi = sm;                         // [ins1][128]
@@ -300,29 +299,29 @@ __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict_
     for (int q = 0; q < HEAD_ROWS; ++q) {
       if (q >= nr) break;
       const int64_t rq = row + q;
-      const uint32_t br = bits[((int64_t)8 * m + rq) * 8 + (j >> 5)], bi = bits[((int64_t)9 * m + rq) * 8 + (j >> 5)];
-      s12[rq * 256 + j] = ((br >> (j & 31)) & 1u) ? a1[q] : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
-      s12[rq * 256 + 128 + j] = ((bi >> (j & 31)) & 1u) ? a2[q] : 0.0f;
+      const uint32_t br = bits[act_bits_index(8, j >> 4, rq, m)], bi = bits[act_bits_index(9, j >> 4, rq, m)];
+      s12[rq * 256 + j] = ((br >> (j & 15)) & 1u) ? a1[q] : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
+      s12[rq * 256 + 128 + j] = ((bi >> (j & 15)) & 1u) ? a2[q] : 0.0f;
     }
   }
 }
 
 // ReLU masks from saved fp32 activation planes (exact-fp32 CUDA-core forward: it does not write ActPlanes::bits itself).
-__global__ void mask_bits_kernel(const float* __restrict__ plane, int width, int64_t m, uint32_t* __restrict__ bits_plane) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (row, 32-column word)
-  const int words = width / 32;
-  if (idx >= m * words) return;
-  const int64_t row = idx / words;
-  const int w = (int)(idx % words);
-  const float4* src = reinterpret_cast<const float4*>(plane + row * width + w * 32);
+__global__ void mask_bits_kernel(const float* __restrict__ plane, int width, int64_t m, uint16_t* __restrict__ bits, int pl) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (group, row), rows fastest
+  const int groups = width / 16;
+  if (idx >= m * groups) return;
+  const int g = (int)(idx / m);
+  const int64_t row = idx % m;
+  const float4* src = reinterpret_cast<const float4*>(plane + row * width + g * 16);
   uint32_t b = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const float4 q = __ldg(src + i);
     b |= (q.x > 0.0f ? 1u : 0u) << (4 * i) | (q.y > 0.0f ? 1u : 0u) << (4 * i + 1) | (q.z > 0.0f ? 1u : 0u) << (4 * i + 2) |
          (q.w > 0.0f ? 1u : 0u) << (4 * i + 3);
   }
-  bits_plane[row * 8 + w] = b;
+  bits[act_bits_index(pl, g, row, m)] = (uint16_t)b;
 }
 
 }  // namespace bk
@@ -333,14 +332,14 @@ int launch_mask_bits(float* acts, int64_t m, cudaStream_t st) {
   for (int pl = 0; pl < 10; ++pl) {
     const float* src = pl < 8 ? ap.h[pl] : (pl == 8 ? ap.rgb_hid : ap.ins_hid);
     const int width = pl < 8 ? W_HID : W_HID / 2;
-    const int64_t total = m * (width / 32);
-    bk::mask_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, width, m, ap.bits + (int64_t)pl * m * 8);
+    const int64_t total = m * (width / 16);
+    bk::mask_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, width, m, ap.bits, pl);
     DMN_LAUNCH_OK();
   }
   return 0;
 }
 
-int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s12, cudaStream_t st) {
+int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint16_t* bits, float* s12, cudaStream_t st) {
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   if (m == 0) return 0;
   const int rows = 64;
@@ -354,7 +353,7 @@ int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const ui
 }
 
 // dY(7..0) of one network from d rgb_hid (s1) and d sigma (column 3 of d_out).  dy: 8 planes [m,256].
-int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint32_t* bits, int64_t m,
+int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint16_t* bits, int64_t m,
                      float* const* dy, cudaStream_t st) {
   using namespace bk;
   DMN_CHECK(w.ready && w.extra, "bwd_chain: weights not packed (call dmnerf_set_weights first)");

@@ -48,12 +48,17 @@ __host__ __device__ inline int layer_in(int l) {
 // Activations saved by the training forward of one network (planes of row-major [M, width] matrices, in this order):
 //   H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128] | emb [M,90]
 // (the 90-wide plane comes last so every other plane starts 16-byte aligned for any M)
-// ... | bits: ReLU masks, 1 bit per unit, [10 planes][M][8 words] (planes 0..7 = H0..H7, 8 = rgb_hid, 9 = ins_hid (4 words used);
-//           bit c of word w = unit 32 w + c is positive) -- what the fused gradient chain (bwd_chain.cu) reads instead of the planes
-constexpr int ACT_BITS_PLANES = 10, ACT_BITS_WORDS = 8;
+// ... | bits: ReLU masks, 1 bit per unit, as 16-bit groups stored ROW-FASTEST: [10 planes][16 groups][M] uint16 (planes 0..7 =
+//           H0..H7, 8 = rgb_hid, 9 = ins_hid (8 groups used); bit c of group g = unit 16 g + c is positive).  A warp (32
+//           consecutive rows, one group) reads or writes 64 contiguous bytes -- what the fused gradient chain (bwd_chain.cu) reads
+//           instead of the planes.
+constexpr int ACT_BITS_PLANES = 10, ACT_BITS_WORDS = 8, ACT_BITS_GROUPS = 16;
+__host__ __device__ inline int64_t act_bits_index(int plane, int group, int64_t row, int64_t m) {
+  return ((int64_t)plane * ACT_BITS_GROUPS + group) * m + row;
+}
 constexpr int ACT_FLOATS_PER_SAMPLE = CH_IN + 8 * W_HID + 2 * W_HID + 2 * (W_HID / 2) + ACT_BITS_PLANES * ACT_BITS_WORDS;   // 2986
 struct ActPlanes {
-  float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid; uint32_t* bits;
+  float* emb; float* h[8]; float* rgb_feat; float* ins_feat; float* rgb_hid; float* ins_hid; uint16_t* bits;
 };
 __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
   ActPlanes a;
@@ -64,7 +69,7 @@ __host__ __device__ inline ActPlanes act_planes(float* base, int64_t m) {
   a.rgb_hid = p; p += m * (W_HID / 2);
   a.ins_hid = p; p += m * (W_HID / 2);
   a.emb = p; p += m * CH_IN;
-  a.bits = reinterpret_cast<uint32_t*>(p);
+  a.bits = reinterpret_cast<uint16_t*>(p);
   return a;
 }
 
@@ -135,8 +140,8 @@ int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* ac
                         float* scratch, int feats_missing, cudaStream_t st);
 // Fused gradient chain (bwd_chain.cu)
 int launch_mask_bits(float* acts, int64_t m, cudaStream_t st);
-int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint32_t* bits, float* s12, cudaStream_t st);
-int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint32_t* bits, int64_t m,
+int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const uint16_t* bits, float* s12, cudaStream_t st);
+int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, const float* d_out, const uint16_t* bits, int64_t m,
                      float* const* dy, cudaStream_t st);
 size_t mlp_backward_scratch_floats(int64_t m);
 

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
     // Epilogue of local tile ti (accumulator ti & 1): warp w -> rows (w & 3) * 32 + lane, columns (w >> 2) * 64 ...
     auto epilogue = [&](int64_t ti) {
       if (!mbar_wait(&acc_done[ti & 1], (uint32_t)(ti >> 1) & 1)) fail(status, 602);
+      __syncwarp();                 // lanes can leave the spin at different times; tcgen05.ld below is .sync.aligned
       tc_fence_after();
       const int64_t m = tile_row(ti);
       const int col0 = (warp >> 2) * 64;
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
       if (tid < NA) atomicAdd(colsum + tid, csum_s[tid]);
     }
     if (!mbar_wait(&acc_done, 0)) fail(status, 612);
+    __syncwarp();                   // lanes can leave the spin at different times; tcgen05.ld below is .sync.aligned
     tc_fence_after();
     // warp w -> accumulator rows (w & 3) * 32 + lane, 32-column groups (w >> 2), (w >> 2) + 4, ...
 #pragma unroll 1

@@ -638,10 +638,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { bwa |= (f[i] > 0.0f ? 1u : 0u) << i; bwb |= (f[16 + i] > 0.0f ? 1u : 0u) << i; }
                 const int plane = (t < 16) ? (t >> 1) : ((t == T_RGB_HID) ? 8 : 9);
-                uint16_t* bh = reinterpret_cast<uint16_t*>(ap.bits + ((int64_t)plane * a.m + row) * ACT_BITS_WORDS);
                 const int ua = ((t < 16) ? (t & 1) * 128 : 0) + colA, ub = ((t < 16) ? (t & 1) * 128 : 0) + colB;   // unit index
-                bh[ua >> 4] = (uint16_t)bwa;         // bit c of 32-bit word w = unit 32 w + c  (little-endian halves)
-                bh[ub >> 4] = (uint16_t)bwb;
+                ap.bits[act_bits_index(plane, ua >> 4, row, a.m)] = (uint16_t)bwa;     // row-fastest: a warp writes 64 contiguous bytes
+                ap.bits[act_bits_index(plane, ub >> 4, row, a.m)] = (uint16_t)bwb;
               }
             }
           }

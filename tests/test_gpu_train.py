@@ -203,11 +203,13 @@ def test_tensor_core_training_forward_saves_the_reference_activations(m):
     assert scale_err(planes["ins_hid"], ih.numpy()) <= 1e-4
     out = O.mlp_forward(p, x).numpy()
     assert scale_err(raw.cpu().numpy(), out) <= 1e-4
-    # ReLU masks, 1 bit per unit (what the fused gradient chain reads): [10 planes][m][8 words] after the embedded inputs
-    bits = acts[off:off + 10 * m * 8].view(np.uint32).reshape(10, m, 8)
+    # ReLU masks, 1 bit per unit (what the fused gradient chain reads): [10 planes][16 groups][m] uint16, rows fastest, after
+    # the embedded inputs; bit c of group g = unit 16 g + c
+    bits = acts[off:off + 10 * m * 8].view(np.uint16).reshape(10, 16, m)
     for pl, name in enumerate(["h%d" % l for l in range(8)] + ["rgb_hid", "ins_hid"]):
         width = planes[name].shape[1]
-        unpacked = ((bits[pl][:, :width // 32, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(m, width)
+        grp = bits[pl][:width // 16].astype(np.uint32)                                        # [groups, m]
+        unpacked = ((grp[:, :, None] >> np.arange(16, dtype=np.uint32)) & 1).transpose(1, 0, 2).reshape(m, width)
         assert np.array_equal(unpacked.astype(bool), planes[name] > 0), name
 
 
