@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) gemm_nn_kernel(const float* __restrict__ 
 
 // C[n, k] += sum_{m in split} A[m, n] B[m, k]   (C zero-initialised by the caller; fp32 atomics across splits)
 __global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                      float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int64_t rows_per_split) {
+                                                      float* __restrict__ Cm, int ldc, int64_t M, int N, int K, int64_t rows_per_split,
+                                                      int64_t b_cm) {
   __shared__ float As[GK][GT];
   __shared__ float Bs[GK][GT];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ 
       const int r = idx / GT, c = idx % GT;
       const int64_t m = m0 + r;
       As[r][c] = (m < me && n0 + c < N) ? A[m * lda + n0 + c] : 0.0f;
-      Bs[r][c] = (m < me && k0 + c < K) ? B[m * ldb + k0 + c] : 0.0f;
+      Bs[r][c] = (m < me && k0 + c < K) ? (b_cm ? B[(int64_t)(k0 + c) * b_cm + m] : B[m * ldb + k0 + c]) : 0.0f;
     }
     __syncthreads();
 #pragma unroll
@@ -450,17 +451,19 @@ static int gemm_nt_bias(const float* A, int lda, const float* W, int ldw, const 
 static int colsum(const float* A, int lda, float* out, int64_t M, int N, cudaStream_t st);
 
 // colsum_out != NULL: also colsum_out[n] += sum_m A[m, n] (the bias gradient of the same layer, zero-initialised by the caller).
+// b_cm != 0: B is column-major (element (m, k) at B[k * b_cm + m]) -- the embedded-input plane of the training forward.
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K, cudaStream_t st,
-                   float* colsum_out = nullptr) {
-  if (bwd_use_tc() && M >= 512 && gemm_tn_tc_supported(N, K)) return launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, colsum_out, M, N, K, 0, st);
-  if (bwd_use_tc() && M >= 512 && !colsum_out && gemm_tn_tc_supported(K, N))      // narrow dY, wide X: compute (X^T dY)^T
+                   float* colsum_out = nullptr, int64_t b_cm = 0) {
+  if (bwd_use_tc() && M >= 512 && gemm_tn_tc_supported(N, K))
+    return launch_gemm_tn_tc(A, lda, B, ldb, C, ldc, colsum_out, M, N, K, 0, st, b_cm);
+  if (bwd_use_tc() && M >= 512 && !colsum_out && !b_cm && gemm_tn_tc_supported(K, N))      // narrow dY, wide X: compute (X^T dY)^T
     return launch_gemm_tn_tc(B, ldb, A, lda, C, ldc, nullptr, M, K, N, 1, st);
   if (colsum_out) {
     int rc = colsum(A, lda, colsum_out, M, N, st);
     if (rc) return rc;
   }
   const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
-  if (aligned && N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && N >= 64 && K >= 64) {
+  if (aligned && !b_cm && N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && N >= 64 && K >= 64) {
     const int tiles_b = ((N + BT - 1) / BT) * ((K + BT - 1) / BT);
     int64_t splits = (3 * 148 + tiles_b - 1) / tiles_b;
     int64_t rows = (M + splits - 1) / splits;
@@ -479,7 +482,7 @@ static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, i
   if (rows < 256) rows = 256;
   splits = (M + rows - 1) / rows;
   dim3 grid((unsigned)((N + GT - 1) / GT), (unsigned)((K + GT - 1) / GT), (unsigned)splits);
-  gemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rows);
+  gemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rows, b_cm);
   DMN_LAUNCH_OK();
   return 0;
 }
@@ -597,7 +600,7 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   DMN_CUDA(cudaMemcpyAsync(gb(L_INS_OUT), cs + 4, ins1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // ---- folded head layers (dm_nerf.py:89-99): one GEMM against h7 for both branches
   R(gemm_tn(S12, 256, ap.h[7], 256, PQ, 256, m, 256, 256, st, c12));
-  R(gemm_tn(S12, 256, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));      // view-direction columns
+  R(gemm_tn(S12, 256, ap.emb + (int64_t)CH_POS * m, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st, nullptr, m));   // view-direction columns
   small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256);
   DMN_LAUNCH_OK();
   small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256);
@@ -612,10 +615,10 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   for (int l = 7; l >= 0; --l) {
     const int kin = layer_in(l);
     if (l == 0) {
-      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st, gb(0)));
+      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st, gb(0), m));
     } else {
       R(gemm_tn(dY[l], 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));
-      if (l == 5) R(gemm_tn(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));    // skip input [h, pts]
+      if (l == 5) R(gemm_tn(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st, nullptr, m));    // skip input [h, pts]
     }
   }
 #undef R
@@ -665,7 +668,7 @@ int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* ac
   R(gemm_nn(d_ins, C, p.w[L_INS_OUT], 128, S2, 128, m, ins1, 128, 0, ap.ins_hid, st));    // through ReLU of ins_hid
   // ---- hidden head layers (dm_nerf.py:90-99)
   R(gemm_tn(S1, 128, ap.rgb_feat, 256, gw(L_RGB_HID), 283, m, 128, 256, st, gb(L_RGB_HID)));      // + bias gradient
-  R(gemm_tn(S1, 128, ap.emb + CH_POS, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st));
+  R(gemm_tn(S1, 128, ap.emb + (int64_t)CH_POS * m, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st, nullptr, m));
   R(gemm_tn(S2, 128, ap.ins_feat, 256, gw(L_INS_HID), 256, m, 128, 256, st, gb(L_INS_HID)));      // + bias gradient
   R(gemm_nn(S1, 128, p.w[L_RGB_HID], 283, S3, 256, m, 128, 256, 0, nullptr, st));         // d rgb_feature (no activation)
   R(gemm_nn(S2, 128, p.w[L_INS_HID], 256, S4, 256, m, 128, 256, 0, nullptr, st));         // d ins_feature
@@ -681,11 +684,11 @@ int launch_mlp_backward(const NetParams& p, const UmmaWeights* packed, float* ac
   for (int l = 7; l >= 0; --l) {
     const int kin = layer_in(l);
     if (l == 0) {
-      R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st));
+      R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st, nullptr, m));
       R(colsum(cur, 256, gb(0), m, 256, st));
     } else {
       R(gemm_tn(cur, 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));             // dW and db of layer l
-      if (l == 5) R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st));   // skip input [h, pts]
+      if (l == 5) R(gemm_tn(cur, 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st, nullptr, m));   // skip input [h, pts]
     }
     if (l > 0) {
       R(gemm_nn(cur, 256, p.w[l], kin, nxt, 256, m, 256, 256, 0, ap.h[l - 1], st));

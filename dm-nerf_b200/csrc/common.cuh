@@ -46,8 +46,9 @@ __host__ __device__ inline int layer_in(int l) {
 }
 
 // Activations saved by the training forward of one network (planes of row-major [M, width] matrices, in this order):
-//   H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128] | emb [M,90]
-// (the 90-wide plane comes last so every other plane starts 16-byte aligned for any M)
+//   H0..H7 [M,256] (post-ReLU trunk outputs) | rgb_feat [M,256] | ins_feat [M,256] | rgb_hid [M,128] | ins_hid [M,128] | emb [90,M]
+// (the embedded inputs are stored COLUMN-major, [90][M]: their writers own one row and a few columns each, so row-fastest storage
+//  makes every store instruction of a warp one contiguous 128-byte line; their only readers are three narrow dW GEMMs)
 // ... | bits: ReLU masks, 1 bit per unit, as 16-bit groups stored ROW-FASTEST: [10 planes][16 groups][M] uint16 (planes 0..7 =
 //           H0..H7, 8 = rgb_hid, 9 = ins_hid (8 groups used); bit c of group g = unit 16 g + c is positive).  A warp (32
 //           consecutive rows, one group) reads or writes 64 contiguous bytes -- what the fused gradient chain (bwd_chain.cu) reads
@@ -151,7 +152,7 @@ bool gemm_tn_tc_supported(int N, int K);
 int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
                       const float* mask, const float* bias, int w_kmajor, cudaStream_t st);
 int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
-                      int transpose, cudaStream_t st);
+                      int transpose, cudaStream_t st, int64_t b_cm = 0);
 int gemm_tc_check_status(cudaStream_t st);
 
 // Emptiness regulariser (penalizer.cu)

@@ -66,6 +66,14 @@ __device__ __forceinline__ void load_unit(Unit& u, const float* __restrict__ src
   }
 }
 
+// The same 8 values of a COLUMN-major matrix (element (r, c) at src[c * col_stride + r]): the embedded-input plane of the
+// training forward is stored that way (ActPlanes::emb) so that its writers are coalesced.
+__device__ __forceinline__ void load_unit_cm(Unit& u, const float* __restrict__ src, int64_t col_stride, int64_t r, int64_t r_end, int col,
+                                             int c_end) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u.v[i] = (r < r_end && col + i < c_end) ? __ldg(src + (int64_t)(col + i) * col_stride + r) : 0.0f;
+}
+
 // Split the unit into bf16 hi / lo and store it at (row, 16-byte unit cu) of the two swizzled slabs.
 __device__ __forceinline__ void store_unit(const Unit& u, uint8_t* hi, uint8_t* lo, int row, int cu) {
   uint32_t h[4], l[4];
@@ -278,7 +286,7 @@ constexpr int TN_STAGES = 3;
 template <int NA, int NB>
 __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                            int nb, float* __restrict__ partial, float* __restrict__ colsum, int64_t M,
-                                                           int64_t rows_per_cta, int vec_a, int vec_b, int32_t* status) {
+                                                           int64_t rows_per_cta, int vec_a, int vec_b, int64_t b_cm, int32_t* status) {
   constexpr int SA = NA / 64, SB = NB / 64;              // slabs per operand
   constexpr uint32_t STAGE = 2 * (SA + SB) * TN_SLAB;   // hi + lo
   constexpr int NH = NA / 128;                           // accumulators of 128 gradient rows
@@ -316,7 +324,10 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
     for (int i = 0; i < UPT; ++i) {
       const int U = tid + i * NT, slab = U >> 8, u = U & 255;
       if (slab < SA) load_unit(r[i], A, lda, m0 + (u >> 3), me, 64 * slab + (u & 7) * 8, NA, vec_a != 0);
-      else if (slab < SA + SB) load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb, vec_b != 0);
+      else if (slab < SA + SB) {
+        if (b_cm) load_unit_cm(r[i], B, b_cm, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb);
+        else load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb, vec_b != 0);
+      }
     }
   };
   auto stage = [&](Unit (&r)[UPT], int64_t q) {            // store chunk q from registers, prefetch chunk q + 2, multiply
@@ -518,7 +529,7 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
 // C[N, K] += A[M, N]^T B[M, K]  (N = 128 or 256 and K = 256, or K <= 64);  transpose != 0: the caller passes the WIDE matrix as A
 // and the narrow one (K <= 64 columns) as B and wants C[K, N] += B^T A.
 int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
-                      int transpose, cudaStream_t st) {
+                      int transpose, cudaStream_t st, int64_t b_cm) {
   using namespace tg;
   if (M <= 0) return 0;
   DevState* ds = nullptr;
@@ -545,10 +556,10 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 64)));
   }
   const int va = vec4_ok(A, lda), vb = vec4_ok(B, ldb);
-  if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
-  else if (N == 256 && NB == 256) gemm_tn_tc_kernel<256, 256><<<grid, NT, smem_of(256, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
-  else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
-  else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, g_status);
+  if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
+  else if (N == 256 && NB == 256) gemm_tn_tc_kernel<256, 256><<<grid, NT, smem_of(256, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
+  else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
+  else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
   DMN_LAUNCH_OK();
   reduce_partials_kernel<<<(N * NB / 4 + 63) / 64, 256, 0, st>>>(scratch, (int)grid, N, NB, K, C, ldc, transpose);
   DMN_LAUNCH_OK();

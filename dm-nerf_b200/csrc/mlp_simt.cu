@@ -141,7 +141,8 @@ mlp_simt_kernel(NetParams p, const float* __restrict__ x, const float* __restric
     ActPlanes ap;
     if (save) {
       ap = act_planes(acts, m);
-      for (int idx = tid; idx < rows_valid * CH_IN; idx += NT) ap.emb[row0 * CH_IN + idx] = E[(idx / CH_IN) * LDE + idx % CH_IN];
+      for (int idx = tid; idx < rows_valid * CH_IN; idx += NT)            // column-major [90][M] (common.cuh ActPlanes)
+        ap.emb[(int64_t)(idx / rows_valid) * m + row0 + idx % rows_valid] = E[(idx % rows_valid) * LDE + idx / rows_valid];
     }
 #define ACT(plane, width) (save ? (plane) + row0 * (width) : nullptr), rows_valid
 

@@ -402,10 +402,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
         constexpr int CNT = decltype(cntc)::value;
         if constexpr (!FUSED) {
           if (a.acts && validp) {
-            float* dst = act_planes(a.acts, a.m).emb + rowp * CH_IN + col0;
+            float* dst = act_planes(a.acts, a.m).emb + (int64_t)col0 * a.m + rowp;      // column-major [90][M]: coalesced per column
 #pragma unroll
             for (int i = 0; i < CNT; ++i)
-              if (col0 + i < CH_IN && (col0 >= CH_POS || col0 + i < CH_POS)) dst[i] = vals[i];
+              if (col0 + i < CH_IN && (col0 >= CH_POS || col0 + i < CH_POS)) dst[(int64_t)i * a.m] = vals[i];
           }
         }
       };

@@ -175,7 +175,8 @@ def test_tensor_core_training_forward_saves_the_reference_activations(m):
     planes = {}
     for name, width in [("h%d" % l, 256) for l in range(8)] + [("rgb_feat", 256), ("ins_feat", 256), ("rgb_hid", 128),
                                                               ("ins_hid", 128), ("emb", 90)]:
-        planes[name] = acts[off:off + m * width].reshape(m, width)
+        block = acts[off:off + m * width]
+        planes[name] = block.reshape(width, m).T if name == "emb" else block.reshape(m, width)      # emb is stored column-major
         off += m * width
     # oracle on the CPU
     p = O.to_torch(w)
