@@ -507,46 +507,57 @@ static bool bwd_use_chain() {
   return v != 0;
 }
 
-// C[m, n] (+)= sum_k A[m, k] W[n, k] + rowscale[m] * bias[n]   (small dense products of the folded head gradients)
-__global__ void __launch_bounds__(256) small_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                       const float* __restrict__ rowscale, const float* __restrict__ bias,
-                                                       float* __restrict__ Cm, int ldc, int M, int N, int K) {
-  __shared__ float As[GK][GT + 1];
-  __shared__ float Ws[GK][GT + 1];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += GK) {
-    for (int idx = tid; idx < GT * GK; idx += 256) {
-      const int r = idx / GK, c = idx % GK;
-      As[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.0f;
-      Ws[c][r] = (n0 + r < N && k0 + c < K) ? W[(size_t)(n0 + r) * ldw + k0 + c] : 0.0f;
-    }
+// Small dense products of the folded head gradients (128..256 x 256 outputs, contraction 128..256): 16 x 16 output tiles, one
+// output per thread, so that the launch fills the machine (a 64 x 64 tiling runs these on 8-16 CTAs at ~35 us apiece).
+//   small_nt_kernel:  C[m, n] = sum_k A[m, k] W[n, k] + rowscale[m] * bias[n]
+//   small_tn_kernel:  C[n, k] = sum_m A[m, n] B[m, k]                          (M small: the whole contraction in one CTA)
+constexpr int ST = 16;
+__global__ void __launch_bounds__(ST * ST) small_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                           const float* __restrict__ rowscale, const float* __restrict__ bias,
+                                                           float* __restrict__ Cm, int ldc, int M, int N, int K) {
+  __shared__ float As[ST][ST + 1], Ws[ST][ST + 1];
+  const int tx = threadIdx.x & (ST - 1), ty = threadIdx.x / ST;
+  const int m = blockIdx.x * ST + ty, n = blockIdx.y * ST + tx;
+  float acc = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += ST) {
+    As[ty][tx] = (m < M && k0 + tx < K) ? A[(size_t)m * lda + k0 + tx] : 0.0f;                       // As[row m][k]
+    const int wn = blockIdx.y * ST + ty;
+    Ws[ty][tx] = (wn < N && k0 + tx < K) ? W[(size_t)wn * ldw + k0 + tx] : 0.0f;                     // Ws[row n][k]
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
+    for (int kk = 0; kk < ST; ++kk) acc = fmaf(As[ty][kk], Ws[tx][kk], acc);
     __syncthreads();
   }
+  if (m < M && n < N) Cm[(size_t)m * ldc + n] = acc + (rowscale ? rowscale[m] * bias[n] : 0.0f);
+}
+
+__global__ void __launch_bounds__(ST * ST) small_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                           float* __restrict__ Cm, int ldc, int M, int N, int K) {
+  __shared__ float As[ST][ST + 1], Bs[ST][ST + 1];
+  const int tx = threadIdx.x & (ST - 1), ty = threadIdx.x / ST;
+  const int n = blockIdx.x * ST + ty, k = blockIdx.y * ST + tx;
+  float acc = 0.0f;
+  for (int m0 = 0; m0 < M; m0 += ST) {
+    As[ty][tx] = (m0 + ty < M && blockIdx.x * ST + tx < N) ? A[(size_t)(m0 + ty) * lda + blockIdx.x * ST + tx] : 0.0f;   // As[m][n]
+    Bs[ty][tx] = (m0 + ty < M && k < K) ? B[(size_t)(m0 + ty) * ldb + k] : 0.0f;                                          // Bs[m][k]
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int mm = m0 + ty * 4 + i;
-    if (mm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx + 16 * j;
-      if (n < N) Cm[(size_t)mm * ldc + n] = acc[i][j] + (rowscale ? rowscale[mm] * bias[n] : 0.0f);
-    }
+    for (int mm = 0; mm < ST; ++mm) acc = fmaf(As[mm][ty], Bs[mm][tx], acc);
+    __syncthreads();
   }
+  if (n < N && k < K) Cm[(size_t)n * ldc + k] = acc;
+}
+
+static int small_nt(const float* A, int lda, const float* W, int ldw, const float* rowscale, const float* bias, float* C, int ldc,
+                    int M, int N, int K, cudaStream_t st) {
+  small_nt_kernel<<<dim3((M + ST - 1) / ST, (N + ST - 1) / ST), ST * ST, 0, st>>>(A, lda, W, ldw, rowscale, bias, C, ldc, M, N, K);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+static int small_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+  small_tn_kernel<<<dim3((N + ST - 1) / ST, (K + ST - 1) / ST), ST * ST, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+  DMN_LAUNCH_OK();
+  return 0;
 }
 
 // The training backward with the fused gradient chain (bwd_chain.cu) and the heads folded like in the forward:
@@ -601,16 +612,14 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   // ---- folded head layers (dm_nerf.py:89-99): one GEMM against h7 for both branches
   R(gemm_tn(S12, 256, ap.h[7], 256, PQ, 256, m, 256, 256, st, c12));
   R(gemm_tn(S12, 256, ap.emb + (int64_t)CH_POS * m, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st, nullptr, m));   // view-direction columns
-  small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256);
-  DMN_LAUNCH_OK();
-  small_nt_kernel<<<dim3(2, 4), 256, 0, st>>>(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256);
-  DMN_LAUNCH_OK();
+  R(small_nt(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256, st));
+  R(small_nt(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256, st));
   DMN_CUDA(cudaMemcpyAsync(gb(L_RGB_HID), c1, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   DMN_CUDA(cudaMemcpyAsync(gb(L_INS_HID), c2, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  R(gemm_tn(p.w[L_RGB_HID], 283, P, 256, gw(L_RGB_FEAT), 256, 128, 256, 256, st));                 // W_rh[:, :256]^T P
-  R(gemm_tn(p.w[L_RGB_HID], 283, c1, 1, gb(L_RGB_FEAT), 1, 128, 256, 1, st));
-  R(gemm_tn(p.w[L_INS_HID], 256, Q, 256, gw(L_INS_FEAT), 256, 128, 256, 256, st));
-  R(gemm_tn(p.w[L_INS_HID], 256, c2, 1, gb(L_INS_FEAT), 1, 128, 256, 1, st));
+  R(small_tn(p.w[L_RGB_HID], 283, P, 256, gw(L_RGB_FEAT), 256, 128, 256, 256, st));                // W_rh[:, :256]^T P
+  R(small_tn(p.w[L_RGB_HID], 283, c1, 1, gb(L_RGB_FEAT), 1, 128, 256, 1, st));
+  R(small_tn(p.w[L_INS_HID], 256, Q, 256, gw(L_INS_FEAT), 256, 128, 256, 256, st));
+  R(small_tn(p.w[L_INS_HID], 256, c2, 1, gb(L_INS_FEAT), 1, 128, 256, 1, st));
   // ---- trunk (dm_nerf.py:83-87)
   for (int l = 7; l >= 0; --l) {
     const int kin = layer_in(l);

@@ -410,10 +410,13 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
         uint32_t v[32];
         tmem_ld_x32(tD + h * NB + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(mine + (size_t)n * NB + c0);
+        // slice layout (private to this kernel and reduce_partials_kernel): float4 ((h * NB/32 + g) * 8 + j) * 128 + row holds
+        // columns 32 g + 4 j .. + 3 of gradient row 128 h + row: the 32 lanes of a store instruction write 512 contiguous bytes
+        (void)n;
+        float4* dst = reinterpret_cast<float4*>(mine) + ((size_t)(h * (NB / 32) + c0 / 32) * 8) * 128 + (warp & 3) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          dst[(size_t)j * 128] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
     }
   } else {
@@ -449,7 +452,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   if (grp != 0 || idx4 >= total4) return;
   const float4 a = red[0][q], b = red[1][q], c = red[2][q], d = red[3][q];
   const float v[4] = {(a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w)};
-  const int idx = idx4 * 4, n = idx / NB, k0 = idx % NB;
+  // slice layout of gemm_tn_tc_kernel: float4 idx4 = ((h * NB/32 + g) * 8 + j) * 128 + row  ->  row 128 h + row, columns 32 g + 4 j ..
+  const int row = idx4 & 127, j = (idx4 >> 7) & 7, hg = idx4 >> 10, g = hg % (NB / 32), h = hg / (NB / 32);
+  const int n = h * 128 + row, k0 = g * 32 + 4 * j;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int k = k0 + e;
