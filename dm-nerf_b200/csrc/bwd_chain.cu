@@ -357,6 +357,8 @@ int launch_bwd_chain(const UmmaWeights& w, const NetParams& p, const float* s1, 
                      float* const* dy, cudaStream_t st) {
   using namespace bk;
   DMN_CHECK(w.ready && w.extra, "bwd_chain: weights not packed (call dmnerf_set_weights first)");
+  DMN_CHECK(umma_status_peek(w) == 0, "bwd_chain: an earlier tcgen05 launch reported protocol error %d (bounded wait expired); its results "
+            "are invalid -- destroy the context", umma_status_peek(w));
   if (m == 0) return 0;
   static PerDeviceOnce attr_once;
   if (attr_once.first())

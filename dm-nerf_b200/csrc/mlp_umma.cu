@@ -998,7 +998,10 @@ __global__ void bias_kernel(NetParams p, const float* __restrict__ fold_b_rgb, c
 // ================================================================================================ API
 struct UmmaExtra {            // hangs off UmmaWeights::image allocation bookkeeping
   uk::Program prog;
-  float* fold_w_rgb; float* fold_w_ins; float* fold_b; uk::PackStage* d_entries; int32_t* d_status;
+  float* fold_w_rgb; float* fold_w_ins; float* fold_b; uk::PackStage* d_entries;
+  int32_t* d_status;          // device alias of h_status
+  volatile int32_t* h_status;  // error word in mapped host memory: a kernel that gave up on a barrier writes its code here, and the
+                              // NEXT launch through this weight set refuses to start (a stalled launch can never pass silently)
   uint8_t* bwd_image;         // operand image of the gradient chain (bwd_chain.cu)
 };
 
@@ -1013,7 +1016,7 @@ void umma_weights_free(UmmaWeights& w) {
     if (x->fold_w_ins) cudaFree(x->fold_w_ins);
     if (x->fold_b) cudaFree(x->fold_b);
     if (x->d_entries) cudaFree(x->d_entries);
-    if (x->d_status) cudaFree(x->d_status);
+    if (x->h_status) cudaFreeHost((void*)x->h_status);
     if (x->bwd_image) cudaFree(x->bwd_image);
     delete x;
   }
@@ -1024,6 +1027,7 @@ bool umma_available(const UmmaWeights& w) { return w.ready; }
 const uint8_t* umma_bwd_image(const UmmaWeights& w) { return w.extra ? extra_of(w)->bwd_image : nullptr; }
 const float* umma_fold_w_rgb(const UmmaWeights& w) { return w.extra ? extra_of(w)->fold_w_rgb : nullptr; }
 int32_t* umma_status_word(const UmmaWeights& w) { return w.extra ? extra_of(w)->d_status : nullptr; }
+int umma_status_peek(const UmmaWeights& w) { return (w.extra && extra_of(w)->h_status) ? (int)*extra_of(w)->h_status : 0; }
 
 int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
   using namespace uk;
@@ -1042,8 +1046,9 @@ int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st) {
     DMN_CUDA(cudaMalloc((void**)&x->fold_b, 256 * sizeof(float)));
     DMN_CUDA(cudaMalloc((void**)&x->d_entries, (MAX_STAGES + BWD_IMAGE_STAGES / 2) * sizeof(PackStage)));
     DMN_CUDA(cudaMalloc((void**)&x->bwd_image, (size_t)BWD_IMAGE_STAGES * STAGE_BYTES));
-    DMN_CUDA(cudaMalloc((void**)&x->d_status, sizeof(int32_t)));
-    DMN_CUDA(cudaMemsetAsync(x->d_status, 0, sizeof(int32_t), st));
+    DMN_CUDA(cudaHostAlloc((void**)&x->h_status, sizeof(int32_t), cudaHostAllocMapped));
+    *x->h_status = 0;
+    DMN_CUDA(cudaHostGetDevicePointer((void**)&x->d_status, (void*)x->h_status, 0));
   }
   UmmaExtra* x = extra_of(w);
   // fold the activation-free feature layers into the following hidden layers (fp64 accumulate)
@@ -1115,6 +1120,8 @@ int launch_mlp_umma(const UmmaWeights& w, const NetParams& p, const float* x, co
   DMN_CHECK(w.ready && w.extra, "mlp(umma): weights not packed (call dmnerf_set_weights first)");
   DMN_CHECK((x != nullptr) != (rays_o != nullptr && rays_d != nullptr), "mlp(umma): pass either x or rays");
   DMN_CHECK(x != nullptr || z != nullptr || s == 1, "mlp(umma): points mode (z == NULL) takes one sample per row");
+  DMN_CHECK(umma_status_peek(w) == 0, "mlp(umma): an earlier tcgen05 launch reported protocol error %d (bounded wait expired); its results "
+            "are invalid -- destroy the context", umma_status_peek(w));
   if (m == 0) return 0;
   UmmaExtra* ex = extra_of(w);
   static PerDeviceOnce attr_once;
@@ -1142,6 +1149,8 @@ int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmner
   using namespace uk;
   DMN_CHECK(wc.ready && wf.ready && wc.extra && wf.extra, "render(umma): weights not packed");
   DMN_CHECK(wc.ins_num == wf.ins_num, "render(umma): coarse/fine ins_num differ");
+  DMN_CHECK(umma_status_peek(wc) == 0, "render(umma): an earlier tcgen05 launch reported protocol error %d (bounded wait expired); its "
+            "results are invalid -- destroy the context", umma_status_peek(wc));
   if (n == 0) return 0;
   UmmaExtra* ex = extra_of(wc);
   static PerDeviceOnce attr_once;
@@ -1174,8 +1183,8 @@ int launch_render_umma(const UmmaWeights& wc, const UmmaWeights& wf, const dmner
 int umma_check_status(const UmmaWeights& w, cudaStream_t st) {
   if (!w.extra) return 0;
   int32_t code = 0;
-  DMN_CUDA(cudaMemcpyAsync(&code, extra_of(w)->d_status, sizeof(code), cudaMemcpyDeviceToHost, st));
   DMN_CUDA(cudaStreamSynchronize(st));
+  code = (int32_t)*extra_of(w)->h_status;
   DMN_CHECK(code == 0, "tcgen05 MLP kernel reported protocol error %d (bounded wait expired)", code);
   return 0;
 }

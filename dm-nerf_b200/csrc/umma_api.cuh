@@ -22,6 +22,7 @@ constexpr int BWD_IMAGE_STAGES = (2 * 2 + 14 * 4) * 2;
 const uint8_t* umma_bwd_image(const UmmaWeights& w);
 const float* umma_fold_w_rgb(const UmmaWeights& w);      // [128][283]: W_rgb_hid[:, :256] W_rgb_feat | W_rgb_hid[:, 256:]
 int32_t* umma_status_word(const UmmaWeights& w);
+int umma_status_peek(const UmmaWeights& w);            // host-side read of the error word (mapped memory, no synchronisation)
 
 int umma_weights_pack(UmmaWeights& w, const NetParams& p, cudaStream_t st);
 void umma_weights_free(UmmaWeights& w);
