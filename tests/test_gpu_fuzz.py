@@ -128,3 +128,54 @@ def test_network_kernels_ragged_batches(m, ins_num, seed):
             assert got.shape == ref.shape
             for sl in (slice(0, 3), slice(3, 4), slice(4, None)):
                 assert scale_err(got[:, sl], ref[:, sl]) <= tol, (impl, m, ins_num, scale_err(got[:, sl], ref[:, sl]))
+
+
+@settings(**COMMON)
+@given(n=st.integers(5, 400), k=st.integers(2, 128), seed=st.integers(0, 2 ** 20), frac_present=st.floats(0.2, 1.0))
+def test_hungarian_loss_fuzz(n, k, seed, frac_present):
+    """Hungarian-matched instance loss (evaluator.py:19-74) at random batch sizes / channel counts / label subsets: loss parts
+    and the gradient w.r.t. the instance map against the oracle (which is pinned bit for bit to the reference)."""
+    from dmnerf_b200.evaluator import ins_criterion
+    gen = torch.Generator().manual_seed(seed)
+    n_present = max(1, min(k, int(round(frac_present * min(k, n)))))
+    present = torch.randperm(k, generator=gen)[:n_present]
+    lab = present[torch.randint(0, n_present, (n,), generator=gen)].float()
+    logits = torch.randn(n, k, generator=gen) * 2
+    logits[torch.arange(n), lab.long()] += 3.0
+    pred = torch.sigmoid(logits)
+    p_ref = pred.clone().requires_grad_(True)
+    ref = O.ins_criterion(p_ref, lab, k)
+    ref[0].sum().backward()
+    p_gpu = _cu(pred).requires_grad_(True)
+    got = ins_criterion(p_gpu, _cu(lab), k)
+    got[0].sum().backward()
+    for a, b in zip(got, ref):
+        assert abs(float(a.detach().float().sum()) - float(b.detach().float().sum())) <= 2e-5 * max(1.0, abs(float(b.detach().float().sum())))
+    g_ref = p_ref.grad.numpy()
+    g_got = p_gpu.grad.cpu().numpy()
+    scale = max(float(np.abs(g_ref).max()), 1e-12)
+    assert float(np.abs(g_got - g_ref).max()) <= 2e-5 * scale, (n, k, n_present)
+
+
+@settings(**COMMON)
+@given(n=st.integers(1, 40), s=st.integers(3, 200), k=st.integers(2, 128), seed=st.integers(0, 2 ** 20))
+def test_penalizer_fuzz(n, s, k, seed):
+    """Emptiness penalizer (penalizer.py:5-62) at ragged sizes and every shared-memory tile size of the kernels (C <= 48, <= 96,
+    <= 132): value and gradient against the oracle."""
+    import types
+    from dmnerf_b200.penalizer import ins_penalizer
+    gen = torch.Generator().manual_seed(seed)
+    raw = torch.randn(n, s, 4 + k, generator=gen) * 2
+    z = torch.rand(n, s, generator=gen).sort(-1).values * 11 + 4
+    rd = torch.randn(n, 3, generator=gen) * 1.3
+    depth = z[torch.arange(n), torch.randint(0, s, (n,), generator=gen)] + 0.01
+    r_ref = raw.clone().requires_grad_(True)
+    ref = O.ins_penalizer(r_ref, z, depth, rd, 0.05, 0.05)
+    ref.sum().backward()
+    r_gpu = _cu(raw).requires_grad_(True)
+    got = ins_penalizer(r_gpu, _cu(z), _cu(depth), _cu(rd), types.SimpleNamespace(tolerance=0.05, deta_w=0.05))
+    got.sum().backward()
+    assert abs(float(got.detach().sum()) - float(ref.detach().sum())) <= 2e-5 * max(1e-6, abs(float(ref.detach().sum())))
+    g_ref, g_got = r_ref.grad.numpy(), r_gpu.grad.cpu().numpy()
+    scale = max(float(np.abs(g_ref).max()), 1e-12)
+    assert float(np.abs(g_got - g_ref).max()) <= 2e-5 * scale and float(np.abs(g_got[..., :4]).max()) == 0.0
