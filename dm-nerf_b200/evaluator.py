@@ -62,32 +62,50 @@ def hungarian(pred_ins, gt_ins, valid_ins_num, ins_num):
 
 
 class _MatchedLoss(torch.autograd.Function):
+    """forward(pred_ins [N,K], gt_row [N] int32, valid_rows): gt_row[i] = cost-matrix row of ray i.  valid_rows = None: the rows
+    are the label VALUES themselves (labels in [0, K)); which of them occur is read off the row populations that come back with
+    the cost matrices -- ONE device->host hop per call.  valid_rows = n: rows 0..n-1 are the compacted labels (general path)."""
+
     @staticmethod
-    def forward(fctx, pred_ins, gt_row, n_valid):
+    def forward(fctx, pred_ins, gt_row, valid_rows):
         pred = pred_ins.detach().contiguous().float()
         n, k = pred.shape
         c = _costs(pred, gt_row)
-        order_row, order_col = _reorder(c["cost_ce"] + c["cost_siou"], n_valid, k)
         dev = pred.device
-        rows = torch.as_tensor(np.asarray(order_row), device=dev, dtype=torch.int64)
-        cols = torch.as_tensor(np.asarray(order_col[:n_valid]), device=dev, dtype=torch.int64)
+        if valid_rows is None:
+            host = torch.cat([(c["cost_ce"] + c["cost_siou"]).reshape(-1), c["row_count"]]).cpu().numpy()   # the one sync
+            scores_all, counts = host[:k * k].reshape(k, k), host[k * k:]
+            if int(round(float(counts.sum()))) != n:
+                raise _LabelsOutOfRange()
+            rows_present = np.nonzero(counts > 0)[0]                                        # ascending = torch.unique order
+            scores = scores_all[rows_present]
+        else:
+            rows_present = np.arange(int(valid_rows))
+            scores = (c["cost_ce"] + c["cost_siou"])[:int(valid_rows)].cpu().numpy()
+        n_valid = len(rows_present)
+        from scipy.optimize import linear_sum_assignment
+        row_ind, col_ind = linear_sum_assignment(scores)                                    # evaluator.py:45-47
+        unmatched = np.array(sorted(set(range(k)) - set(col_ind.tolist())), dtype=np.int64)
+        rows = torch.as_tensor(rows_present[row_ind], device=dev, dtype=torch.int64)
+        cols = torch.as_tensor(col_ind, device=dev, dtype=torch.int64)
         valid_ce = c["cost_ce"][rows, cols].mean()                                          # evaluator.py:28
         valid_siou = c["cost_siou"][rows, cols].mean()                                      # evaluator.py:34
         row_of_col = torch.full((k,), -1, device=dev, dtype=torch.int32)
         row_of_col[cols] = rows.to(torch.int32)
-        if len(order_col) != n_valid:                                                       # evaluator.py:30-33
-            un = torch.as_tensor(np.asarray(order_col[n_valid:]), device=dev, dtype=torch.int64)
+        if len(unmatched):                                                                  # evaluator.py:30-33
+            un = torch.as_tensor(unmatched, device=dev, dtype=torch.int64)
             invalid_ce = c["col_sum"][un].sum() / float(n * len(un))
         else:
             invalid_ce = torch.zeros((), device=dev)
         fctx.save_for_backward(pred, gt_row, row_of_col, c["tp"], c["col_sum"], c["row_count"])
         fctx.n_valid = int(n_valid)
         fctx.in_shape = pred_ins.shape
-        fctx.order = (order_row, order_col)
-        return valid_ce, invalid_ce, valid_siou
+        n_valid_t = torch.tensor(int(n_valid))                                               # host-side by-product, not differentiable
+        fctx.mark_non_differentiable(n_valid_t)
+        return valid_ce, invalid_ce, valid_siou, n_valid_t
 
     @staticmethod
-    def backward(fctx, g_ce, g_inv, g_siou):
+    def backward(fctx, g_ce, g_inv, g_siou, _g_n=None):
         pred, gt_row, row_of_col, tp, col_sum, row_count = fctx.saved_tensors
         n, k = pred.shape
         zero = pred.new_zeros(())
@@ -100,6 +118,10 @@ class _MatchedLoss(torch.autograd.Function):
         return d_pred.reshape(fctx.in_shape), None, None
 
 
+class _LabelsOutOfRange(Exception):
+    pass
+
+
 def ins_criterion(pred_ins, gt_labels, ins_num):
     """evaluator.py:19-37.  pred_ins [N, ins_num] (rendered instance probabilities, CUDA), gt_labels [N] (object ids)."""
     if not pred_ins.is_cuda:
@@ -108,13 +130,18 @@ def ins_criterion(pred_ins, gt_labels, ins_num):
         raise RuntimeError("ins_criterion: pred_ins %s / gt_labels %s / ins_num %d are inconsistent"
                            % (tuple(pred_ins.shape), tuple(gt_labels.shape), ins_num))
     labels = gt_labels.to(pred_ins.device).reshape(-1)
-    valid = torch.unique(labels)                                                            # evaluator.py:21 (sorted)
-    n_valid = int(valid.numel())
-    if n_valid > ins_num:
-        raise RuntimeError("ins_criterion: %d distinct labels for ins_num %d" % (n_valid, ins_num))
-    gt_row = torch.searchsorted(valid, labels).to(torch.int32).contiguous()                 # column of the one-hot, :25
-    valid_ce, invalid_ce, valid_siou = _MatchedLoss.apply(pred_ins, gt_row, n_valid)
-    if n_valid == ins_num:
+    try:
+        # object ids in [0, ins_num) (every dataset of the reference): the id IS the cost-matrix row; which ids occur comes back
+        # with the matrices, so the call makes a single device->host hop (no torch.unique synchronisation)
+        valid_ce, invalid_ce, valid_siou, n_valid_t = _MatchedLoss.apply(pred_ins, labels.to(torch.int32).contiguous(), None)
+    except _LabelsOutOfRange:
+        valid = torch.unique(labels)                                                        # evaluator.py:21 (sorted)
+        n_valid = int(valid.numel())
+        if n_valid > ins_num:
+            raise RuntimeError("ins_criterion: %d distinct labels for ins_num %d" % (n_valid, ins_num))
+        gt_row = torch.searchsorted(valid, labels).to(torch.int32).contiguous()             # column of the one-hot, :25
+        valid_ce, invalid_ce, valid_siou, n_valid_t = _MatchedLoss.apply(pred_ins, gt_row, n_valid)
+    if int(n_valid_t) == ins_num:
         invalid_ce = torch.tensor([0], device=pred_ins.device)                              # evaluator.py:33
     ins_loss_sum = valid_ce + invalid_ce + valid_siou                                       # evaluator.py:36
     return ins_loss_sum, valid_ce, invalid_ce, valid_siou
