@@ -27,8 +27,34 @@ def get_context(device):
     return ctx
 
 
+_param_cache = {}      # id(model) -> (weakref to the model, [(owner module, leaf name, parameter)], ins_num)
+
+
 def ordered_params(model):
-    """The 30 parameter tensors of a DM_NeRF-shaped module in reference state_dict order."""
+    """The 30 parameter tensors of a DM_NeRF-shaped module in reference state_dict order.  The walk over the module tree is
+    cached per model (a renderer called per 4096-ray chunk does this twice per call); the cache entry is revalidated against
+    the modules' own parameter tables, so re-assigned Parameter objects are picked up."""
+    import weakref
+    hit = _param_cache.get(id(model))
+    if hit is not None and hit[0]() is model and all(mod._parameters.get(leaf) is prm for mod, leaf, prm in hit[1]):
+        return [prm for _, _, prm in hit[1]], hit[2]
+    params, ins_num = _ordered_params_walk(model)
+    owners = {}
+    for mname, mod in model.named_modules():
+        for leaf, prm in mod._parameters.items():
+            if prm is not None:
+                owners[id(prm)] = (mod, leaf)
+    try:
+        _param_cache[id(model)] = (weakref.ref(model), [owners[id(prm)] + (prm,) for prm in params], ins_num)
+        if len(_param_cache) > 64:
+            for k in [k for k, v in _param_cache.items() if v[0]() is None]:
+                del _param_cache[k]
+    except (KeyError, TypeError):
+        pass
+    return params, ins_num
+
+
+def _ordered_params_walk(model):
     named = dict(model.named_parameters())
     ins_num = named["ins_linear.weight"].shape[0] - 1
     names = param_names(ins_num)
