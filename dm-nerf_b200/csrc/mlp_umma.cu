@@ -38,6 +38,17 @@ namespace uk {
 using namespace umma;
 enum ChunkKind : int8_t { CK_E = 6, CK_D = 7 };              // 0..3 = slot*2 + chunk
 
+#ifdef DMN_DEBUG_STALL
+}  // namespace uk
+}  // namespace dmnerf
+extern "C" __attribute__((visibility("default"))) int dmnerf_debug_stall(int* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, dmnerf::uk::g_stall_dbg, sizeof(int) * 641);
+}
+namespace dmnerf {
+namespace uk {
+#endif
+
 #ifdef DMN_KPROF
 __device__ long long g_kprof[160][16];
 __device__ long long g_ktrace[4][64];     // CTA 0, tile KTRACE_TILE: [mma step ready | mma step issued | epi acc_full seen | epi arrived][step]
@@ -197,6 +208,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       const uint8_t* image = (FUSED && (ti & 3) != 0) ? a.image_fine : a.image;
       for (int si = 0; si < n_stages; ++si) {
         const uint32_t off = prog.stage_off[si], bytes = prog.stage_off[si + 1] - off;
+        DBG_SITE(20000 + si);
         wait_bar(&misc->empty[ring.slot], ring.phase ^ 1, misc, 101, a.status);
         if (elect_one()) {
 #ifdef DMN_EXP_NOWEIGHTS     /* timing experiment only: no weight traffic (results are garbage) */
@@ -236,6 +248,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
       uint32_t& sn = (gd & 1) ? (c ? seen11 : seen10) : (c ? seen01 : seen00);
       const uint32_t need = gd / 2 + 1;
       while (sn < need) {
+        DBG_SITE(10000 + (int)(gd % 1000) * 4 + c);
         wait_bar(&misc->epi_done[gd & 1][c], sn & 1, misc, 201, a.status);
         ++sn;
       }
@@ -552,7 +565,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             bb[jj] = __ldg(reinterpret_cast<const float4*>(bias + colA) + jj);
             bb[4 + jj] = __ldg(reinterpret_cast<const float4*>(bias + colB) + jj);
           }
+          DBG_SITE(t * 100 + 1);
           { KP_T0(); wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+          DBG_SITE(t * 100 + 2);
           tc_fence_after();
 #ifdef DMN_KPROF
           const long long kp_body0 = clock64();
@@ -590,6 +605,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             if ((t & 1) == 0 && t >= 2) {
               // slot 0 still feeds the MMAs of the odd half-step issued behind this one: wait until it has released it
               KP_T0();
+              DBG_SITE(t * 100 + 3);
 #ifndef DMN_EXP_NO_AFREE      /* timing experiment only (results are garbage): the even epilogue does not wait for slot 0 */
               wait_bar_warp(&misc->a_free, (uint32_t)((t >> 1) - 1) & 1u, misc, 302, a.status);
 #endif
@@ -616,6 +632,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
 #ifdef DMN_KPROF
             if (blockIdx.x == 0 && ti >= KTRACE_TILE && ti < KTRACE_TILE + 2 && et == 0) g_ktrace[3][(ti - KTRACE_TILE) * 20 + t] = clock64();
 #endif
+            DBG_SITE(t * 100 + 4);
             if (t == 14) density_partial();      // off the critical path
           }
           if constexpr (!FUSED) {
@@ -630,7 +647,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
                 store_row16_paired(dst + colA, width, f, valid, ok_other, r & 31);
                 store_row16_paired(dst + colB, width, f + 16, valid, ok_other, r & 31);
               } else {
+#ifdef DMN_QUAD_STORE
+                DBG_SITE(t * 100 + 50);
+                store_row32_quad(dst + colA, width, f, row - (r & 3), a.m, r & 31);
+                DBG_SITE(t * 100 + 51);
+#else
                 if (valid) store_row32(dst + colA, f);
+#endif
               }
 #endif
               if (valid) {
@@ -645,6 +668,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
             }
           }
           // Prepare the next tile in the idle time after odd half-steps: E was last read by half-step 11.
+          DBG_SITE(t * 100 + 6);
           if ((t == 11 || t == 13) && early_ok(ti + 1)) {
             KP_T0();
             prologue(ti + 1, t == 11 ? PRO_E0 : PRO_E1);
@@ -670,6 +694,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           // After a coarse tile of the fused kernel the next tile's depths do not exist yet: everybody waits for column
           // group 0 to composite this tile and draw the importance samples, then prepares the first fine tile in one piece
           // (the instance head of this tile is drained afterwards, off the critical path).
+          DBG_SITE(t * 100 + 7);
           if (cg != 0) {
             named_bar_arrive<4, 512>();
             if (early_ok(ti + 1)) { KP_T0(); prologue(ti + 1, PRO_D | PRO_DONE); KP_ADD(10); }
@@ -764,7 +789,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_umma_kernel(const __grid_con
           continue;
         }
         const Step& st = prog.step[t];
+        DBG_SITE(t * 100 + 11);
         { KP_T0(); wait_bar_warp(&misc->acc_full[acc], (g / 2) & 1, misc, 301, a.status); KP_ADD(8); }
+        DBG_SITE(t * 100 + 12);
         tc_fence_after();
         if (cg >= 2) {
           // the instance head is drained by column groups 0 and 1 (256 threads, q = 64-column half) alone

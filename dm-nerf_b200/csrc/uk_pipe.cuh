@@ -82,6 +82,16 @@ static_assert(sizeof(Misc) <= 9216, "Misc does not fit its shared-memory block")
 #define KP_ADD(i) ((void)0)
 #endif
 
+// ------------------------------------------------------------------------------------------------ stall diagnostics
+// Diagnostics build only (-DDMN_DEBUG_STALL, tools/stall_debug.py): every thread keeps the id of the last "site" it passed in
+// shared memory; the first thread whose bounded wait expires snapshots all 640 of them for the host.
+#ifdef DMN_DEBUG_STALL
+static __device__ int g_stall_dbg[641];     // one copy per translation unit (the export in mlp_umma.cu reads its own)
+#define DBG_SITE(site_) (reinterpret_cast<volatile int*>(smem + SM_FUSED)[threadIdx.x] = (site_))
+#else
+#define DBG_SITE(site_) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ bounded waits
 // Slow path of a barrier wait (kept out of line so the hot path is one try_wait + branch).
 // On a timeout the abort flag is raised and execution simply continues: every later wait returns at once, the kernel
@@ -96,7 +106,15 @@ static __device__ __noinline__ void slow_wait(uint64_t* bar, uint32_t parity, Mi
     if (*(volatile int32_t*)&misc->abort_flag) return;
     if (clock64() - t0 > 4000000000LL) {           // ~2 s: protocol failure
       atomicExch(&misc->abort_flag, code);
+#ifdef DMN_DEBUG_STALL
+      if (atomicCAS(status, 0, code) == 0) {
+        const volatile int* sd = reinterpret_cast<const volatile int*>(reinterpret_cast<uint8_t*>(misc) - SM_MISC + SM_FUSED);
+        for (int i = 0; i < 640; ++i) g_stall_dbg[i] = sd[i];
+        g_stall_dbg[640] = (int)blockIdx.x * 100000 + code * 1000 + (int)threadIdx.x;
+      }
+#else
       atomicCAS(status, 0, code);
+#endif
       return;
     }
   }
@@ -250,6 +268,44 @@ __device__ __forceinline__ void store_row16_paired(float* __restrict__ dst, int6
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pb), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]),
                  "f"(b[5]), "f"(b[6]), "f"(b[7]) : "memory");
 }
+
+#ifdef DMN_QUAD_STORE      /* diagnostics only: the four-lane store variant that stalled intermittently (tools/stall_debug.py) */
+// Four neighbouring lanes (rows 4k..4k+3 of the tile) store their 32-column groups TOGETHER: a 4 x 4 transpose of 8-float
+// blocks in two shuffle rounds, after which lane q holds block q of all four rows and every 256-bit store instruction writes
+// whole 128-byte lines (8 per instruction instead of 32 scattered sectors).  `dst` = this lane's own row (column of v[0]);
+// row_base = index of the quad's first row; all 32 lanes must call it.
+__device__ __forceinline__ void store_row32_quad(float* __restrict__ dst, int64_t row_stride, const float* v, int64_t row_base,
+                                                 int64_t n_rows, int lane) {
+  __syncwarp();
+  const int q = lane & 3;
+  const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0;
+  // round 1 (xor 1): lanes with bit 0 clear keep blocks 0, 2 and receive the partner's blocks 0, 2; the others blocks 1, 3
+  float xe[2][8], xo[2][8];             // [lower / upper block][8 floats] of the pair's even row / odd row
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float r0 = __shfl_xor_sync(0xffffffffu, b0 ? v[i] : v[8 + i], 1);          // partner's lower block of MY parity
+    const float r1 = __shfl_xor_sync(0xffffffffu, b0 ? v[16 + i] : v[24 + i], 1);    // partner's upper block of MY parity
+    xe[0][i] = b0 ? r0 : v[i];        xe[1][i] = b0 ? r1 : v[16 + i];
+    xo[0][i] = b0 ? v[8 + i] : r0;    xo[1][i] = b0 ? v[24 + i] : r1;
+  }
+  // round 2 (xor 2): lanes with bit 1 clear keep the lower blocks and receive the other pair's lower blocks; the others upper
+  float t[4][8];                         // block q of rows row_base + 0..3
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float re = __shfl_xor_sync(0xffffffffu, b1 ? xe[0][i] : xe[1][i], 2);
+    const float ro = __shfl_xor_sync(0xffffffffu, b1 ? xo[0][i] : xo[1][i], 2);
+    t[0][i] = b1 ? re : xe[0][i];   t[1][i] = b1 ? ro : xo[0][i];       // rows of pair A (quad rows 0, 1)
+    t[2][i] = b1 ? xe[1][i] : re;   t[3][i] = b1 ? xo[1][i] : ro;       // rows of pair B (quad rows 2, 3)
+  }
+  float* base = dst - (int64_t)q * row_stride + 8 * q;      // quad row 0, this lane's 8-float block
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (row_base + i < n_rows)
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base + (int64_t)i * row_stride), "f"(t[i][0]),
+                   "f"(t[i][1]), "f"(t[i][2]), "f"(t[i][3]), "f"(t[i][4]), "f"(t[i][5]), "f"(t[i][6]), "f"(t[i][7]) : "memory");
+}
+
+#endif
 
 // 32 consecutive fp32 values of one row (128 B, 32-byte aligned) to global memory as four 256-bit stores: every store is a
 // whole 32-byte sector (a 128-bit store leaves half-sector partial writes for the L2 to merge, at twice the request count).
