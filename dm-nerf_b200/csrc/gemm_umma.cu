@@ -293,13 +293,13 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
   constexpr int UPT = ((SA + SB) * 256 + NT - 1) / NT;   // units per thread per stage; unit U = tid + i * NT
   constexpr int ACC_COLS = (NH * NB < 32) ? 32 : NH * NB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t done[TN_STAGES], acc_done;
+  __shared__ uint64_t done[TN_STAGES], filled[TN_STAGES], acc_done;
   __shared__ uint32_t tmem_base_s;
   __shared__ float csum_s[NA];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < TN_STAGES; ++i) mbar_init(&done[i], 1);
+    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(&done[i], 1); mbar_init(&filled[i], NT); }
     mbar_init(&acc_done, 1);
     fence_barrier_init();
   }
@@ -349,9 +349,13 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
       }
     }
     if (q + 2 < n_chunks) issue(r, q + 2);
+    // every thread announces its part of the stage on an mbarrier; only the issuing warp waits for the stage to be complete
+    // (a block-wide barrier here held all 16 loader warps back until the slowest had stored: ncu stall_barrier 12 %)
     fence_proxy_async_smem();
-    __syncthreads();
+    mbar_arrive(&filled[s]);
     if (warp == 0) {
+      if (!mbar_wait(&filled[s], (uint32_t)(q / TN_STAGES) & 1)) fail(status, 613);
+      __syncwarp();
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
