@@ -279,3 +279,31 @@ def test_point_query_matches_embedded_forward():
         ref2 = O.mlp_forward(O.to_torch(w), torch.cat([O.embed(pts, 10), O.embed(vd, 4)], -1)).numpy()
     assert got.shape == (1000, 18)
     assert scale_err(got, ref) <= 1e-4 and scale_err(got2, ref2) <= 1e-4, (scale_err(got, ref), scale_err(got2, ref2))
+
+
+def test_round2_entry_points_edge_cases():
+    """Empty / degenerate inputs of the round-2 entry points: ray selection of zero pixels, a batch with a single object,
+    the penalizer on zero rays, the matched loss with every channel matched."""
+    import types
+    from dmnerf_b200.helpers import get_rays_at
+    from dmnerf_b200.evaluator import ins_criterion
+    from dmnerf_b200.penalizer import ins_penalizer
+    wl = synth.workload("dmsr_study")
+    pose = torch.from_numpy(wl["c2w"]).to(DEV)
+    ro, rd = get_rays_at(480, 640, wl["K"], pose, torch.zeros(0, dtype=torch.int64))
+    assert ro.shape == (0, 3) and rd.shape == (0, 3)
+    ro, rd = get_rays_at(480, 640, wl["K"], pose, [0, 307199])
+    assert torch.equal(ro[0].cpu(), torch.from_numpy(wl["rays_o"][0])) and torch.equal(rd[1].cpu(), torch.from_numpy(wl["rays_d"][307199]))
+    gen = torch.Generator().manual_seed(1)
+    pred = torch.sigmoid(torch.randn(33, 5, generator=gen)).to(DEV).requires_grad_(True)
+    out = ins_criterion(pred, torch.full((33,), 3.0, device=DEV), 5)              # one object in the batch
+    out[0].sum().backward()
+    assert torch.isfinite(out[0]).all() and torch.isfinite(pred.grad).all() and float(out[2].sum()) > 0   # 4 unmatched channels
+    pred2 = torch.sigmoid(torch.randn(40, 4, generator=gen)).to(DEV)
+    lab = (torch.arange(40) % 4).float().to(DEV)
+    out2 = ins_criterion(pred2, lab, 4)                                            # every channel matched
+    assert out2[2].shape == (1,) and int(out2[2]) == 0 and out2[0].shape == (1,)
+    args = types.SimpleNamespace(tolerance=0.05, deta_w=0.05)
+    loss = ins_penalizer(torch.zeros(0, 64, 18, device=DEV), torch.zeros(0, 64, device=DEV), torch.zeros(0, device=DEV),
+                         torch.zeros(0, 3, device=DEV), args)
+    assert loss.shape == (1,) and float(loss) == 0.0
