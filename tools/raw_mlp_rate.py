@@ -10,7 +10,7 @@ pts = (torch.rand(n, 3, device=dev) * 6 - 3)
 with torch.no_grad():
     for _ in range(3): out = mlp_forward_points(nf, pts)
     torch.cuda.synchronize()
-    for reps in (5, 150):
+    for reps in (5, 150, 600):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps): out = mlp_forward_points(nf, pts)
