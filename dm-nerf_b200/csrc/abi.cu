@@ -198,9 +198,32 @@ DMNERF_API int dmnerf_ins_loss_backward(const float* pred, const int32_t* gt_row
   DMN_CHECK(n >= 0, "ins_loss_backward: negative ray count");
   DMN_CHECK(n == 0 || (pred && gt_row && row_of_col && tp && col_sum && row_count && g_losses && d_pred),
             "ins_loss_backward: NULL buffer");
-  return launch_ins_loss_grad(pred, gt_row, n, ins_num, row_of_col, n_valid, tp, col_sum, row_count, g_losses, d_pred,
+  return launch_ins_loss_grad(pred, gt_row, n, ins_num, row_of_col, n_valid, nullptr, tp, col_sum, row_count, g_losses, d_pred,
                               (cudaStream_t)stream);
 }
+
+DMNERF_API int dmnerf_ins_label_rows(const int32_t* labels, int64_t n, int ins_num, int32_t* gt_row, int32_t* n_valid, void* stream) {
+  DMN_CHECK(labels && gt_row && n_valid, "ins_label_rows: NULL buffer");
+  return launch_label_rows(labels, n, ins_num, gt_row, n_valid, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_hungarian_assign(const float* cost_ce, const float* cost_siou, const float* col_sum, const int32_t* n_valid,
+                                       int64_t n, int ins_num, int32_t* row_of_col, float* losses, void* stream) {
+  DMN_CHECK(cost_ce && cost_siou && col_sum && n_valid && row_of_col && losses, "hungarian_assign: NULL buffer");
+  return launch_hungarian_assign(cost_ce, cost_siou, col_sum, n_valid, n, ins_num, row_of_col, losses, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_ins_loss_backward_dev(const float* pred, const int32_t* gt_row, int64_t n, int ins_num,
+                                            const int32_t* row_of_col, const int32_t* n_valid, const float* tp, const float* col_sum,
+                                            const float* row_count, const float* g_losses, float* d_pred, void* stream) {
+  DMN_CHECK(n >= 0, "ins_loss_backward_dev: negative ray count");
+  DMN_CHECK(n == 0 || (pred && gt_row && row_of_col && n_valid && tp && col_sum && row_count && g_losses && d_pred),
+            "ins_loss_backward_dev: NULL buffer");
+  return launch_ins_loss_grad(pred, gt_row, n, ins_num, row_of_col, 0, n_valid, tp, col_sum, row_count, g_losses, d_pred,
+                              (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_ins_status_take(void) { return ins_status_take(); }
 
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,
                                void* stream) {

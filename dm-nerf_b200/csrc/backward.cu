@@ -594,24 +594,64 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   DMN_CUDA(cudaMemsetAsync(PQ, 0, (256 * 256 + 256 + 256) * sizeof(float), st));
   int rc = 0;
 #define R(x) do { if ((rc = (x))) return rc; } while (0)
+  // Every weight-gradient product of the network contracts over the same m samples and all their operands exist once the
+  // gradient chain has run: they are queued by shape class and each class goes out as ONE batched tensor-core launch
+  // (launch_gemm_tn_tc_batch) -- 3 GEMM + 3 reduction launches per network instead of 14 + 14.
+  struct Queue { TnProblem p[TN_MAX_BATCH]; int n = 0, N = 0; } q_wide, q_in256, q_in128;      // [256 x 256], [256 x <=64], [128 x <=64]
+  const bool batched = bwd_use_tc() && m >= 512;
+  auto flush = [&](Queue& q) -> int {
+    const int r = q.n ? launch_gemm_tn_tc_batch(q.p, q.n, m, q.N, st) : 0;
+    q.n = 0;
+    return r;
+  };
+  auto dW = [&](const float* A, int lda, const float* B, int ldb, float* Cw, int ldc, int N, int K, float* colsum_out = nullptr,
+                int64_t b_cm = 0) -> int {
+    TnProblem pr;
+    Queue* q = nullptr;
+    if (batched && gemm_tn_tc_supported(N, K)) {
+      pr.A = A; pr.lda = lda; pr.B = B; pr.ldb = ldb; pr.K = K; pr.transpose = 0; pr.colsum = colsum_out; pr.b_cm = b_cm;
+      q = (K > 64) ? &q_wide : (N == 256 ? &q_in256 : &q_in128);
+      if (K > 64 && N != 256) q = nullptr;                                      // [128 x 256]: not a shape of this network
+      pr.ldc = ldc; pr.C = Cw;
+      if (q) q->N = N;
+    } else if (batched && !colsum_out && !b_cm && K > 64 && gemm_tn_tc_supported(K, N)) {      // narrow dY, wide X: (X^T dY)^T
+      pr.A = B; pr.lda = ldb; pr.B = A; pr.ldb = lda; pr.K = N; pr.transpose = 1; pr.colsum = nullptr; pr.b_cm = 0;
+      pr.ldc = ldc; pr.C = Cw;
+      q = (K == 256) ? &q_in256 : &q_in128;
+      q->N = K;
+    }
+    if (!q) return gemm_tn(A, lda, B, ldb, Cw, ldc, m, N, K, st, colsum_out, b_cm);
+    if (q->n == TN_MAX_BATCH) { const int r = flush(*q); if (r) return r; }
+    q->p[q->n++] = pr;
+    return 0;
+  };
   if (!feats_missing) R(launch_mask_bits(acts, m, st));          // exact-fp32 forward: masks from its planes
   const float* d_rgb = d_out;
   const float* d_sig = d_out + 3;
   const float* d_ins = d_out + 4;
   R(launch_bwd_heads(p, d_out, m, ap.bits, S12, st));
   R(launch_bwd_chain(packed, p, S12, d_out, ap.bits, m, dY, st));
-  // ---- output layers (dm_nerf.py:101-103): weight gradients, and the three bias gradients from one sweep over d_out
-  R(gemm_tn(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, m, 3, 128, st));
-  R(gemm_tn(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, m, ins1, 128, st));
-  R(gemm_tn(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, m, 1, 256, st));
+  // ---- folded head layers (dm_nerf.py:89-99): one product against h7 for both branches; trunk (dm_nerf.py:83-87)
+  R(dW(S12, 256, ap.h[7], 256, PQ, 256, 256, 256, c12));
+  for (int l = 7; l >= 1; --l) R(dW(dY[l], 256, ap.h[l - 1], 256, gw(l), layer_in(l), 256, 256, gb(l)));
+  R(flush(q_wide));
+  // ---- input columns: layer 0 and the skip input [h, pts] of layer 5 (embedded position, column-major plane), density weights
+  R(dW(dY[0], 256, ap.emb, CH_IN, gw(0), layer_in(0), 256, CH_POS, gb(0), m));
+  R(dW(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, layer_in(5), 256, CH_POS, nullptr, m));
+  R(dW(d_sig, C, ap.h[7], 256, gw(L_DENSITY), 256, 1, 256));
+  R(flush(q_in256));
+  // ---- output layers (dm_nerf.py:101-103) and the view-direction columns of the colour hidden layer
+  R(dW(d_rgb, C, ap.rgb_hid, 128, gw(L_RGB_OUT), 128, 3, 128));
+  R(dW(d_ins, C, ap.ins_hid, 128, gw(L_INS_OUT), 128, ins1, 128));
+  R(dW(S12, 256, ap.emb + (int64_t)CH_POS * m, CH_IN, gw(L_RGB_HID) + 256, 283, 128, CH_DIR, nullptr, m));
+  R(flush(q_in128));
+  // the three output bias gradients from one sweep over d_out
   colsum_flat_kernel<<<148 * 4, 256, 0, st>>>(d_out, C, m * C, cs);
   DMN_LAUNCH_OK();
   DMN_CUDA(cudaMemcpyAsync(gb(L_RGB_OUT), cs, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   DMN_CUDA(cudaMemcpyAsync(gb(L_DENSITY), cs + 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
   DMN_CUDA(cudaMemcpyAsync(gb(L_INS_OUT), cs + 4, ins1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // ---- folded head layers (dm_nerf.py:89-99): one GEMM against h7 for both branches
-  R(gemm_tn(S12, 256, ap.h[7], 256, PQ, 256, m, 256, 256, st, c12));
-  R(gemm_tn(S12, 256, ap.emb + (int64_t)CH_POS * m, CH_IN, gw(L_RGB_HID) + 256, 283, m, 128, CH_DIR, st, nullptr, m));   // view-direction columns
+  // ---- folded head layers, small products on P / Q
   R(small_nt(P, 256, p.w[L_RGB_FEAT], 256, c1, p.b[L_RGB_FEAT], gw(L_RGB_HID), 283, 128, 256, 256, st));
   R(small_nt(Q, 256, p.w[L_INS_FEAT], 256, c2, p.b[L_INS_FEAT], gw(L_INS_HID), 256, 128, 256, 256, st));
   DMN_CUDA(cudaMemcpyAsync(gb(L_RGB_HID), c1, 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -620,16 +660,6 @@ static int mlp_backward_chain(const NetParams& p, const UmmaWeights& packed, flo
   R(small_tn(p.w[L_RGB_HID], 283, c1, 1, gb(L_RGB_FEAT), 1, 128, 256, 1, st));
   R(small_tn(p.w[L_INS_HID], 256, Q, 256, gw(L_INS_FEAT), 256, 128, 256, 256, st));
   R(small_tn(p.w[L_INS_HID], 256, c2, 1, gb(L_INS_FEAT), 1, 128, 256, 1, st));
-  // ---- trunk (dm_nerf.py:83-87)
-  for (int l = 7; l >= 0; --l) {
-    const int kin = layer_in(l);
-    if (l == 0) {
-      R(gemm_tn(dY[0], 256, ap.emb, CH_IN, gw(0), kin, m, 256, CH_POS, st, gb(0), m));
-    } else {
-      R(gemm_tn(dY[l], 256, ap.h[l - 1], 256, gw(l), kin, m, 256, 256, st, gb(l)));
-      if (l == 5) R(gemm_tn(dY[5], 256, ap.emb, CH_IN, gw(5) + 256, kin, m, 256, CH_POS, st, nullptr, m));    // skip input [h, pts]
-    }
-  }
 #undef R
   return 0;
 }

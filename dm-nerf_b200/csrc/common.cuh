@@ -151,6 +151,15 @@ bool gemm_nn_tc_supported(int N, int K, int ldc, const float* C, const float* ma
 bool gemm_tn_tc_supported(int N, int K);
 int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int64_t M, int N, int accumulate,
                       const float* mask, const float* bias, int w_kmajor, cudaStream_t st);
+// One product of a batched dW launch (gemm_umma.cu): C[N, K] += A[M, N]^T B[M, K]; b_cm != 0: B is column-major with that column
+// stride; transpose: A is the wide operand and the result goes to C[K, N].
+constexpr int TN_MAX_BATCH = 8;
+struct TnProblem {
+  const float* A; const float* B; float* C; float* colsum;
+  int64_t b_cm;
+  int lda, ldb, ldc, K, transpose;
+};
+int launch_gemm_tn_tc_batch(const TnProblem* probs, int n, int64_t M, int N, cudaStream_t st);
 int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
                       int transpose, cudaStream_t st, int64_t b_cm = 0);
 int gemm_tc_check_status(cudaStream_t st);
@@ -167,6 +176,11 @@ size_t penalizer_state_bytes();
 int launch_hungarian_costs(const float* pred, const int32_t* gt_row, int64_t n, int k, float* cost_ce, float* cost_siou,
                            float* tp, float* s_sum, float* cnt, cudaStream_t st);
 int launch_ins_loss_grad(const float* pred, const int32_t* gt_row, int64_t n, int k, const int32_t* row_of_col, int n_valid,
-                         const float* tp, const float* s_sum, const float* cnt, const float* g3, float* d_pred, cudaStream_t st);
+                         const int32_t* n_valid_dev, const float* tp, const float* s_sum, const float* cnt, const float* g3,
+                         float* d_pred, cudaStream_t st);
+int launch_label_rows(const int32_t* labels, int64_t n, int k, int32_t* gt_row, int32_t* n_valid, cudaStream_t st);
+int launch_hungarian_assign(const float* cost_ce, const float* cost_siou, const float* s_sum, const int32_t* n_valid, int64_t n, int k,
+                            int32_t* row_of_col, float* loss3, cudaStream_t st);
+int ins_status_take();
 
 }  // namespace dmnerf

@@ -283,10 +283,28 @@ __global__ void __launch_bounds__(NN_THREADS, 1) gemm_nn_tc_kernel(const float* 
 constexpr uint32_t TN_SLAB = 32 * 128;                   // one [32 x 64] slab
 constexpr int TN_STAGES = 3;
 
+// A launch multiplies up to TN_MAX_BATCH independent products over the same M samples (the weight gradients of several layers of
+// one network: their operands are all on hand once the gradient chain has run): CTA b works on product b / slices, sample
+// slice b % slices.  With 8 products a CTA's slice is 8x longer than with one product per launch (fewer, longer pipelines:
+// the fill / drain and the 256 KB accumulator write are paid once per 8x the samples) and 8x fewer partial slices are written
+// and re-read by the reduction.
+struct TnBatch {
+  TnProblem p[TN_MAX_BATCH];
+  int vec_a[TN_MAX_BATCH], vec_b[TN_MAX_BATCH];
+  int n, slices;
+  int64_t rows_per_cta;
+};
+
 template <int NA, int NB>
-__global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                           int nb, float* __restrict__ partial, float* __restrict__ colsum, int64_t M,
-                                                           int64_t rows_per_cta, int vec_a, int vec_b, int64_t b_cm, int32_t* status) {
+__global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const __grid_constant__ TnBatch batch, float* __restrict__ partial,
+                                                           int64_t M, int32_t* status) {
+  const int prob = (int)blockIdx.x / batch.slices, slice = (int)blockIdx.x - prob * batch.slices;
+  const float* __restrict__ A = batch.p[prob].A;
+  const float* __restrict__ B = batch.p[prob].B;
+  float* __restrict__ colsum = batch.p[prob].colsum;
+  const int lda = batch.p[prob].lda, ldb = batch.p[prob].ldb, nb = batch.p[prob].K;
+  const int vec_a = batch.vec_a[prob], vec_b = batch.vec_b[prob];
+  const int64_t b_cm = batch.p[prob].b_cm, rows_per_cta = batch.rows_per_cta;
   constexpr int SA = NA / 64, SB = NB / 64;              // slabs per operand
   constexpr uint32_t STAGE = 2 * (SA + SB) * TN_SLAB;   // hi + lo
   constexpr int NH = NA / 128;                           // accumulators of 128 gradient rows
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
   tc_fence_after();
   const uint32_t tD = tmem_base_s;
   const uint32_t idesc = make_idesc_bf16(128, NB) | A_MN | B_MN;
-  const int64_t mb = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t mb = (int64_t)slice * rows_per_cta;
   const int64_t me = (mb + rows_per_cta < M) ? mb + rows_per_cta : M;
   const int64_t n_chunks = (me > mb) ? (me - mb + 31) / 32 : 0;
   float csum[UPT][8];
@@ -431,17 +449,21 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const float* __restri
   if (warp == 0) tmem_dealloc(tD, ACC_COLS);
 }
 
-// C[n, k] += sum_cta partial[cta][n][k]  (k < kb valid columns of the NB-wide partials);  transpose: C[k, n] instead
-// (the product was computed with the roles of the two operands exchanged).  64 float4 columns x 4 slice groups per block: every
-// thread keeps several independent 16-byte loads in flight (the slices were just written: they come from L2).
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int NA, int NB, int kb,
-                                                              float* __restrict__ C, int ldc, int transpose) {
+// C[n, k] += sum_slice partial[slice][n][k]  (k < K valid columns of the NB-wide partials) for product blockIdx.y of the batch;
+// transpose: C[k, n] instead (the product was computed with the roles of the two operands exchanged).  64 float4 columns x 4
+// slice groups per block: every thread keeps several independent 16-byte loads in flight (the slices were just written: they
+// come from L2).  The slices of a product are added in a fixed order: the gradient is reproducible from run to run.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, const __grid_constant__ TnBatch batch,
+                                                              int NA, int NB) {
   __shared__ float4 red[4][64];
+  const TnProblem& pr = batch.p[blockIdx.y];
+  const int n_cta = batch.slices, kb = pr.K, ldc = pr.ldc, transpose = pr.transpose;
+  float* __restrict__ C = pr.C;
   const int q = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int idx4 = blockIdx.x * 64 + q, total4 = NA * NB / 4;
   float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
   if (idx4 < total4) {
-    const float4* src = reinterpret_cast<const float4*>(partial) + idx4;
+    const float4* src = reinterpret_cast<const float4*>(partial) + (size_t)blockIdx.y * n_cta * total4 + idx4;
     const size_t stride = (size_t)total4;
     int c = grp;
     for (; c + 4 < n_cta; c += 8) {
@@ -535,20 +557,34 @@ int launch_gemm_nn_tc(const float* A, int lda, const float* W, int ldw, float* C
   return 0;
 }
 
-// C[N, K] += A[M, N]^T B[M, K]  (N = 128 or 256 and K = 256, or K <= 64);  transpose != 0: the caller passes the WIDE matrix as A
-// and the narrow one (K <= 64 columns) as B and wants C[K, N] += B^T A.
-int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
-                      int transpose, cudaStream_t st, int64_t b_cm) {
+// For every product i < n:  C_i[N, K_i] += A_i[M, N]^T B_i[M, K_i]  (N = 128 or 256; every K_i = 256, or every K_i <= 64);
+// transpose != 0: the caller passes the WIDE matrix as A and the narrow one (K <= 64 columns) as B and wants C[K, N] += B^T A.
+// One GEMM launch + one reduction launch for the whole batch.
+int launch_gemm_tn_tc_batch(const TnProblem* probs, int n, int64_t M, int N, cudaStream_t st) {
   using namespace tg;
-  if (M <= 0) return 0;
+  if (M <= 0 || n <= 0) return 0;
   DevState* ds = nullptr;
   if (dev_state(&ds)) return 1;
   int32_t* g_status = ds->status;
-  const int NB = (K > 64) ? 256 : 64;
-  DMN_CHECK((N == 128 || N == 256) && K >= 1 && K <= 256 && (NB == 64 || K == 256), "gemm_tn(tc): shape %d x %d not supported", N, K);
-  int64_t rows = (M + ds->sms - 1) / ds->sms;
+  DMN_CHECK(n <= TN_MAX_BATCH, "gemm_tn(tc): %d products in one batch (max %d)", n, TN_MAX_BATCH);
+  const int NB = (probs[0].K > 64) ? 256 : 64;
+  TnBatch batch;
+  memset(&batch, 0, sizeof(batch));
+  for (int i = 0; i < n; ++i) {
+    const int K = probs[i].K;
+    DMN_CHECK((N == 128 || N == 256) && K >= 1 && K <= 256 && ((K > 64) ? 256 : 64) == NB && (NB == 64 || K == 256),
+              "gemm_tn(tc): shape %d x %d not supported", N, K);
+    batch.p[i] = probs[i];
+    batch.vec_a[i] = vec4_ok(probs[i].A, probs[i].lda);
+    batch.vec_b[i] = vec4_ok(probs[i].B, probs[i].ldb);
+  }
+  int slices = ds->sms / n;
+  if (slices < 1) slices = 1;
+  int64_t rows = (M + slices - 1) / slices;
   rows = ((rows + 31) / 32) * 32;
-  const unsigned grid = (unsigned)((M + rows - 1) / rows);
+  slices = (int)((M + rows - 1) / rows);
+  batch.n = n; batch.slices = slices; batch.rows_per_cta = rows;
+  const unsigned grid = (unsigned)(n * slices);
   if (!ds->partial || ds->partial_ctas < grid) {      // up to one [256 x 256] fp32 slice per CTA
     if (ds->partial) DMN_CUDA(cudaFree(ds->partial));
     ds->partial = nullptr;
@@ -564,15 +600,23 @@ int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(128, 64)));
     DMN_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(256, 64)));
   }
-  const int va = vec4_ok(A, lda), vb = vec4_ok(B, ldb);
-  if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
-  else if (N == 256 && NB == 256) gemm_tn_tc_kernel<256, 256><<<grid, NT, smem_of(256, 256), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
-  else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
-  else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(A, lda, B, ldb, K, scratch, colsum, M, rows, va, vb, b_cm, g_status);
+  if (N == 128 && NB == 256) gemm_tn_tc_kernel<128, 256><<<grid, NT, smem_of(128, 256), st>>>(batch, scratch, M, g_status);
+  else if (N == 256 && NB == 256) gemm_tn_tc_kernel<256, 256><<<grid, NT, smem_of(256, 256), st>>>(batch, scratch, M, g_status);
+  else if (N == 128) gemm_tn_tc_kernel<128, 64><<<grid, NT, smem_of(128, 64), st>>>(batch, scratch, M, g_status);
+  else gemm_tn_tc_kernel<256, 64><<<grid, NT, smem_of(256, 64), st>>>(batch, scratch, M, g_status);
   DMN_LAUNCH_OK();
-  reduce_partials_kernel<<<(N * NB / 4 + 63) / 64, 256, 0, st>>>(scratch, (int)grid, N, NB, K, C, ldc, transpose);
+  reduce_partials_kernel<<<dim3((N * NB / 4 + 63) / 64, n), 256, 0, st>>>(scratch, batch, N, NB);
   DMN_LAUNCH_OK();
   return 0;
+}
+
+// The single product C[N, K] += A[M, N]^T B[M, K] (a batch of one: every SM takes a slice of the samples).
+int launch_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* colsum, int64_t M, int N, int K,
+                      int transpose, cudaStream_t st, int64_t b_cm) {
+  TnProblem pr;
+  pr.A = A; pr.lda = lda; pr.B = B; pr.ldb = ldb; pr.C = C; pr.ldc = ldc; pr.colsum = colsum; pr.K = K; pr.transpose = transpose;
+  pr.b_cm = b_cm;
+  return launch_gemm_tn_tc_batch(&pr, 1, M, N, st);
 }
 
 // Asynchronous failure word of the GEMM kernels (0 = fine); checked by dmnerf_sync_check.

@@ -5,10 +5,13 @@
     img2mse, mse2psnr, to8b                                                                             evaluator.py:11,14,15
 
 The two [ins x ins] cost matrices come out of ONE pass over the rays (csrc/evaluator.cu: gt is one-hot, so the reference's
-[ins x ins x N] broadcast collapses to per-row sums); the assignment is scipy's linear_sum_assignment on the host, exactly as
-in the reference (its only device->host hop: the [valid x ins] score matrix); the matched loss and its gradient w.r.t. the
-rendered instance map are evaluated on the device (autograd Function -> dmnerf_ins_loss_backward).
+[ins x ins x N] broadcast collapses to per-row sums).  ins_criterion then runs the assignment ON THE DEVICE (scipy's
+shortest-augmenting-path algorithm restated for one warp, same fp64 duals and tie rule: the training iteration has no
+device->host hop left; DMNERF_INS_ASSIGN=host selects scipy on the host, the reference's own arrangement, with one hop per
+call).  hungarian() returns the reference's numpy orders and therefore always uses scipy.  The matched loss and its gradient
+w.r.t. the rendered instance map are evaluated on the device (dmnerf_hungarian_assign / dmnerf_ins_loss_backward[_dev]).
 """
+import os
 import numpy as np
 import torch
 
@@ -122,6 +125,58 @@ class _LabelsOutOfRange(Exception):
     pass
 
 
+class _MatchedLossDevice(torch.autograd.Function):
+    """forward(pred_ins [N,K], labels [N] int32): ranks of the labels, cost matrices, assignment and the three loss terms in four
+    launches, nothing read back.  Labels outside [0, 65536) or more distinct labels than K: NaN losses, zero gradient, and the
+    next ins_criterion call raises (error word in mapped host memory)."""
+
+    @staticmethod
+    def forward(fctx, pred_ins, labels):
+        pred = pred_ins.detach().contiguous().float()
+        n, k = pred.shape
+        dev = pred.device
+        ctx = get_context(dev)
+        gt_row = torch.empty(n, device=dev, dtype=torch.int32)
+        n_valid = torch.empty(1, device=dev, dtype=torch.int32)
+        _lib.check(ctx.lib.dmnerf_ins_label_rows(labels.data_ptr(), n, k, gt_row.data_ptr(), n_valid.data_ptr(), ctx.stream()),
+                   "dmnerf_ins_label_rows")
+        c = _costs(pred, gt_row)
+        row_of_col = torch.empty(k, device=dev, dtype=torch.int32)
+        losses = torch.empty(3, device=dev, dtype=torch.float32)
+        _lib.check(ctx.lib.dmnerf_hungarian_assign(_lib.ptr(c["cost_ce"]), _lib.ptr(c["cost_siou"]), _lib.ptr(c["col_sum"]),
+                                                   n_valid.data_ptr(), n, k, row_of_col.data_ptr(), _lib.ptr(losses), ctx.stream()),
+                   "dmnerf_hungarian_assign")
+        fctx.save_for_backward(pred, gt_row, row_of_col, n_valid, c["tp"], c["col_sum"], c["row_count"])
+        fctx.in_shape = pred_ins.shape
+        fctx.mark_non_differentiable(n_valid, row_of_col)
+        valid_ce, invalid_ce, valid_siou = losses[0].clone(), losses[1].clone(), losses[2].clone()
+        return valid_ce, invalid_ce, valid_siou, n_valid, row_of_col
+
+    @staticmethod
+    def backward(fctx, g_ce, g_inv, g_siou, _g_n=None, _g_r=None):
+        pred, gt_row, row_of_col, n_valid, tp, col_sum, row_count = fctx.saved_tensors
+        n, k = pred.shape
+        zero = pred.new_zeros(())
+        g3 = torch.stack([(g if g is not None else zero).reshape(()).float() for g in (g_ce, g_inv, g_siou)]).contiguous()
+        d_pred = torch.empty_like(pred)
+        ctx = get_context(pred.device)
+        _lib.check(ctx.lib.dmnerf_ins_loss_backward_dev(_lib.ptr(pred), gt_row.data_ptr(), n, k, row_of_col.data_ptr(),
+                                                        n_valid.data_ptr(), _lib.ptr(tp), _lib.ptr(col_sum), _lib.ptr(row_count),
+                                                        _lib.ptr(g3), _lib.ptr(d_pred), ctx.stream()), "dmnerf_ins_loss_backward_dev")
+        return d_pred.reshape(fctx.in_shape), None
+
+
+_STATUS_TEXT = {701: "a label outside [0, 65536)", 702: "more distinct labels than ins_num (or an empty batch)"}
+
+
+def ins_assignment(pred_ins, gt_labels, ins_num):
+    """Device-side matching only: (row_of_col [ins_num] int32: rank of the matched label per prediction channel or -1,
+    n_valid [1] int32), both on the device.  Same kernels as ins_criterion; for tests and diagnostics."""
+    labels = gt_labels.to(pred_ins.device).reshape(-1).to(torch.int32).contiguous()
+    out = _MatchedLossDevice.apply(pred_ins, labels)
+    return out[4], out[3]
+
+
 def ins_criterion(pred_ins, gt_labels, ins_num):
     """evaluator.py:19-37.  pred_ins [N, ins_num] (rendered instance probabilities, CUDA), gt_labels [N] (object ids)."""
     if not pred_ins.is_cuda:
@@ -130,6 +185,16 @@ def ins_criterion(pred_ins, gt_labels, ins_num):
         raise RuntimeError("ins_criterion: pred_ins %s / gt_labels %s / ins_num %d are inconsistent"
                            % (tuple(pred_ins.shape), tuple(gt_labels.shape), ins_num))
     labels = gt_labels.to(pred_ins.device).reshape(-1)
+    if os.environ.get("DMNERF_INS_ASSIGN", "device") != "host":
+        code = get_context(pred_ins.device).lib.dmnerf_ins_status_take()
+        if code:
+            raise RuntimeError("ins_criterion: an earlier call was given %s (code %d); its loss was NaN and its gradient zero. "
+                               "DMNERF_INS_ASSIGN=host handles arbitrary integer labels (one synchronisation per call)."
+                               % (_STATUS_TEXT.get(code, "labels it cannot rank"), code))
+        valid_ce, invalid_ce, valid_siou, _, _ = _MatchedLossDevice.apply(pred_ins, labels.to(torch.int32).contiguous())
+        # evaluator.py:33 returns tensor([0]) (shape [1]) when every channel is matched; here invalid_ce is a 0-dim zero in that
+        # case (the number of distinct labels is not known on the host)
+        return valid_ce + invalid_ce + valid_siou, valid_ce, invalid_ce, valid_siou             # evaluator.py:36
     try:
         # object ids in [0, ins_num) (every dataset of the reference): the id IS the cost-matrix row; which ids occur comes back
         # with the matrices, so the call makes a single device->host hop (no torch.unique synchronisation)

@@ -133,6 +133,24 @@ DMNERF_API int dmnerf_ins_loss_backward(const float* pred, const int32_t* gt_row
                                         const int32_t* row_of_col, int n_valid, const float* tp, const float* col_sum,
                                         const float* row_count, const float* g_losses, float* d_pred, void* stream);
 
+/* The same loss with the assignment ON THE DEVICE: no device->host hop in the training iteration (the reference's
+ * valid_scores.cpu() + scipy call, evaluator.py:43-45, is its last synchronisation point).
+ * dmnerf_ins_label_rows: labels [N] (int32 object ids in [0, 65536)) -> gt_row [N] = rank of the ray's label among the distinct
+ *   labels of the batch (torch.unique order, evaluator.py:21-25) and n_valid[0] = their number (DEVICE int32; -1 when a label is
+ *   out of range or there are more distinct labels than ins_num).
+ * dmnerf_hungarian_assign: scipy.optimize.linear_sum_assignment's algorithm (shortest augmenting paths, fp64 duals, scipy's tie
+ *   rule) on rows 0..n_valid-1 of cost_ce + cost_siou -> row_of_col [ins_num] (matched row or -1) and
+ *   losses[3] = { valid_ce, invalid_ce, valid_siou } (evaluator.py:27-36; NaN after rejected labels).
+ * dmnerf_ins_loss_backward_dev: dmnerf_ins_loss_backward with n_valid read from the device (zero gradient after rejected labels).
+ * dmnerf_ins_status_take: returns and clears the error word of rejected labels (0 = none; mapped host memory, no synchronisation). */
+DMNERF_API int dmnerf_ins_label_rows(const int32_t* labels, int64_t n, int ins_num, int32_t* gt_row, int32_t* n_valid, void* stream);
+DMNERF_API int dmnerf_hungarian_assign(const float* cost_ce, const float* cost_siou, const float* col_sum, const int32_t* n_valid,
+                                       int64_t n, int ins_num, int32_t* row_of_col, float* losses, void* stream);
+DMNERF_API int dmnerf_ins_loss_backward_dev(const float* pred, const int32_t* gt_row, int64_t n, int ins_num,
+                                            const int32_t* row_of_col, const int32_t* n_valid, const float* tp, const float* col_sum,
+                                            const float* row_count, const float* g_losses, float* d_pred, void* stream);
+DMNERF_API int dmnerf_ins_status_take(void);
+
 /* Coarse depths, networks/render.py:40-47: z_out[n, i] = z_in row (shared when z_row_stride = 0), jittered inside its
  * stratum by t_rand [N,S] when given. */
 DMNERF_API int dmnerf_stratify(const float* z_in, int64_t z_row_stride, const float* t_rand, int64_t n, int s, float* z_out,

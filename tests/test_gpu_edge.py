@@ -302,7 +302,15 @@ def test_round2_entry_points_edge_cases():
     pred2 = torch.sigmoid(torch.randn(40, 4, generator=gen)).to(DEV)
     lab = (torch.arange(40) % 4).float().to(DEV)
     out2 = ins_criterion(pred2, lab, 4)                                            # every channel matched
-    assert out2[2].shape == (1,) and int(out2[2]) == 0 and out2[0].shape == (1,)
+    # assignment on the device: the number of distinct labels never reaches the host, invalid_ce is a 0-dim zero
+    assert out2[2].shape == () and float(out2[2]) == 0.0 and torch.isfinite(out2[0]).all()
+    os.environ["DMNERF_INS_ASSIGN"] = "host"
+    try:
+        out3 = ins_criterion(pred2, lab, 4)                                        # evaluator.py:33: tensor([0]), shape [1]
+    finally:
+        del os.environ["DMNERF_INS_ASSIGN"]
+    assert out3[2].shape == (1,) and int(out3[2]) == 0 and out3[0].shape == (1,)
+    assert abs(float(out3[0]) - float(out2[0])) <= 1e-6 * abs(float(out3[0]))
     args = types.SimpleNamespace(tolerance=0.05, deta_w=0.05)
     loss = ins_penalizer(torch.zeros(0, 64, 18, device=DEV), torch.zeros(0, 64, device=DEV), torch.zeros(0, device=DEV),
                          torch.zeros(0, 3, device=DEV), args)

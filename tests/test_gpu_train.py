@@ -298,6 +298,114 @@ def test_hungarian_instance_loss_matches_reference(golden_dir, tag):
     assert sorted(cols) == list(range(k))
 
 
+def _device_assign(cost, n_valid):
+    """hungarian_assign_kernel on an arbitrary score matrix (as cost_ce, with cost_siou = 0) through the C ABI."""
+    from dmnerf_b200.engine import get_context
+    k = cost.shape[0]
+    ctx = get_context(torch.device(DEV))
+    ce = cu(cost.astype(np.float32))
+    si = torch.zeros_like(ce)
+    col_sum = torch.ones(k, device=DEV)
+    nv = torch.tensor([n_valid], device=DEV, dtype=torch.int32)
+    row_of_col = torch.full((k,), -7, device=DEV, dtype=torch.int32)
+    losses = torch.empty(3, device=DEV)
+    _lib.check(ctx.lib.dmnerf_hungarian_assign(_lib.ptr(ce), _lib.ptr(si), _lib.ptr(col_sum), nv.data_ptr(), 10, k,
+                                               row_of_col.data_ptr(), _lib.ptr(losses), ctx.stream()), "dmnerf_hungarian_assign")
+    return row_of_col.cpu().numpy(), losses.cpu().numpy()
+
+
+def test_device_assignment_is_scipys_assignment_including_ties():
+    """The one-warp shortest-augmenting-path solver against scipy.optimize.linear_sum_assignment (evaluator.py:45) on random,
+    small-integer (tie-heavy), constant and duplicate-column score matrices of every shape class: the SAME columns, not just the
+    same total, because the matched channel decides where the gradient goes."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(3)
+    cases = 0
+    for trial in range(160):
+        k = int(rng.integers(1, 129)) if trial % 5 else int(rng.choice([1, 2, 32, 33, 94, 127, 128]))
+        v = int(rng.integers(1, k + 1)) if trial % 3 else k
+        kind = trial % 4
+        if kind == 0:
+            c = rng.random((k, k))
+        elif kind == 1:
+            c = rng.integers(0, 3, (k, k)).astype(np.float64)
+        elif kind == 2:
+            c = np.full((k, k), float(rng.integers(0, 2)))
+        else:
+            c = rng.random((k, k))
+            c[:, rng.integers(0, k, max(1, k // 2))] = c[:, [0]]
+        c = c.astype(np.float32)
+        rows, cols = linear_sum_assignment(c[:v])
+        got, losses = _device_assign(c, v)
+        want = np.full(k, -1)
+        want[cols] = rows
+        assert np.array_equal(got, want), (trial, k, v, kind)
+        np.testing.assert_allclose(losses[0], c[rows, cols].mean(), rtol=1e-6, atol=1e-7)
+        assert losses[2] == 0.0
+        np.testing.assert_allclose(losses[1], (k - v) / (10.0 * (k - v)) if k > v else 0.0, rtol=1e-6)
+        cases += 1
+    assert cases == 160
+    # non-finite scores: no assignment, NaN losses (scipy raises "matrix contains invalid numeric entries")
+    bad = np.ones((4, 4), np.float32); bad[1, :] = np.nan
+    got, losses = _device_assign(bad, 4)
+    assert (got == -1).all() and np.isnan(losses).all()
+
+
+def test_instance_loss_device_and_host_assignment_agree_and_nothing_synchronises(monkeypatch):
+    """ins_criterion with the assignment on the device (default) against DMNERF_INS_ASSIGN=host (scipy, the reference's
+    arrangement): same loss parts, same gradient; labels need not be dense or below ins_num; and the device path raises under
+    torch's synchronisation detector neither in forward nor in backward (the host path does: its .cpu() hop)."""
+    from dmnerf_b200.evaluator import ins_criterion, ins_assignment
+    gen = torch.Generator().manual_seed(21)
+    for n, k, label_values in ((1024, 13, [0, 3, 4, 9]), (777, 94, list(range(0, 94, 3))), (64, 5, [7, 200, 65535]), (300, 7, list(range(7)))):
+        lv = torch.tensor(label_values)
+        lab = lv[torch.randint(0, len(lv), (n,), generator=gen)]
+        logits = torch.randn(n, k, generator=gen) * 2
+        pred = torch.sigmoid(logits)
+        out = {}
+        for mode in ("device", "host"):
+            monkeypatch.setenv("DMNERF_INS_ASSIGN", mode)
+            p = cu(pred.numpy()).requires_grad_(True)
+            parts = ins_criterion(p, cu(lab.numpy()), k)
+            parts[0].sum().backward()
+            out[mode] = ([float(x.detach().float().sum()) for x in parts], p.grad.clone())
+        np.testing.assert_allclose(out["device"][0], out["host"][0], rtol=2e-6, atol=1e-7)
+        assert float((out["device"][1] - out["host"][1]).abs().max()) <= 1e-6 * float(out["host"][1].abs().max())
+        monkeypatch.setenv("DMNERF_INS_ASSIGN", "device")
+        roc, nv = ins_assignment(cu(pred.numpy()), cu(lab.numpy()), k)
+        assert int(nv) == len(label_values) and int((roc >= 0).sum()) == len(label_values)
+    monkeypatch.setenv("DMNERF_INS_ASSIGN", "device")
+    p = cu(pred.numpy()).requires_grad_(True)
+    labd = cu(lab.numpy()).to(torch.int32)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        parts = ins_criterion(p, labd, k)
+        parts[0].backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.isfinite(p.grad).all()
+
+
+def test_instance_loss_rejected_labels_are_reported_on_the_next_call():
+    """Labels the device ranking cannot take (>= 65536, negative, or more distinct labels than channels): that call's loss is NaN
+    and its gradient zero -- nothing is read back -- and the NEXT ins_criterion call raises."""
+    from dmnerf_b200.evaluator import ins_criterion
+    gen = torch.Generator().manual_seed(2)
+    pred = torch.sigmoid(torch.randn(128, 6, generator=gen))
+    for lab in (torch.randint(0, 6, (128,), generator=gen) + 70000, torch.randint(0, 6, (128,), generator=gen) - 3,
+                torch.arange(128) % 9):
+        p = cu(pred.numpy()).requires_grad_(True)
+        parts = ins_criterion(p, cu(lab.numpy()), 6)
+        parts[0].backward()
+        assert torch.isnan(parts[0]).all() and float(p.grad.abs().max()) == 0.0
+        torch.cuda.synchronize()
+        with pytest.raises(RuntimeError, match="earlier call"):
+            ins_criterion(p, cu((torch.arange(128) % 6).numpy()), 6)
+    parts = ins_criterion(cu(pred.numpy()), cu((torch.arange(128) % 6).numpy()), 6)       # the word was cleared: back to normal
+    assert torch.isfinite(parts[0]).all()
+
+
 def test_ray_selection_generates_only_the_selected_rays(golden_dir):
     """get_select_full / get_select_crop (helpers.py:64-111) natively: same numpy draws, rays bit-identical to the rows of the
     full get_rays_k grid, colours / labels gathered at the same pixels."""
