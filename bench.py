@@ -457,7 +457,7 @@ def run_ours(args):
             opt.step()
 
         # the reference's whole iteration (train_dmsr.py:23-64) through the same call surface: ray selection, both Hungarian
-        # instance losses (host assignment inside), both emptiness penalizers, backward, Adam
+        # instance losses (assignment on the device), both emptiness penalizers, backward, Adam
         gt_rgb = torch.rand(wl["H"], wl["W"], 3, device=dev)
         gt_lab = (torch.arange(n_rays, device=dev).reshape(wl["H"], wl["W"]) * min(7, ins_num) // n_rays).to(torch.int16)
         pose = torch.from_numpy(wl["c2w"]).to(dev)
@@ -499,8 +499,18 @@ def run_ours(args):
         try:
             fms, fms_dev = timed(full_iteration, 5)
             train["full_iteration"] = {"ms_per_step": fms, "device_ms_per_step": fms_dev,
-                                       "what": "train_dmsr.py:23-64 through the drop-in call surface: get_select_full, dm_nerf, 2 x MSE, "
-                                               "2 x ins_criterion (Hungarian assignment on the host), 2 x ins_penalizer, backward, Adam"}
+                                       "what": "train_dmsr.py:23-64 through the drop-in call surface: get_select_full (the reference's "
+                                               "np.random.choice draw: a host-side shuffle of all H*W pixel indices, 3-4 ms, bounds "
+                                               "this number), dm_nerf, 2 x MSE, 2 x ins_criterion (Hungarian assignment on the device, "
+                                               "no host hop), 2 x ins_penalizer, backward, Adam"}
+            os.environ["DMNERF_SELECT"] = "device"
+            try:
+                fms2, fms2_dev = timed(full_iteration, 10)
+            finally:
+                del os.environ["DMNERF_SELECT"]
+            train["full_iteration_device_select"] = {"ms_per_step": fms2, "device_ms_per_step": fms2_dev,
+                                                     "what": "the same iteration with DMNERF_SELECT=device (pixels drawn by the native "
+                                                             "keyed-bijection kernel: uniform without replacement, not numpy's stream)"}
         except Exception as exc:                       # informational block: never fail the bench line because of it
             train["full_iteration"] = {"error": str(exc)}
         # the emptiness penalizer on the fine network's per-sample outputs (forward + backward), HBM-streaming

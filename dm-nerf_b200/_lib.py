@@ -51,6 +51,9 @@ PROTOTYPES = {
     "dmnerf_get_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, _f32p, _f32p, C.c_void_p]),
     "dmnerf_get_rays_at": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p, C.c_int64, _f32p,
                                      _f32p, C.c_void_p]),
+    "dmnerf_get_rays_at_dev": (C.c_int, [C.POINTER(C.c_float), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, _f32p,
+                                         _f32p, C.c_void_p]),
+    "dmnerf_select_pixels": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "dmnerf_hungarian_costs": (C.c_int, [_f32p, C.c_void_p, C.c_int64, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "dmnerf_ins_loss_backward": (C.c_int, [_f32p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p,
                                            _f32p, C.c_void_p]),

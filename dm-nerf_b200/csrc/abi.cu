@@ -183,7 +183,19 @@ DMNERF_API int dmnerf_get_rays_at(const float* K_host, const float* c2w_host, in
                                   float* rays_o, float* rays_d, void* stream) {
   DMN_CHECK(K_host && c2w_host && (n == 0 || (pixels && rays_o && rays_d)), "get_rays_at: NULL argument");
   DMN_CHECK(n >= 0, "get_rays_at: negative count");
-  return launch_rays_at(K_host, c2w_host, H, W, pixels, n, rays_o, rays_d, (cudaStream_t)stream);
+  return launch_rays_at(K_host, c2w_host, nullptr, 0, H, W, pixels, n, rays_o, rays_d, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_get_rays_at_dev(const float* K_host, const float* c2w_dev, int64_t c2w_row_stride, int H, int W,
+                                      const int64_t* pixels, int64_t n, float* rays_o, float* rays_d, void* stream) {
+  DMN_CHECK(K_host && c2w_dev && (n == 0 || (pixels && rays_o && rays_d)), "get_rays_at_dev: NULL argument");
+  DMN_CHECK(n >= 0 && c2w_row_stride >= 4, "get_rays_at_dev: bad count / row stride");
+  return launch_rays_at(K_host, nullptr, c2w_dev, c2w_row_stride, H, W, pixels, n, rays_o, rays_d, (cudaStream_t)stream);
+}
+
+DMNERF_API int dmnerf_select_pixels(uint64_t seed, int H, int W, int64_t n, int64_t* pixels, void* stream) {
+  DMN_CHECK(n == 0 || pixels, "select_pixels: NULL buffer");
+  return launch_select_pixels(seed, H, W, n, pixels, (cudaStream_t)stream);
 }
 
 DMNERF_API int dmnerf_hungarian_costs(const float* pred, const int32_t* gt_row, int64_t n, int ins_num, float* cost_ce,

@@ -262,38 +262,47 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
 // ------------------------------------------------------------------------------------------------ head gradients
 // d rgb_hid = mask . (d_rgb W_rgb_out), d ins_hid = mask . (d_ins W_ins_out)   (dm_nerf.py:102-103 backwards, K = 3 / ins_num+1)
 // written side by side into one [M,256] plane so that ONE dW GEMM against h7 serves both branches.
-// One thread per (row, hidden unit); the head weights live in shared memory.
-constexpr int HEAD_ROWS = 4;        // rows per iteration: one barrier pair per 4 rows
+// One thread per (row, hidden unit); the head weights live in shared memory.  The rows of d_out are staged zero-padded to a
+// multiple of 4 channels and read back as float4 broadcasts (the scalar version issued one shared-memory load per multiply-add
+// and was bound by the load unit, not by the 268 MB it writes).
+constexpr int HEAD_ROWS = 8;        // rows per iteration: one barrier pair per 8 rows
 __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict__ d_out, int C, int64_t m, const float* __restrict__ w_rgb,
                                                         const float* __restrict__ w_ins, int ins1, const uint16_t* __restrict__ bits,
                                                         float* __restrict__ s12, int rows_per_block) {
-  extern __shared__ float sm[];
-  float* wi = sm;                         // [ins1][128]
-  float* wr = wi + ins1 * 128;            // [3][128]
-  float* drow = wr + 3 * 128;             // [HEAD_ROWS][C]: contiguous rows of d_out
+  extern __shared__ __align__(16) float sm[];
+  const int ins4 = (ins1 + 3) & ~3;       // instance channels padded to a multiple of 4 (zero weights)
+  const int CP = 4 + ins4;                // staged row: rgb, sigma, padded instance channels
+  float* wi = sm;                         // [ins4][128]
+  float* drow = wi + ins4 * 128;          // [HEAD_ROWS][CP]
   const int j = threadIdx.x;
-  for (int k = 0; k < ins1; ++k) wi[k * 128 + j] = w_ins[k * 128 + j];
-  for (int k = 0; k < 3; ++k) wr[k * 128 + j] = w_rgb[k * 128 + j];
+  for (int k = 0; k < ins4; ++k) wi[k * 128 + j] = (k < ins1) ? w_ins[k * 128 + j] : 0.0f;
+  const float wr0 = w_rgb[j], wr1 = w_rgb[128 + j], wr2 = w_rgb[256 + j];
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < m) ? r0 + rows_per_block : m;
   for (int64_t row = r0; row < r1; row += HEAD_ROWS) {
     const int nr = (int)((r1 - row < HEAD_ROWS) ? r1 - row : HEAD_ROWS);
     __syncthreads();
-    for (int i = j; i < nr * C; i += 128) drow[i] = d_out[row * C + i];
+    for (int i = j; i < HEAD_ROWS * CP; i += 128) {
+      const int q = i / CP, c = i - q * CP;
+      drow[i] = (q < nr && c < C) ? d_out[(row + q) * C + c] : 0.0f;
+    }
     __syncthreads();
     float a1[HEAD_ROWS], a2[HEAD_ROWS];
+    const float4* d4 = reinterpret_cast<const float4*>(drow);
 #pragma unroll
-    for (int q = 0; q < HEAD_ROWS; ++q) { a1[q] = 0.0f; a2[q] = 0.0f; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float wv = wr[k * 128 + j];
-#pragma unroll
-      for (int q = 0; q < HEAD_ROWS; ++q) a1[q] = fmaf(drow[q * C + k], wv, a1[q]);
+    for (int q = 0; q < HEAD_ROWS; ++q) {
+      const float4 d = d4[q * (CP / 4)];
+      a1[q] = fmaf(d.z, wr2, fmaf(d.y, wr1, __fmul_rn(d.x, wr0)));        // same order as the scalar loop: ((0 + x w0) + y w1) + z w2
+      a2[q] = 0.0f;
     }
-    for (int k = 0; k < ins1; ++k) {
-      const float wv = wi[k * 128 + j];
+    for (int k4 = 0; k4 < ins4 / 4; ++k4) {
+      const float w0 = wi[(4 * k4) * 128 + j], w1 = wi[(4 * k4 + 1) * 128 + j], w2 = wi[(4 * k4 + 2) * 128 + j],
+                  w3 = wi[(4 * k4 + 3) * 128 + j];
 #pragma unroll
-      for (int q = 0; q < HEAD_ROWS; ++q) a2[q] = fmaf(drow[q * C + 4 + k], wv, a2[q]);
+      for (int q = 0; q < HEAD_ROWS; ++q) {
+        const float4 d = d4[q * (CP / 4) + 1 + k4];
+        a2[q] = fmaf(d.w, w3, fmaf(d.z, w2, fmaf(d.y, w1, fmaf(d.x, w0, a2[q]))));
+      }
     }
 #pragma unroll
     for (int q = 0; q < HEAD_ROWS; ++q) {
@@ -343,7 +352,8 @@ int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const ui
   const int ins1 = p.ins_num + 1, C = 4 + ins1;
   if (m == 0) return 0;
   const int rows = 64;
-  const size_t smem = (size_t)((ins1 + 3) * 128 + bk::HEAD_ROWS * C) * sizeof(float);
+  const int ins4 = (ins1 + 3) & ~3;
+  const size_t smem = (size_t)(ins4 * 128 + bk::HEAD_ROWS * (4 + ins4)) * sizeof(float);
   static PerDeviceOnce once;
   if (once.first()) DMN_CUDA(cudaFuncSetAttribute(bk::bwd_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   bk::bwd_heads_kernel<<<(unsigned)((m + rows - 1) / rows), 128, smem, st>>>(d_out, C, m, p.w[L_RGB_OUT], p.w[L_INS_OUT], ins1, bits, s12,

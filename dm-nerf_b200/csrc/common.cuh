@@ -125,8 +125,9 @@ int launch_prep_z(const float* z_in, int64_t z_stride, const float* t_rand, int6
 int launch_hier_sample(const float* z_c, const float* w_c, const float* u, int64_t n, int s, int ni, float* z_fine,
                        cudaStream_t st);
 int launch_rays(const float* K9, const float* c2w12, int H, int W, float* rays_o, float* rays_d, cudaStream_t st);
-int launch_rays_at(const float* K9, const float* c2w12, int H, int W, const int64_t* pix, int64_t n, float* rays_o, float* rays_d,
-                   cudaStream_t st);
+int launch_rays_at(const float* K9, const float* c2w12, const float* c2w_dev, int64_t c2w_ld, int H, int W, const int64_t* pix,
+                   int64_t n, float* rays_o, float* rays_d, cudaStream_t st);
+int launch_select_pixels(uint64_t seed, int H, int W, int64_t n, int64_t* pix, cudaStream_t st);
 // MLP, SIMT fp32 path.  Exactly one of x / (rays_o, rays_d, z) is used.
 int launch_mlp_simt(const NetParams& p, const float* x, const float* rays_o, const float* rays_d, const float* z,
                     int64_t m, int s, float* out, float* acts, cudaStream_t st);

@@ -236,10 +236,18 @@ __global__ void rays_kernel(Camera cam, int H, int W, float* __restrict__ rays_o
 // Rays of selected pixels only (training: get_select_full / get_select_crop, helpers.py:64-111, keep 1024-3072 of the H*W
 // rays of a frame): pix[i] = row * W + column of sample i.  Same arithmetic as rays_kernel, so the rows are bit-identical to
 // get_rays_k(...)[row, column].
-__global__ void rays_at_kernel(Camera cam, int W, const int64_t* __restrict__ pix, int64_t n, float* __restrict__ rays_o,
-                               float* __restrict__ rays_d) {
+// c2w_dev != NULL: the pose is read from device memory (rows of 4 floats, c2w_ld apart) -- the training loop hands over a CUDA
+// tensor (train_dmsr.py:27) and copying it to the host would synchronise every iteration.
+__global__ void rays_at_kernel(Camera cam, const float* __restrict__ c2w_dev, int64_t c2w_ld, int W, const int64_t* __restrict__ pix,
+                               int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
+  if (c2w_dev) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cam.c2w[4 * r + c] = __ldg(c2w_dev + r * c2w_ld + c);
+  }
   const int64_t idx = pix[t];
   const float i = (float)(idx % W), j = (float)(idx / W);
   const float dx = __fdiv_rn(__fsub_rn(i, cam.K[2]), cam.K[0]);
@@ -253,14 +261,55 @@ __global__ void rays_at_kernel(Camera cam, int W, const int64_t* __restrict__ pi
   }
 }
 
-int launch_rays_at(const float* K9, const float* c2w12, int H, int W, const int64_t* pix, int64_t n, float* rays_o, float* rays_d,
-                   cudaStream_t st) {
+int launch_rays_at(const float* K9, const float* c2w12, const float* c2w_dev, int64_t c2w_ld, int H, int W, const int64_t* pix,
+                   int64_t n, float* rays_o, float* rays_d, cudaStream_t st) {
   DMN_CHECK(H >= 1 && W >= 1 && (int64_t)H * W <= (1LL << 31), "get_rays_at: bad image size %dx%d", H, W);
   if (n == 0) return 0;
   Camera cam;
   for (int i = 0; i < 9; ++i) cam.K[i] = K9[i];
-  for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w12[i];
-  rays_at_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, W, pix, n, rays_o, rays_d);
+  for (int i = 0; i < 12; ++i) cam.c2w[i] = c2w12 ? c2w12[i] : 0.0f;
+  rays_at_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, c2w_dev, c2w_ld, W, pix, n, rays_o, rays_d);
+  DMN_LAUNCH_OK();
+  return 0;
+}
+
+// n DISTINCT pseudo-random pixels of an H x W image without any host work: pix[i] = P(i), P a keyed bijection of [0, H*W)
+// (6-round Feistel network on the next even power of two, cycle-walked back into range: at most 4 expected steps).  The
+// uniform-without-replacement draw of helpers.py:100 (np.random.choice(H*W, N, replace=False)) costs the host a 307 200-element
+// shuffle per iteration; this is the opt-in replacement (DMNERF_SELECT=device: NOT the reference's random stream).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void select_pixels_kernel(uint64_t seed, uint32_t total, int half_bits, int64_t n, int64_t* __restrict__ pix) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t x = (uint32_t)t;
+  do {
+    uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+    for (int round = 0; round < 6; ++round) {
+      const uint32_t k = (uint32_t)(seed >> (8 * (round & 3))) ^ (uint32_t)(seed >> 32) * (2u * round + 1u);
+      const uint32_t f = mix32(r ^ k ^ (0x9e3779b9u * (round + 1))) & mask;
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << half_bits) | r;
+  } while (x >= total);
+  pix[t] = (int64_t)x;
+}
+
+int launch_select_pixels(uint64_t seed, int H, int W, int64_t n, int64_t* pix, cudaStream_t st) {
+  const int64_t total = (int64_t)H * W;
+  DMN_CHECK(H >= 1 && W >= 1 && total <= (1LL << 30), "select_pixels: bad image size %dx%d", H, W);
+  DMN_CHECK(n >= 0 && n <= total, "select_pixels: %lld distinct pixels of %lld", (long long)n, (long long)total);
+  if (n == 0) return 0;
+  int bits = 1;
+  while ((1LL << bits) < total) ++bits;
+  const int half_bits = (bits + 1) / 2;
+  select_pixels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, (uint32_t)total, half_bits, n, pix);
   DMN_LAUNCH_OK();
   return 0;
 }

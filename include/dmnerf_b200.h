@@ -118,6 +118,14 @@ DMNERF_API int dmnerf_get_rays(const float* K_host, const float* c2w_host, int H
  * row * W + column) -> rays_o, rays_d [n,3], bit-identical to the rows get_rays_k would produce. */
 DMNERF_API int dmnerf_get_rays_at(const float* K_host, const float* c2w_host, int H, int W, const int64_t* pixels, int64_t n,
                                   float* rays_o, float* rays_d, void* stream);
+/* The same with the pose in DEVICE memory (3 rows of 4 floats, c2w_row_stride floats apart): train_dmsr.py:27 hands
+ * get_select_full a CUDA tensor, and reading it back would synchronise every iteration. */
+DMNERF_API int dmnerf_get_rays_at_dev(const float* K_host, const float* c2w_dev, int64_t c2w_row_stride, int H, int W,
+                                      const int64_t* pixels, int64_t n, float* rays_o, float* rays_d, void* stream);
+/* n distinct pseudo-random pixels (row * W + column, DEVICE int64) of an H x W image from a keyed bijection of [0, H*W): the
+ * opt-in device-side replacement of np.random.choice(H*W, N, replace=False) in helpers.py:100 (uniform without replacement, but
+ * NOT numpy's random stream). */
+DMNERF_API int dmnerf_select_pixels(uint64_t seed, int H, int W, int64_t n, int64_t* pixels, void* stream);
 
 /* Hungarian-matched instance loss, networks/evaluator.py:19-74 (ins_criterion / hungarian; train_dmsr.py:38-45).
  * dmnerf_hungarian_costs: pred [N,ins_num] (rendered instance probabilities), gt_row [N] (int32: index of the ray's label among

@@ -442,6 +442,57 @@ def test_ray_selection_generates_only_the_selected_rays(golden_dir):
     assert torch.equal(ti, lab.reshape(-1)[torch.from_numpy(labeled).to(DEV)])
 
 
+def test_device_side_pixel_selection_and_device_resident_pose(monkeypatch):
+    """DMNERF_SELECT=device: N distinct in-range pixels from the keyed-bijection kernel (every pixel reachable, seeds differ,
+    roughly uniform), rays bit-identical to the full grid at those pixels; and get_rays_at reads a strided device pose without
+    synchronising."""
+    from dmnerf_b200.helpers import get_select_full, get_rays_k, get_rays_at, select_pixels
+    wl = synth.workload("dmsr_study")
+    H, W = 480, 640
+    K = wl["K"]
+    pose44 = torch.eye(4, device=DEV)
+    pose44[:3, :4] = cu(wl["c2w"])[:3, :4]
+    a = select_pixels(H, W, 1024, DEV, seed=5).cpu().numpy()
+    b = select_pixels(H, W, 1024, DEV, seed=6).cpu().numpy()
+    assert len(set(a.tolist())) == 1024 and a.min() >= 0 and a.max() < H * W and len(set(a.tolist()) & set(b.tolist())) < 40
+    full = select_pixels(37, 41, 37 * 41, DEV, seed=9).cpu().numpy()               # the whole image: a permutation
+    assert sorted(full.tolist()) == list(range(37 * 41))
+    hist = np.zeros(16)
+    for s in range(64):
+        hist += np.bincount(select_pixels(H, W, 4096, DEV, seed=1000 + s).cpu().numpy() * 16 // (H * W), minlength=16)
+    assert np.abs(hist / hist.sum() - 1 / 16).max() < 0.004                       # 262 144 draws: sigma of a bin share = 0.0005
+    assert select_pixels(H, W, 0, DEV, seed=1).shape == (0,)
+    ro, rd = get_rays_k(H, W, K, pose44[:3, :4])
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        pix = select_pixels(H, W, 777, DEV, seed=3)
+        o2, d2 = get_rays_at(H, W, K, pose44, pix)                                # [4,4] device pose, rows 4 floats apart
+        o3, d3 = get_rays_at(H, W, K, pose44[:3, :4], pix)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.equal(d2, rd.reshape(-1, 3)[pix]) and torch.equal(o2, ro.reshape(-1, 3)[pix])
+    assert torch.equal(d3, d2) and torch.equal(o3, o2)
+    monkeypatch.setenv("DMNERF_SELECT", "device")
+    import dmnerf_b200.helpers as helpers_mod
+    drawn = []
+    real = helpers_mod.select_pixels
+    monkeypatch.setattr(helpers_mod, "select_pixels", lambda *a, **k: drawn.append(real(*a, **k)) or drawn[-1])
+    gen = torch.Generator().manual_seed(5)
+    rgb = torch.rand(H, W, 3, generator=gen).to(DEV)
+    lab = torch.randint(0, 13, (H, W), generator=gen).to(torch.int16).to(DEV)
+    np.random.seed(4)
+    tc, ti, rays = get_select_full(rgb, pose44[:3, :4], K, lab, 1024)
+    np.random.seed(4)
+    tc2, ti2, rays2 = get_select_full(rgb, pose44[:3, :4], K, lab, 1024)
+    assert rays.shape == (2, 1024, 3) and tc.shape == (1024, 3) and ti.shape == (1024,) and len(drawn) == 2
+    assert not torch.equal(drawn[0], drawn[1])                                    # the call counter moves the permutation on
+    p0 = drawn[0]
+    assert len(set(p0.tolist())) == 1024
+    assert torch.equal(rays[1], rd.reshape(-1, 3)[p0]) and torch.equal(rays[0], ro.reshape(-1, 3)[p0])
+    assert torch.equal(tc, rgb.reshape(-1, 3)[p0]) and torch.equal(ti, lab.reshape(-1)[p0])
+
+
 def test_reference_training_iteration_through_the_dropin_imports():
     """One iteration of train_dmsr.py:23-64 written against the drop-in `networks` package exactly as the reference script
     imports it (ray selection -> dm_nerf -> MSE + Hungarian instance loss + emptiness penalizer -> backward -> Adam), every
