@@ -43,6 +43,9 @@ struct Scratch {
 
 using namespace dmnerf;
 
+constexpr int HOST_PARTS = 4;              // a *_host call on >= HOST_PART_MIN_RAYS rays is rendered in this many parts
+constexpr int64_t HOST_PART_MIN_RAYS = 131072;
+
 struct dmnerf_ctx {
   int device = 0;
   NetParams net[2];
@@ -55,6 +58,9 @@ struct dmnerf_ctx {
   bool last_fused = false;       // the last render call took the single-kernel path
   bool profile_valid = false;
   cudaEvent_t ev[DMNERF_N_STAGES + 1] = {};
+  // *_host entry points: second stream + events so that the copies of one part of a large batch overlap the kernels of the next
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[HOST_PARTS] = {}, ev_done[HOST_PARTS] = {}, ev_start = nullptr;
   dmnerf_ctx() { memset(net, 0, sizeof(net)); }
 };
 
@@ -89,6 +95,10 @@ DMNERF_API int dmnerf_ctx_destroy(dmnerf_ctx* ctx) {
                     &ctx->host_in, &ctx->host_out, &ctx->frame_rays};
   for (Scratch* s : all) s->release();
   for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_in) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_done) if (e) cudaEventDestroy(e);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return 0;
 }
@@ -437,41 +447,114 @@ static int render_host_impl(dmnerf_ctx* ctx, const dmnerf_render_io* h, const fl
   dmnerf_render_io io;
   memset(&io, 0, sizeof(io));
   float* p = d;
+  float *d_ro = nullptr, *d_rd = nullptr, *d_tr = nullptr, *d_u = nullptr;
   if (dev_rays) {
     io.rays_o = dev_rays_o; io.rays_d = dev_rays_d;
   } else {
-    DMN_CUDA(cudaMemcpyAsync(p, h->rays_o, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_o = p; p += n * 3;
-    DMN_CUDA(cudaMemcpyAsync(p, h->rays_d, (size_t)n * 12, cudaMemcpyHostToDevice, st)); io.rays_d = p; p += n * 3;
+    d_ro = p; io.rays_o = p; p += n * 3;
+    d_rd = p; io.rays_d = p; p += n * 3;
   }
-  DMN_CUDA(cudaMemcpyAsync(p, h->z_coarse, zin * 4, cudaMemcpyHostToDevice, st)); io.z_coarse = p; p += zin;
+  float* d_z = p; io.z_coarse = p; p += zin;
   io.z_row_stride = h->z_row_stride;
   if (perturb) {
     DMN_CHECK(h->t_rand && h->u, "render_forward_host: PERTURB needs t_rand and u");
-    DMN_CUDA(cudaMemcpyAsync(p, h->t_rand, (size_t)n * S * 4, cudaMemcpyHostToDevice, st)); io.t_rand = p; p += n * S;
-    DMN_CUDA(cudaMemcpyAsync(p, h->u, (size_t)n * NI * 4, cudaMemcpyHostToDevice, st)); io.u = p; p += n * NI;
+    d_tr = p; io.t_rand = p; p += n * S;
+    d_u = p; io.u = p; p += n * NI;
   }
   // ---- outputs: one device arena, carved for every non-NULL host output
-  struct Out { float* dmnerf_render_io::* hp; float* dmnerf_render_io::* dp; size_t per_ray; };
+  struct Out { float* dmnerf_render_io::* hp; size_t per_ray; };
   const Out outs[] = {
-      {&dmnerf_render_io::rgb_coarse, &dmnerf_render_io::rgb_coarse, 3}, {&dmnerf_render_io::rgb_fine, &dmnerf_render_io::rgb_fine, 3},
-      {&dmnerf_render_io::depth_coarse, &dmnerf_render_io::depth_coarse, 1}, {&dmnerf_render_io::depth_fine, &dmnerf_render_io::depth_fine, 1},
-      {&dmnerf_render_io::acc_coarse, &dmnerf_render_io::acc_coarse, 1}, {&dmnerf_render_io::acc_fine, &dmnerf_render_io::acc_fine, 1},
-      {&dmnerf_render_io::ins_coarse, &dmnerf_render_io::ins_coarse, (size_t)n_ins_out}, {&dmnerf_render_io::ins_fine, &dmnerf_render_io::ins_fine, (size_t)n_ins_out},
-      {&dmnerf_render_io::z_vals_coarse, &dmnerf_render_io::z_vals_coarse, (size_t)S}, {&dmnerf_render_io::z_vals_fine, &dmnerf_render_io::z_vals_fine, (size_t)F},
-      {&dmnerf_render_io::weights_coarse, &dmnerf_render_io::weights_coarse, (size_t)S}, {&dmnerf_render_io::weights_fine, &dmnerf_render_io::weights_fine, (size_t)F},
-      {&dmnerf_render_io::raw_coarse, &dmnerf_render_io::raw_coarse, (size_t)S * C}, {&dmnerf_render_io::raw_fine, &dmnerf_render_io::raw_fine, (size_t)F * C},
+      {&dmnerf_render_io::rgb_coarse, 3}, {&dmnerf_render_io::rgb_fine, 3},
+      {&dmnerf_render_io::depth_coarse, 1}, {&dmnerf_render_io::depth_fine, 1},
+      {&dmnerf_render_io::acc_coarse, 1}, {&dmnerf_render_io::acc_fine, 1},
+      {&dmnerf_render_io::ins_coarse, (size_t)n_ins_out}, {&dmnerf_render_io::ins_fine, (size_t)n_ins_out},
+      {&dmnerf_render_io::z_vals_coarse, (size_t)S}, {&dmnerf_render_io::z_vals_fine, (size_t)F},
+      {&dmnerf_render_io::weights_coarse, (size_t)S}, {&dmnerf_render_io::weights_fine, (size_t)F},
+      {&dmnerf_render_io::raw_coarse, (size_t)S * C}, {&dmnerf_render_io::raw_fine, (size_t)F * C},
   };
   size_t out_floats = 0;
   for (const Out& o : outs) if (h->*(o.hp)) out_floats += (size_t)n * o.per_ray;
   if (ctx->host_out.reserve(out_floats * 4 + 16)) return 2;
   float* q = (float*)ctx->host_out.ptr;
-  for (const Out& o : outs) if (h->*(o.hp)) { io.*(o.dp) = q; q += (size_t)n * o.per_ray; }
+  for (const Out& o : outs) if (h->*(o.hp)) { io.*(o.hp) = q; q += (size_t)n * o.per_ray; }
 
-  int rc = dmnerf_render_forward(ctx, &io, n, S, NI, flags, impl, stream);
-  if (rc) return rc;
-  for (const Out& o : outs)
-    if (h->*(o.hp))
-      DMN_CUDA(cudaMemcpyAsync(h->*(o.hp), io.*(o.dp), (size_t)n * o.per_ray * 4, cudaMemcpyDeviceToHost, st));
+  // Copies of rows [r0, r1) of the batch.  Every ray is rendered independently of its neighbours (the rows of a tile never
+  // mix), so rendering a large batch in parts gives the same bits as one launch.
+  auto copy_in = [&](int64_t r0, int64_t r1, cudaStream_t cs) -> int {
+    const size_t cnt = (size_t)(r1 - r0);
+    if (!dev_rays) {
+      DMN_CUDA(cudaMemcpyAsync(d_ro + r0 * 3, h->rays_o + r0 * 3, cnt * 12, cudaMemcpyHostToDevice, cs));
+      DMN_CUDA(cudaMemcpyAsync(d_rd + r0 * 3, h->rays_d + r0 * 3, cnt * 12, cudaMemcpyHostToDevice, cs));
+    }
+    if (h->z_row_stride != 0)
+      DMN_CUDA(cudaMemcpyAsync(d_z + r0 * h->z_row_stride, h->z_coarse + r0 * h->z_row_stride, cnt * h->z_row_stride * 4,
+                               cudaMemcpyHostToDevice, cs));
+    if (perturb) {
+      DMN_CUDA(cudaMemcpyAsync(d_tr + r0 * S, h->t_rand + r0 * S, cnt * S * 4, cudaMemcpyHostToDevice, cs));
+      DMN_CUDA(cudaMemcpyAsync(d_u + r0 * NI, h->u + r0 * NI, cnt * NI * 4, cudaMemcpyHostToDevice, cs));
+    }
+    return 0;
+  };
+  auto copy_out = [&](int64_t r0, int64_t r1, cudaStream_t cs) -> int {
+    for (const Out& o : outs)
+      if (h->*(o.hp))
+        DMN_CUDA(cudaMemcpyAsync(h->*(o.hp) + r0 * o.per_ray, io.*(o.hp) + r0 * o.per_ray, (size_t)(r1 - r0) * o.per_ray * 4,
+                                 cudaMemcpyDeviceToHost, cs));
+    return 0;
+  };
+  auto part_io = [&](int64_t r0) {
+    dmnerf_render_io pi = io;
+    if (pi.rays_o) { pi.rays_o += r0 * 3; pi.rays_d += r0 * 3; }
+    if (pi.z_row_stride != 0) pi.z_coarse += r0 * pi.z_row_stride;
+    if (pi.t_rand) pi.t_rand += r0 * S;
+    if (pi.u) pi.u += r0 * NI;
+    for (const Out& o : outs) if (pi.*(o.hp)) pi.*(o.hp) += r0 * o.per_ray;
+    return pi;
+  };
+  if (h->z_row_stride == 0) DMN_CUDA(cudaMemcpyAsync(d_z, h->z_coarse, zin * 4, cudaMemcpyHostToDevice, st));   // the shared depth row
+
+  const bool parts = n >= HOST_PART_MIN_RAYS && !ctx->profiling;
+  if (!parts) {
+    if (copy_in(0, n, st)) return 1;
+    int rc = dmnerf_render_forward(ctx, &io, n, S, NI, flags, impl, stream);
+    if (rc) return rc;
+    if (copy_out(0, n, st)) return 1;
+    return dmnerf_sync_check(ctx, stream);
+  }
+  // Large batch: HOST_PARTS launches on the caller's stream; the inputs of part i+1 and the maps of part i-1 travel on a second
+  // stream while part i is rendered, so that only the first upload and the last download are not hidden behind kernels.
+  if (!ctx->copy_stream) {
+    DMN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < HOST_PARTS; ++i) {
+      DMN_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      DMN_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    }
+    DMN_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  int64_t edge[HOST_PARTS + 1];
+  for (int i = 0; i <= HOST_PARTS; ++i) edge[i] = ((n * i / HOST_PARTS) + 1) & ~(int64_t)1;      // even boundaries: whole ray pairs
+  edge[0] = 0; edge[HOST_PARTS] = n;
+  DMN_CUDA(cudaEventRecord(ctx->ev_start, st));                   // the copy stream starts after everything already queued on st
+  DMN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_start, 0));
+  if (copy_in(edge[0], edge[1], st)) return 1;
+  for (int i = 1; i < HOST_PARTS; ++i) {
+    if (copy_in(edge[i], edge[i + 1], cs)) return 1;
+    DMN_CUDA(cudaEventRecord(ctx->ev_in[i], cs));
+  }
+  int rc = 0;
+  for (int i = 0; i < HOST_PARTS && !rc; ++i) {
+    if (i > 0) DMN_CUDA(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
+    const dmnerf_render_io pi = part_io(edge[i]);
+    rc = dmnerf_render_forward(ctx, &pi, edge[i + 1] - edge[i], S, NI, flags, impl, stream);
+    if (rc) break;
+    DMN_CUDA(cudaEventRecord(ctx->ev_done[i], st));
+    DMN_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[i], 0));
+    if (copy_out(edge[i], edge[i + 1], cs)) { rc = 1; break; }
+  }
+  const cudaError_t ce = cudaStreamSynchronize(cs);               // also on the error path: nothing of this call stays in flight
+  if (rc) { cudaStreamSynchronize(st); return rc; }
+  DMN_CUDA(ce);
   return dmnerf_sync_check(ctx, stream);
 }
 

@@ -241,7 +241,9 @@ DMNERF_API int dmnerf_render_forward(dmnerf_ctx* ctx, const dmnerf_render_io* io
                           int n_importance, int flags, int impl, void* stream);
 
 /* Same call with HOST buffers (pageable or pinned): copies rays in, renders, copies every non-NULL
- * output back, and synchronises the stream.  This is the end-to-end entry point bench.py times. */
+ * output back, and synchronises the stream.  This is the end-to-end entry point bench.py times.
+ * A batch of >= 131 072 rays is rendered in four parts (same bits: rays are independent) whose uploads / downloads travel on a
+ * second stream while the neighbouring parts are rendered: only the first upload and the last download are exposed. */
 DMNERF_API int dmnerf_render_forward_host(dmnerf_ctx* ctx, const dmnerf_render_io* io_host, int64_t n_rays, int n_coarse,
                                int n_importance, int flags, int impl, void* stream);
 

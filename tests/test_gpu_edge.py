@@ -143,6 +143,41 @@ def test_render_frame_driver_matches_explicit_rays():
     assert torch.equal(part["rgb"], ref["rgb_fine"].cpu()[37:138]) and torch.equal(part["acc"], fr["acc"].reshape(-1)[37:138])
 
 
+def test_host_entry_point_in_parts_is_bitwise_the_single_launch():
+    """dmnerf_render_forward_host on >= 131 072 rays renders the batch in four parts whose copies overlap the neighbouring
+    parts' kernels (second stream): same bits as the device-resident single launch, odd ray count, per-ray depth rows
+    (z_row_stride != 0) and the shared row (stride 0), and a small batch (single part) through the same call."""
+    import ctypes as C
+    from dmnerf_b200.testing import make_models
+    from dmnerf_b200.engine import get_context
+    from dmnerf_b200.render import render_rays
+    wl = synth.workload("dmsr_study")
+    nc, nf, _, _ = make_models(5, 6, 13, "cuda")
+    ctx = get_context(torch.device("cuda"))
+    ctx.bind(0, nc); ctx.bind(1, nf)
+    for n, per_ray_z in ((131073, False), (131080, True), (4097, False)):
+        ro = torch.from_numpy(wl["rays_o"][:n]).contiguous().pin_memory()
+        rd = torch.from_numpy(wl["rays_d"][:n]).contiguous().pin_memory()
+        zrow = torch.linspace(float(wl["near"]), float(wl["far"]), 64)
+        zc = (zrow[None].expand(n, 64) + 0.01 * torch.arange(n)[:, None] / n).contiguous() if per_ray_z else zrow.contiguous()
+        zc = zc.pin_memory()
+        out = {k: torch.full((n,) + shape, float("nan")).pin_memory() for k, shape in
+               (("rgb_fine", (3,)), ("depth_fine", ()), ("acc_coarse", ()), ("ins_fine", (13,)))}
+        io = _lib.RenderIO()
+        io.rays_o, io.rays_d, io.z_coarse, io.z_row_stride = _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(zc), (64 if per_ray_z else 0)
+        for k, v in out.items():
+            setattr(io, k, _lib.ptr(v))
+        before = _lib.launch_count()
+        _lib.check(ctx.lib.dmnerf_render_forward_host(ctx.handle, io, n, 64, 128, 0, 0, ctx.stream()), "dmnerf_render_forward_host")
+        launches = _lib.launch_count() - before
+        assert launches == (4 if n >= 131072 else 1), launches
+        with torch.no_grad():
+            zdev = zc.cuda() if per_ray_z else zc.cuda()[None].expand(n, 64)
+            ref = render_rays(ro.cuda(), rd.cuda(), nc, nf, zdev, N_importance=128, want_raw=False)
+        for k, v in out.items():
+            assert torch.equal(v, ref[k].cpu()), (n, k)
+
+
 def _manip_setup(golden_dir):
     g = dict(np.load(os.path.join(golden_dir, "manipulator.npz")))
     ins_num = int(g["ins_num"])
