@@ -47,5 +47,25 @@ for cc in (18, 64, 132):
     praw = torch.randn(9, 50, cc, device=dev, requires_grad=True)
     pz = torch.rand(9, 50, device=dev).sort(-1).values * 11 + 4
     ins_penalizer(praw, pz, pz[:, 20].clone(), torch.randn(9, 3, device=dev), pargs).sum().backward()
+# late round 2: device-side pixel selection, host-side assignment path, host entry point rendered in parts (second stream)
+from dmnerf_b200.helpers import select_pixels            # noqa: E402
+pix = select_pixels(48, 64, 48 * 64, dev, seed=3)
+assert sorted(pix.tolist()) == list(range(48 * 64))
+os.environ["DMNERF_INS_ASSIGN"] = "host"
+ins_criterion(pred, ti, 13)[0].sum().backward()
+del os.environ["DMNERF_INS_ASSIGN"]
+if os.environ.get("SANITIZE_PARTS", "1") == "1":
+    nn = 131074
+    hro = torch.from_numpy(wl["rays_o"][:nn]).contiguous().pin_memory()
+    hrd = torch.from_numpy(wl["rays_d"][:nn]).contiguous().pin_memory()
+    hz = z.cpu().contiguous().pin_memory()
+    hout = torch.empty(nn, 3).pin_memory()
+    io = _lib.RenderIO()
+    io.rays_o, io.rays_d, io.z_coarse, io.z_row_stride, io.rgb_fine = _lib.ptr(hro), _lib.ptr(hrd), _lib.ptr(hz), 0, _lib.ptr(hout)
+    nc.eval(); nf.eval()
+    cx = get_context(torch.device(dev))
+    cx.bind(0, nc); cx.bind(1, nf)
+    _lib.check(cx.lib.dmnerf_render_forward_host(cx.handle, io, nn, 64, 128, 0, 0, cx.stream()), "dmnerf_render_forward_host")
+    assert torch.isfinite(hout).all()
 get_context(dev).sync_check()
 print("sanitize run ok", float(a["rgb_fine"].sum()), float(b["rgb_fine"].sum()), float(c["rgb_fine"].sum()))

@@ -48,8 +48,9 @@ for rep, fname, title in (("prof_fused.ncu-rep", "ncu_fused_render", "one launch
                            "training step (196 608 samples; tools/train_step.py)"),
                           ("r02_fwdtrain.ncu-rep", "ncu_train_forward", "one launch of `mlp_umma_kernel<false>` with activations kept: the fine network's "
                            "training forward (196 608 samples; tools/train_step.py)"),
-                          ("r02_dw.ncu-rep", "ncu_dw_gemm", "one launch of `gemm_tn_tc_kernel` (dW = dY^T X of one trunk layer of the fine network) inside a "
-                           "training step")):
+                          ("r02_dw.ncu-rep", "ncu_dw_gemm", "one BATCHED launch of `gemm_tn_tc_kernel<256,256>`: the eight [256x256] weight-gradient "
+                           "products of the network whose backward runs first (144 CTAs = 8 products x 18 sample slices) inside a training step"),
+                          ("r02_dw_b.ncu-rep", "ncu_dw_gemm_b", "the same batched launch for the other network of the step")):
   rp = os.path.join(go, rep)
   if os.path.exists(rp):
       raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
