@@ -55,9 +55,18 @@ struct Unit { float v[8]; };
 
 // 8 floats of row r (valid below r_end), columns col.. (valid below c_end) of a row-major matrix; zero outside.
 __device__ __forceinline__ void load_unit(Unit& u, const float* __restrict__ src, int64_t ld, int64_t r, int64_t r_end, int col,
-                                          int c_end, bool vec_ok) {
+                                          int c_end, int vec_ok) {
   if (r < r_end && vec_ok && col + 8 <= c_end) {
-    const float4* p4 = reinterpret_cast<const float4*>(src + r * ld + col);
+    const float* p = src + r * ld + col;
+#ifdef DMN_LD256
+    if (vec_ok & 2) {       // 32-byte aligned rows: one 256-bit load per unit instead of two 128-bit ones
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(u.v[0]), "=f"(u.v[1]), "=f"(u.v[2]), "=f"(u.v[3]), "=f"(u.v[4]), "=f"(u.v[5]), "=f"(u.v[6]), "=f"(u.v[7])
+                   : "l"(p));
+      return;
+    }
+#endif
+    const float4* p4 = reinterpret_cast<const float4*>(p);
     const float4 x = __ldg(p4), y = __ldg(p4 + 1);
     u.v[0] = x.x; u.v[1] = x.y; u.v[2] = x.z; u.v[3] = x.w; u.v[4] = y.x; u.v[5] = y.y; u.v[6] = y.z; u.v[7] = y.w;
   } else {
@@ -341,10 +350,10 @@ __global__ void __launch_bounds__(NT, 1) gemm_tn_tc_kernel(const __grid_constant
 #pragma unroll
     for (int i = 0; i < UPT; ++i) {
       const int U = tid + i * NT, slab = U >> 8, u = U & 255;
-      if (slab < SA) load_unit(r[i], A, lda, m0 + (u >> 3), me, 64 * slab + (u & 7) * 8, NA, vec_a != 0);
+      if (slab < SA) load_unit(r[i], A, lda, m0 + (u >> 3), me, 64 * slab + (u & 7) * 8, NA, vec_a);
       else if (slab < SA + SB) {
         if (b_cm) load_unit_cm(r[i], B, b_cm, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb);
-        else load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb, vec_b != 0);
+        else load_unit(r[i], B, ldb, m0 + (u >> 3), me, 64 * (slab - SA) + (u & 7) * 8, nb, vec_b);
       }
     }
   };
@@ -517,7 +526,11 @@ static int dev_state(DevState** out) {
   return 0;
 }
 
-static bool vec4_ok(const void* p, int ld) { return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0); }
+// bit 0: rows are 16-byte aligned (128-bit loads); bit 1: 32-byte aligned (256-bit loads)
+static int vec4_ok(const void* p, int ld) {
+  const int v16 = ((uintptr_t)p % 16 == 0) && (ld % 4 == 0), v32 = ((uintptr_t)p % 32 == 0) && (ld % 8 == 0);
+  return v16 | (v16 && v32 ? 2 : 0);
+}
 
 }  // namespace tg
 

@@ -2,6 +2,12 @@
 // bwd_chain.cu: fused gradient chain of the training backward): tensor-memory and shared-memory maps, the barrier block,
 // bounded waits, the weight ring and the issue of one 64-wide K chunk, and the split-bf16 store helpers.
 #pragma once
+
+// Cache operator of the 256-bit activation / gradient plane stores of the training kernels (A/B knob: -DDMN_ST_COP='".cs"').
+#ifndef DMN_ST_COP
+#define DMN_ST_COP ""
+#endif
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -236,7 +242,7 @@ __device__ __forceinline__ void store_split16_tmem(const float* vals, uint32_t t
 __device__ __forceinline__ void store_row16(float* __restrict__ dst, const float* v) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+    asm volatile("st.global" DMN_ST_COP ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
                  "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
                  : "memory");
 }
@@ -262,10 +268,10 @@ __device__ __forceinline__ void store_row16_paired(float* __restrict__ dst, int6
   float* pa = even_row + (odd ? 8 : 0);                // instruction 1: the even row's 64 bytes, 32 per lane
   float* pb = odd_row + (odd ? 8 : 0);                 // instruction 2: the odd row's
   if (ok_even)
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pa), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]),
+    asm volatile("st.global" DMN_ST_COP ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pa), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]),
                  "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
   if (ok_odd)
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pb), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]),
+    asm volatile("st.global" DMN_ST_COP ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(pb), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]), "f"(b[4]),
                  "f"(b[5]), "f"(b[6]), "f"(b[7]) : "memory");
 }
 
@@ -301,7 +307,7 @@ __device__ __forceinline__ void store_row32_quad(float* __restrict__ dst, int64_
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (row_base + i < n_rows)
-      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base + (int64_t)i * row_stride), "f"(t[i][0]),
+      asm volatile("st.global" DMN_ST_COP ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base + (int64_t)i * row_stride), "f"(t[i][0]),
                    "f"(t[i][1]), "f"(t[i][2]), "f"(t[i][3]), "f"(t[i][4]), "f"(t[i][5]), "f"(t[i][6]), "f"(t[i][7]) : "memory");
 }
 
@@ -312,7 +318,7 @@ __device__ __forceinline__ void store_row32_quad(float* __restrict__ dst, int64_
 __device__ __forceinline__ void store_row32(float* __restrict__ dst, const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+    asm volatile("st.global" DMN_ST_COP ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
                  "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
                  : "memory");
 }
