@@ -262,10 +262,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) bwd_chain_kernel(const CArgs a) 
 // ------------------------------------------------------------------------------------------------ head gradients
 // d rgb_hid = mask . (d_rgb W_rgb_out), d ins_hid = mask . (d_ins W_ins_out)   (dm_nerf.py:102-103 backwards, K = 3 / ins_num+1)
 // written side by side into one [M,256] plane so that ONE dW GEMM against h7 serves both branches.
-// One thread per (row, hidden unit); the head weights live in shared memory.  The rows of d_out are staged zero-padded to a
-// multiple of 4 channels and read back as float4 broadcasts (the scalar version issued one shared-memory load per multiply-add
-// and was bound by the load unit, not by the 268 MB it writes).
-constexpr int HEAD_ROWS = 8;        // rows per iteration: one barrier pair per 8 rows
+// A warp handles 8 rows, a lane 4 adjacent hidden units of both halves (float4 weights from shared memory, float4 broadcasts of the
+// staged d_out rows, 512 contiguous bytes per warp store).  The rows of d_out are staged zero-padded to a multiple of 4
+// channels.  (The first version -- one thread per unit, one scalar shared-memory load per multiply-add -- was bound by the
+// shared-memory load unit, not by the 268 MB it writes.)
+constexpr int HEAD_ROWS = 8;        // rows per warp and iteration
+constexpr int HEAD_BLOCK_ROWS = 4 * HEAD_ROWS;
 __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict__ d_out, int C, int64_t m, const float* __restrict__ w_rgb,
                                                         const float* __restrict__ w_ins, int ins1, const uint16_t* __restrict__ bits,
                                                         float* __restrict__ s12, int rows_per_block) {
@@ -273,44 +275,64 @@ __global__ void __launch_bounds__(128) bwd_heads_kernel(const float* __restrict_
   const int ins4 = (ins1 + 3) & ~3;       // instance channels padded to a multiple of 4 (zero weights)
   const int CP = 4 + ins4;                // staged row: rgb, sigma, padded instance channels
   float* wi = sm;                         // [ins4][128]
-  float* drow = wi + ins4 * 128;          // [HEAD_ROWS][CP]
-  const int j = threadIdx.x;
-  for (int k = 0; k < ins4; ++k) wi[k * 128 + j] = (k < ins1) ? w_ins[k * 128 + j] : 0.0f;
-  const float wr0 = w_rgb[j], wr1 = w_rgb[128 + j], wr2 = w_rgb[256 + j];
+  float* drow = wi + ins4 * 128;          // [HEAD_BLOCK_ROWS][CP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = 0; k < ins4; ++k) wi[k * 128 + tid] = (k < ins1) ? w_ins[k * 128 + tid] : 0.0f;
+  const float* wl = w_rgb + 4 * lane;     // scalar loads: a parameter tensor need not be 16-byte aligned
+  const float4 wr0 = make_float4(wl[0], wl[1], wl[2], wl[3]), wr1 = make_float4(wl[128], wl[129], wl[130], wl[131]),
+               wr2 = make_float4(wl[256], wl[257], wl[258], wl[259]);
+  const float4* wi4 = reinterpret_cast<const float4*>(wi) + lane;       // + k * 32: units 4 lane .. 4 lane + 3 of channel k
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < m) ? r0 + rows_per_block : m;
-  for (int64_t row = r0; row < r1; row += HEAD_ROWS) {
-    const int nr = (int)((r1 - row < HEAD_ROWS) ? r1 - row : HEAD_ROWS);
+  for (int64_t row = r0; row < r1; row += HEAD_BLOCK_ROWS) {
+    const int nr = (int)((r1 - row < HEAD_BLOCK_ROWS) ? r1 - row : HEAD_BLOCK_ROWS);
     __syncthreads();
-    for (int i = j; i < HEAD_ROWS * CP; i += 128) {
+    for (int i = tid; i < HEAD_BLOCK_ROWS * CP; i += 128) {
       const int q = i / CP, c = i - q * CP;
       drow[i] = (q < nr && c < C) ? d_out[(row + q) * C + c] : 0.0f;
     }
     __syncthreads();
-    float a1[HEAD_ROWS], a2[HEAD_ROWS];
-    const float4* d4 = reinterpret_cast<const float4*>(drow);
+    const float4* d4 = reinterpret_cast<const float4*>(drow) + warp * HEAD_ROWS * (CP / 4);
+    float4 a1[HEAD_ROWS], a2[HEAD_ROWS];
 #pragma unroll
     for (int q = 0; q < HEAD_ROWS; ++q) {
       const float4 d = d4[q * (CP / 4)];
-      a1[q] = fmaf(d.z, wr2, fmaf(d.y, wr1, __fmul_rn(d.x, wr0)));        // same order as the scalar loop: ((0 + x w0) + y w1) + z w2
-      a2[q] = 0.0f;
+      // per unit the same order as a scalar loop over the channels: ((0 + x w0) + y w1) + z w2
+      a1[q].x = fmaf(d.z, wr2.x, fmaf(d.y, wr1.x, __fmul_rn(d.x, wr0.x)));
+      a1[q].y = fmaf(d.z, wr2.y, fmaf(d.y, wr1.y, __fmul_rn(d.x, wr0.y)));
+      a1[q].z = fmaf(d.z, wr2.z, fmaf(d.y, wr1.z, __fmul_rn(d.x, wr0.z)));
+      a1[q].w = fmaf(d.z, wr2.w, fmaf(d.y, wr1.w, __fmul_rn(d.x, wr0.w)));
+      a2[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     for (int k4 = 0; k4 < ins4 / 4; ++k4) {
-      const float w0 = wi[(4 * k4) * 128 + j], w1 = wi[(4 * k4 + 1) * 128 + j], w2 = wi[(4 * k4 + 2) * 128 + j],
-                  w3 = wi[(4 * k4 + 3) * 128 + j];
+      const float4 w0 = wi4[(4 * k4) * 32], w1 = wi4[(4 * k4 + 1) * 32], w2 = wi4[(4 * k4 + 2) * 32], w3 = wi4[(4 * k4 + 3) * 32];
 #pragma unroll
       for (int q = 0; q < HEAD_ROWS; ++q) {
         const float4 d = d4[q * (CP / 4) + 1 + k4];
-        a2[q] = fmaf(d.w, w3, fmaf(d.z, w2, fmaf(d.y, w1, fmaf(d.x, w0, a2[q]))));
+        a2[q].x = fmaf(d.w, w3.x, fmaf(d.z, w2.x, fmaf(d.y, w1.x, fmaf(d.x, w0.x, a2[q].x))));
+        a2[q].y = fmaf(d.w, w3.y, fmaf(d.z, w2.y, fmaf(d.y, w1.y, fmaf(d.x, w0.y, a2[q].y))));
+        a2[q].z = fmaf(d.w, w3.z, fmaf(d.z, w2.z, fmaf(d.y, w1.z, fmaf(d.x, w0.z, a2[q].z))));
+        a2[q].w = fmaf(d.w, w3.w, fmaf(d.z, w2.w, fmaf(d.y, w1.w, fmaf(d.x, w0.w, a2[q].w))));
       }
     }
+    const int sh = (lane & 3) * 4;          // this lane's 4 units inside their 16-unit mask group (lane >> 2)
 #pragma unroll
     for (int q = 0; q < HEAD_ROWS; ++q) {
-      if (q >= nr) break;
-      const int64_t rq = row + q;
-      const uint32_t br = bits[act_bits_index(8, j >> 4, rq, m)], bi = bits[act_bits_index(9, j >> 4, rq, m)];
-      s12[rq * 256 + j] = ((br >> (j & 15)) & 1u) ? a1[q] : 0.0f;            // one [M,256] plane: d rgb_hid | d ins_hid
-      s12[rq * 256 + 128 + j] = ((bi >> (j & 15)) & 1u) ? a2[q] : 0.0f;
+      const int lr = warp * HEAD_ROWS + q;
+      if (lr >= nr) break;
+      const int64_t rq = row + lr;
+      const uint32_t br = (uint32_t)bits[act_bits_index(8, lane >> 2, rq, m)] >> sh, bi = (uint32_t)bits[act_bits_index(9, lane >> 2, rq, m)] >> sh;
+      float4 o1 = a1[q], o2 = a2[q];
+      if (!(br & 1u)) o1.x = 0.0f;
+      if (!(br & 2u)) o1.y = 0.0f;
+      if (!(br & 4u)) o1.z = 0.0f;
+      if (!(br & 8u)) o1.w = 0.0f;
+      if (!(bi & 1u)) o2.x = 0.0f;
+      if (!(bi & 2u)) o2.y = 0.0f;
+      if (!(bi & 4u)) o2.z = 0.0f;
+      if (!(bi & 8u)) o2.w = 0.0f;
+      *reinterpret_cast<float4*>(s12 + rq * 256 + 4 * lane) = o1;               // one [M,256] plane: d rgb_hid | d ins_hid
+      *reinterpret_cast<float4*>(s12 + rq * 256 + 128 + 4 * lane) = o2;
     }
   }
 }
@@ -353,9 +375,9 @@ int launch_bwd_heads(const NetParams& p, const float* d_out, int64_t m, const ui
   if (m == 0) return 0;
   const int rows = 64;
   const int ins4 = (ins1 + 3) & ~3;
-  const size_t smem = (size_t)(ins4 * 128 + bk::HEAD_ROWS * (4 + ins4)) * sizeof(float);
+  const size_t smem = (size_t)(ins4 * 128 + bk::HEAD_BLOCK_ROWS * (4 + ins4)) * sizeof(float);
   static PerDeviceOnce once;
-  if (once.first()) DMN_CUDA(cudaFuncSetAttribute(bk::bwd_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  if (once.first()) DMN_CUDA(cudaFuncSetAttribute(bk::bwd_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   bk::bwd_heads_kernel<<<(unsigned)((m + rows - 1) / rows), 128, smem, st>>>(d_out, C, m, p.w[L_RGB_OUT], p.w[L_INS_OUT], ins1, bits, s12,
                                                                            rows);
   DMN_LAUNCH_OK();

@@ -28,7 +28,8 @@ targs = types.SimpleNamespace(perturb=1.0, N_importance=128, is_train=True, N_in
 pe, ve = get_embedder(10)[0], get_embedder(4)[0]
 zc = torch.linspace(float(wl["near"]), float(wl["far"]), 64, device=dev)[None].expand(1024, 64)
 nc.train(); nf.train()
-opt = torch.optim.Adam(list(nc.parameters()) + list(nf.parameters()), lr=5e-4)
+_adam_kw = {"fused": True} if os.environ.get("ADAM", "") == "fused" else {}      # default: torch's choice (_foreach kernels), as train_dmsr.py
+opt = torch.optim.Adam(list(nc.parameters()) + list(nf.parameters()), lr=5e-4, **_adam_kw)
 gt_rgb = torch.rand(H, W, 3, device=dev)
 gt_lab = (torch.arange(H * W, device=dev).reshape(H, W) * 7 // (H * W)).to(torch.int16)
 pose = torch.from_numpy(wl["c2w"]).to(dev)
@@ -61,6 +62,7 @@ e0.record()
 for _ in range(10):
     full_iteration()
 e1.record(); torch.cuda.synchronize()
+print("adam=%s " % os.environ.get("ADAM", "foreach (torch default)"), end="")
 print("parts=%s: %.3f ms per iteration (CUDA events, 10 iterations back to back)" % (",".join(parts), e0.elapsed_time(e1) / 10))
 host = []
 for _ in range(6):
