@@ -74,19 +74,22 @@ __global__ void composite_backward_kernel(const float* __restrict__ raw, const f
   }
   __syncwarp();
 
-  // ---- instance logits: ins_map_k = sigmoid(sum_i w_i raw_ik); weights are detached unless keep_all (manipulator_render)
-  for (int k = lane; k < C - 4; k += 32) {
+  // ---- instance logits: ins_map_k = sigmoid(sum_i w_i raw_ik); weights are detached unless keep_all (manipulator_render).
+  // Lanes run over the samples like in the other phases (the channel index is warp-uniform): every lane owns samples lane,
+  // lane + 32, ... -- no serial pass over all S samples per channel, and the keep_all term lands in gw[i] of the owning lane.
+  for (int k = 0; k < C - 4; ++k) {
     float a = 0.0f;
-    for (int i = 0; i < S; ++i) a += w[i] * rr[(size_t)i * C + 4 + k];
+    for (int i = lane; i < S; i += 32) a = fmaf(w[i], rr[(size_t)i * C + 4 + k], a);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(FULL, a, d);
     const float sk = sigmoidf_acc(a);
     const float gk = (g_ins && k < n_ins_out) ? g_ins[ray * n_ins_out + k] * sk * (1.0f - sk) : 0.0f;
-    for (int i = 0; i < S; ++i) {
+    for (int i = lane; i < S; i += 32) {
       float v = gk * w[i];
       if (accumulate) v += dr[(size_t)i * C + 4 + k];
       dr[(size_t)i * C + 4 + k] = v;
+      if (keep_all && gk != 0.0f) gw[i] += gk * rr[(size_t)i * C + 4 + k];
     }
-    if (keep_all && gk != 0.0f)
-      for (int i = 0; i < S; ++i) atomicAdd(&gw[i], gk * rr[(size_t)i * C + 4 + k]);   // shared-memory atomics
   }
   __syncwarp();
 
