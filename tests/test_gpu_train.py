@@ -319,6 +319,7 @@ def test_device_assignment_is_scipys_assignment_including_ties():
     small-integer (tie-heavy), constant and duplicate-column score matrices of every shape class: the SAME columns, not just the
     same total, because the matched channel decides where the gradient goes."""
     from scipy.optimize import linear_sum_assignment
+    from oracle import lsap
     rng = np.random.default_rng(3)
     cases = 0
     for trial in range(160):
@@ -340,6 +341,8 @@ def test_device_assignment_is_scipys_assignment_including_ties():
         want = np.full(k, -1)
         want[cols] = rows
         assert np.array_equal(got, want), (trial, k, v, kind)
+        if k <= 40:        # and the oracle's restatement of scipy's algorithm (oracle/lsap.py, order-free arg-min form)
+            assert np.array_equal(lsap.lsap_lane_parallel(c[:v])[1], cols), (trial, k, v, kind)
         np.testing.assert_allclose(losses[0], c[rows, cols].mean(), rtol=1e-6, atol=1e-7)
         assert losses[2] == 0.0
         np.testing.assert_allclose(losses[1], (k - v) / (10.0 * (k - v)) if k > v else 0.0, rtol=1e-6)

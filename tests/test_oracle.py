@@ -4,6 +4,7 @@ host BLAS may round differently, hence the small tolerances (stage-wise, teacher
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import dmnerf_oracle as O
@@ -187,3 +188,24 @@ def test_oracle_domain_properties():
         assert bool((zs[..., 1:] >= zs[..., :-1] - 1e-6).all())
         zf = torch.sort(torch.cat([z, zs], -1), -1).values
         assert float(zf.min()) >= 4.0 - 1e-5 and float(zf.max()) <= 15.0 + 1e-5
+
+
+def test_assignment_restatement_is_scipys_algorithm():
+    """oracle/lsap.py (the shortest-augmenting-path solver scipy implements; the reference calls scipy at evaluator.py:45) against
+    the installed scipy: the SAME columns on random, tie-heavy integer, constant and duplicate-column matrices -- for the
+    column-by-column form and for the order-free arg-min form the device kernel uses."""
+    from scipy.optimize import linear_sum_assignment
+    from oracle import lsap
+    n = 0
+    for c in lsap.tie_heavy_cases(400, 24, seed=7):
+        rows, cols = linear_sum_assignment(c)
+        r1, c1 = lsap.lsap_sequential(c)
+        r2, c2 = lsap.lsap_lane_parallel(c)
+        assert np.array_equal(r1, rows) and np.array_equal(c1, cols), c.shape
+        assert np.array_equal(c2, cols), c.shape
+        n += 1
+    assert n == 400
+    big = next(iter(lsap.tie_heavy_cases(1, 94, seed=11)))
+    assert np.array_equal(lsap.lsap_lane_parallel(big)[1], linear_sum_assignment(big)[1])
+    with pytest.raises(ValueError):
+        lsap.lsap_sequential(np.full((2, 2), np.inf))
