@@ -187,3 +187,37 @@ def test_hungarian_host_logic_matches_the_oracle():
     # and the oracle's ins_criterion runs on the same tiny case (sanity of the fixture generator's path)
     pred = torch.sigmoid(torch.randn(5, 9, generator=gen))
     assert np.isfinite(float(O.ins_criterion(pred, lab.float(), 9)[0].sum()))
+
+
+def test_shipped_library_hot_kernels_are_tcgen05_code():
+    """cuobjdump -sass of the built library (no GPU needed): the network, gradient-chain and weight-gradient kernels issue
+    tcgen05.mma (UTCHMMA) with tensor-memory loads (LDTM); the persistent kernels stream their weights with the bulk-copy engine
+    (UBLKCP); no legacy mma.sync (HMMA) anywhere.  The counts are committed in profiles/r02_sass_histogram.txt."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    path = os.path.join(ROOT, "dm-nerf_b200", "lib", "libdmnerf_b200.so")
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    per, cur = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = per.setdefault(m.group(1), {"UTCHMMA": 0, "LDTM": 0, "STTM": 0, "UBLKCP": 0, "HMMA": 0})
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur is not None and m.group(1) in cur:
+            cur[m.group(1)] += 1
+    assert per, "no kernels found in the library"
+    assert sum(c["HMMA"] for c in per.values()) == 0
+    hot = {"mlp_umma_kernel": 2, "bwd_chain_kernel": 1, "gemm_tn_tc_kernel": 4, "gemm_nn_tc_kernel": 3}
+    for name, n_inst in hot.items():
+        ks = [c for k, c in per.items() if name in k]
+        assert len(ks) == n_inst, (name, len(ks))
+        for c in ks:
+            assert c["UTCHMMA"] > 0 and c["LDTM"] > 0, (name, c)
+    for name in ("mlp_umma_kernel", "bwd_chain_kernel"):
+        for k, c in per.items():
+            if name in k:
+                assert c["UBLKCP"] > 0 and c["STTM"] > 0, (name, c)
